@@ -1,0 +1,159 @@
+/*
+ * pmpc_b200 — C ABI of the B200-native particle-SCP MPC solver.
+ *
+ * This library is the drop-in for the ONE native boundary of StanfordASL/pmpc's solve path:
+ * the `pmpcjl` extension (reference `PMPC.jl/pmpcjl/module.cpp:9-23`) which forwards raw
+ * `double*` to the ahead-of-time compiled Julia entry points `c_lqp_solve` / `c_lcone_solve`
+ * (reference `PMPC.jl/src/c_interface.jl:77-141`, `:146-214`).  Plain pointers and sizes, no
+ * torch / numpy types.  All computation runs in hand-written sm_100a CUDA kernels; there is no
+ * CPU fallback: every entry point returns an error (or NaN-fills the outputs for the two
+ * void-returning compat symbols, the reference's own failure convention,
+ * `PMPC.jl/src/osqp_solver.jl:69-71`) when no CUDA device is usable.
+ *
+ * ARRAY LAYOUT (identical to the reference C ABI, `c_interface.jl:28-46`): column-major
+ *     x0(n,M) f(n,N,M) fx(n,n,N,M) fu(n,m,N,M) X_prev(n,N,M) U_prev(m,N,M) Q(n,n,N,M)
+ *     R(m,m,N,M) X_ref(n,N,M) U_ref(m,N,M) lx,ux(n,N,M) lu,uu(m,N,M)
+ *     slew_reg(M) slew_reg0(M) slew_um1(m,M);  outputs X(n,N,M) (WITHOUT x0), U(m,N,M).
+ * i.e. NumPy C-order (M,N,n) vectors and (M,N,cols,rows) matrices.  For the batched handle API a
+ * leading problem dimension B is simply more particles: index g = b*M + i.
+ *
+ * OPTIONAL ARGUMENTS use the reference's NaN sentinels (`c_interface.jl:56-70`): any NaN in
+ * lx|ux disables the state box, in lu|uu the control box, in slew_reg the slew penalty, in
+ * slew_reg0|slew_um1 the u_{-1} term.  The handle API additionally accepts NULL for "absent".
+ * Nc < 0 means Nc = N (`main.jl:127-128`).
+ */
+#ifndef PMPC_B200_H
+#define PMPC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Byte-compatible replacements of the reference entry points
+ *    (prototype copied in meaning from `PMPC.jl/pmpcjl/module.cpp:9-23`).
+ *    Host pointers in, host pointers out; caller owns every buffer; no pointer is retained.
+ *    On failure X_out/U_out are NaN-filled (reference convention, `scp_mpc.py:391-394`).
+ * ------------------------------------------------------------------------------------------ */
+void c_lqp_solve(double *X_out, double *U_out, size_t xdim, size_t udim, size_t N, size_t M,
+                 long long Nc, double *x0, double *f, double *fx, double *fu, double *X_prev,
+                 double *U_prev, double *Q, double *R, double *X_ref, double *U_ref, double *lx,
+                 double *ux, double *lu, double *uu, double reg_x, double reg_u, double *slew_reg,
+                 double *slew_reg0, double *slew_um1, long long verbose);
+
+/* Cone route (`c_interface.jl:146-214`).  Served only where its minimiser coincides with the
+ * QP's: M == 1 (or Nc-coupled particles with identical costs are NOT assumed), hard constraints
+ * (smooth_alpha NaN).  Otherwise outputs are NaN-filled — see DESIGN.md "out of scope". */
+void c_lcone_solve(double *X_out, double *U_out, size_t xdim, size_t udim, size_t N, size_t M,
+                   long long Nc, double *x0, double *f, double *fx, double *fu, double *X_prev,
+                   double *U_prev, double *Q, double *R, double *X_ref, double *U_ref, double *lx,
+                   double *ux, double *lu, double *uu, double reg_x, double reg_u,
+                   double *slew_reg, double *slew_reg0, double *slew_um1, long long verbose,
+                   double smooth_alpha, char *solver);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Handle API (the fast path): problem data stays resident in HBM, the whole SCP loop of
+ *    `pmpc/scp_mpc.py:337-428` runs on the device for built-in dynamics.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pmpc_handle_s *pmpc_handle_t;
+
+enum {
+  PMPC_OK = 0,
+  PMPC_ERR_NO_DEVICE = 1,   /* no usable CUDA device / driver */
+  PMPC_ERR_BAD_ARG = 2,
+  PMPC_ERR_UNSUPPORTED = 3, /* dimensions outside the compiled kernel table */
+  PMPC_ERR_CUDA = 4,
+  PMPC_ERR_STATE = 5        /* call order (e.g. solve before data was set) */
+};
+
+enum { PMPC_DYN_AFFINE = 0, /* f,fx,fu supplied by the caller (pmpc_set_linearization) or LTV */
+       PMPC_DYN_DUBINS = 1  /* reference `tests/dubins_car.py:48-90`, params (v_scale,w_scale,T) */ };
+
+typedef struct {
+  double rho0;         /* initial ADMM penalty                         (default 1.0)   */
+  double alpha;        /* ADMM over-relaxation                          (1.6)          */
+  double eps_abs;      /* ADMM primal/dual residual tolerances          (1e-9)         */
+  double eps_rel;      /*                                               (1e-9)         */
+  double kkt_tol;      /* relative KKT tolerance accepted from a polish (1e-9)         */
+  double adapt_tol;    /* refactor when the rho estimate moves by this factor (3.0)    */
+  int max_admm_iter;   /* per QP                                        (4000)         */
+  int check_every;     /* ADMM iterations between residual checks       (10)           */
+  int polish;          /* active-set (masked Riccati) polish on/off     (1)            */
+  int polish_iters;    /* primal-dual active-set refinements / attempt  (8)            */
+  int adapt_rho;       /*                                               (1)            */
+  int warm_start;      /* carry (w,y,active set) across SCP iterations  (1)            */
+} pmpc_settings;
+
+void pmpc_default_settings(pmpc_settings *s);
+const char *pmpc_last_error(void);
+const char *pmpc_version(void);
+int pmpc_device_count(void);
+
+/* B independent problems of M particles each (N stages, xdim states, udim controls, Nc shared
+ * leading controls).  device < 0 selects the current device. */
+int pmpc_create(pmpc_handle_t *h, int device, size_t B, size_t M, size_t N, size_t xdim,
+                size_t udim, long long Nc);
+int pmpc_destroy(pmpc_handle_t h);
+int pmpc_set_settings(pmpc_handle_t h, const pmpc_settings *s);
+
+/* Cost / constraints / start (host pointers, reference layout with leading B).  Any of
+ * lx,ux,lu,uu,slew_* may be NULL or NaN (absent).  X_ref/U_ref NULL = zeros. */
+int pmpc_set_problem(pmpc_handle_t h, const double *x0, const double *Q, const double *R,
+                     const double *X_ref, const double *U_ref, const double *lx, const double *ux,
+                     const double *lu, const double *uu, double reg_x, double reg_u,
+                     const double *slew_reg, const double *slew_reg0, const double *slew_um1);
+/* Warm start X_prev (n,N,B*M), U_prev (m,N,B*M); NULL = zeros.  Also resets the ADMM state. */
+int pmpc_set_warm_start(pmpc_handle_t h, const double *X_prev, const double *U_prev);
+
+/* Built-in device dynamics.  params: (nparam, B*M) column-major; DUBINS nparam = 3
+ * (v_scale, w_scale, T), `eps` is the +-eps control offset (reference 1e-6). */
+int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double *params, size_t nparam, double eps);
+/* Caller-supplied linearisation about (X_prev, U_prev) — the host-callable path that keeps
+ * arbitrary Python `f_fx_fu_fn` working (`scp_mpc.py:338-342`).  Sets kind = AFFINE. */
+int pmpc_set_linearization(pmpc_handle_t h, const double *f, const double *fx, const double *fu);
+/* LTV system x+ = A_j x + B_j u + c_j given once (fx = A, fu = B, c may be NULL). */
+int pmpc_set_ltv(pmpc_handle_t h, const double *A, const double *Bm, const double *c);
+
+/* Linearise only (built-in dynamics) about the handle's (X_prev, U_prev); results readable with
+ * pmpc_get_linearization in reference layout. */
+int pmpc_linearize(pmpc_handle_t h);
+int pmpc_get_linearization(pmpc_handle_t h, double *f, double *fx, double *fu);
+
+/* One convex sub-problem at the current linearisation (= one `aff_solve`, scp_mpc.py:370),
+ * followed by the SCP bookkeeping of scp_mpc.py:397-407 (X_prev <- X unless keep_prev). */
+int pmpc_qp_solve(pmpc_handle_t h, int keep_prev);
+/* Whole SCP loop on the device (built-in dynamics or LTV): up to max_it iterations, stop when
+ * max_res < res_tol (scp_mpc.py:424).  Asynchronous on the handle's stream; pmpc_sync waits. */
+int pmpc_scp_solve(pmpc_handle_t h, int max_it, double res_tol);
+int pmpc_scp_solve_async(pmpc_handle_t h, int max_it, double res_tol);
+int pmpc_sync(pmpc_handle_t h);
+
+/* Results.  X (n,N,B*M) without x0, U (m,N,B*M). */
+int pmpc_get_solution(pmpc_handle_t h, double *X, double *U);
+/* Per problem b: info[b*8 + k], k = 0 scp_iters, 1 total ADMM iterations, 2 factorisations,
+ * 3 polish passes, 4 status (0 ok, 1 NaN failure, 2 ADMM hit max_iter in some QP),
+ * 5 QPs finished by polish, 6 QPs finished by ADMM tolerance, 7 reserved. */
+int pmpc_get_info(pmpc_handle_t h, long long *info);
+/* hist (4, max_it, B): obj, resid, admm_iters(it), kkt_violation of the accepted QP solution. */
+int pmpc_get_hist(pmpc_handle_t h, double *hist, int max_it);
+
+/* Device-time of the last solve kernel in milliseconds (CUDA events on the handle stream). */
+int pmpc_last_kernel_ms(pmpc_handle_t h, float *ms);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. int-returning variant of the compat entry with explicit settings and statistics.
+ * ------------------------------------------------------------------------------------------ */
+int pmpc_lqp_solve(double *X_out, double *U_out, size_t xdim, size_t udim, size_t N, size_t M,
+                   long long Nc, const double *x0, const double *f, const double *fx,
+                   const double *fu, const double *X_prev, const double *U_prev, const double *Q,
+                   const double *R, const double *X_ref, const double *U_ref, const double *lx,
+                   const double *ux, const double *lu, const double *uu, double reg_x,
+                   double reg_u, const double *slew_reg, const double *slew_reg0,
+                   const double *slew_um1, const pmpc_settings *settings, long long *info8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMPC_B200_H */

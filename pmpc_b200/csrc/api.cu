@@ -1,0 +1,733 @@
+// C ABI of libpmpc_b200.so: handle management, layout packing kernels, kernel dispatch and the
+// byte-compatible `c_lqp_solve` / `c_lcone_solve` entry points (see include/pmpc_b200.h).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/pmpc_b200.h"
+#include "kernels.cuh"
+
+using namespace pmpc;
+
+namespace pmpc {
+template <> cudaError_t launch_scp<2, 1>(const DevProb&, cudaStream_t);
+template <> cudaError_t launch_scp<4, 2>(const DevProb&, cudaStream_t);
+template <> cudaError_t launch_scp<8, 4>(const DevProb&, cudaStream_t);
+template <> cudaError_t launch_scp<12, 4>(const DevProb&, cudaStream_t);
+template <> cudaError_t launch_scp<16, 8>(const DevProb&, cudaStream_t);
+template <> cudaError_t launch_scp<32, 8>(const DevProb&, cudaStream_t);
+}  // namespace pmpc
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(PMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+struct Shape { int NX, NU; };
+static const Shape kShapes[] = {{2, 1}, {4, 2}, {8, 4}, {12, 4}, {16, 8}, {32, 8}};
+
+static bool pick_shape(int n, int m, Shape* out) {
+  for (const Shape& s : kShapes)
+    if (s.NX >= n && s.NU >= m) { *out = s; return true; }
+  return false;
+}
+
+struct pmpc_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevProb pb{};
+  Shape shape{};
+  long long Nc_orig = 0;
+  size_t Ptot = 0;            // B*M
+  void* slab = nullptr;       // all device arrays
+  size_t slab_bytes = 0;
+  double* stage = nullptr;    // device staging for raw (reference-layout) inputs / outputs
+  size_t stage_doubles = 0;
+  double *lin_f = nullptr, *lin_fx = nullptr, *lin_fu = nullptr;  // reference-layout linearisation
+  bool have_problem = false, have_dyn = false, solved = false;
+  pmpc_settings settings{};
+  float last_ms = 0.f;
+};
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels: reference layout (particle-major, column-major blocks) -> SoA [j][e][P]
+// one thread per (g, j); g fastest so the SoA stores are coalesced.
+__global__ void pack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, int N,
+                                int Ei, int Eo, double fill) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Ptot * N) return;
+  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  for (int e = 0; e < Eo; ++e) {
+    double v = fill;
+    if (in != nullptr && e < Ei) v = in[((size_t)g * N + j) * Ei + e];
+    out[((size_t)j * Eo + e) * P + g] = v;
+  }
+}
+
+__global__ void unpack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, int N,
+                                  int Ei, int Eo) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)Ptot * N) return;
+  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  for (int e = 0; e < Eo; ++e) out[((size_t)g * N + j) * Eo + e] = in[((size_t)j * Ei + e) * P + g];
+}
+
+__global__ void pack_particle_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, int Ei,
+                                     int Eo, double fill) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Ptot) return;
+  for (int e = 0; e < Eo; ++e) out[(size_t)e * P + g] = (in != nullptr && e < Ei) ? in[(size_t)g * Ei + e] : fill;
+}
+
+// cost terms (lqp_utils.jl:26-40, 130-142, 164-214): Qs = triu(Q) mirrored + reg_x I, etc.
+__global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __restrict__ Q, const double* __restrict__ R,
+                                 const double* __restrict__ Xref, const double* __restrict__ Uref,
+                                 const double* __restrict__ s, const double* __restrict__ s0,
+                                 const double* __restrict__ um1, int Ptot, int quirk_keep_um1) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = pb.N, n = pb.n, m = pb.m;
+  if (idx >= (size_t)Ptot * N) return;
+  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const size_t P = pb.P;
+  const double* Qb = Q + ((size_t)g * N + j) * n * n;  // column-major: Q[r,t] = Qb[t*n + r]
+  const double* Rb = R + ((size_t)g * N + j) * m * m;
+  const double* xr = Xref ? Xref + ((size_t)g * N + j) * n : nullptr;
+  const double* ur = Uref ? Uref + ((size_t)g * N + j) * m : nullptr;
+  const int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2;
+  for (int r = 0; r < NX; ++r) {
+    for (int t = r; t < NX; ++t) {
+      double v = (r < n && t < n) ? Qb[(size_t)t * n + r] : 0.0;
+      if (r == t) v += (r < n) ? pb.reg_x : 1.0;
+      pb.Qs[((size_t)j * NQ + pk(r, t, NX)) * P + g] = v;
+    }
+    double acc = 0.0;
+    if (r < n && xr)
+      for (int t = 0; t < n; ++t) acc += Qb[(size_t)t * n + r] * xr[t];
+    pb.qref[((size_t)j * NX + r) * P + g] = acc;
+    pb.xref[((size_t)j * NX + r) * P + g] = (r < n && xr) ? xr[r] : 0.0;
+  }
+  const double sv = s ? s[g] : 0.0, s0v = s0 ? s0[g] : 0.0;
+  const double extra = (j == 0 ? s0v : 0.0) + ((N == 1 && j == 0) ? sv : 0.0);  // lqp_utils.jl:31-37
+  for (int a = 0; a < NU; ++a) {
+    for (int b = a; b < NU; ++b) {
+      double v = (a < m && b < m) ? Rb[(size_t)b * m + a] : 0.0;
+      if (a == b) v += (a < m) ? (pb.reg_u + extra) : 1.0;
+      pb.Rs[((size_t)j * NR + pk(a, b, NU)) * P + g] = v;
+    }
+    double acc = 0.0;
+    if (a < m && ur)
+      for (int t = 0; t < m; ++t) acc += Rb[(size_t)t * m + a] * ur[t];
+    if (a < m && j == 0 && quirk_keep_um1 && um1) acc += s0v * um1[(size_t)g * m + a];  // lqp_utils.jl:165
+    pb.rref[((size_t)j * NU + a) * P + g] = acc;
+    pb.uref[((size_t)j * NU + a) * P + g] = (a < m && ur) ? ur[a] : 0.0;
+  }
+  if (j == 0) {
+    pb.slew[g] = sv;
+    pb.rdiag0[g] = extra;
+  }
+}
+
+// caller-supplied linearisation -> A, B, c   (lqp_utils.jl:231-300: c_j = f_j - fu_j ubar_j - fx_j xbar_{j-1})
+__global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __restrict__ f, const double* __restrict__ fx,
+                                const double* __restrict__ fu, int Ptot, int c_is_f) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = pb.N, n = pb.n, m = pb.m;
+  if (idx >= (size_t)Ptot * N) return;
+  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const size_t P = pb.P;
+  const double* fxb = fx + ((size_t)g * N + j) * n * n;  // fx[r,t] = fxb[t*n + r]
+  const double* fub = fu + ((size_t)g * N + j) * n * m;  // fu[r,t] = fub[t*n + r]
+  const double* fb = f ? f + ((size_t)g * N + j) * n : nullptr;
+  for (int r = 0; r < NX; ++r) {
+    double cv = (r < n && fb) ? fb[r] : 0.0;
+    for (int t = 0; t < NX; ++t) {
+      const double a = (r < n && t < n && j >= 1) ? fxb[(size_t)t * n + r] : 0.0;
+      pb.A[((size_t)j * NX * NX + r * NX + t) * P + g] = a;
+      if (!c_is_f && j >= 1) cv -= a * pb.Xp[((size_t)(j - 1) * NX + t) * P + g];
+    }
+    for (int t = 0; t < NU; ++t) {
+      const double b = (r < n && t < m) ? fub[(size_t)t * n + r] : 0.0;
+      pb.Bm[((size_t)j * NX * NU + r * NU + t) * P + g] = b;
+      if (!c_is_f) cv -= b * pb.Up[((size_t)j * NU + t) * P + g];
+    }
+    pb.c[((size_t)j * NX + r) * P + g] = cv;
+  }
+}
+
+// K1 stand-alone: Dubins f, fx, fu at (X_ = [x0, X_prev[:-1]], U_prev) in reference layout
+__global__ void linearize_dubins_kernel(DevProb pb, double* __restrict__ f, double* __restrict__ fx,
+                                        double* __restrict__ fu, int Ptot) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = pb.N;
+  if (idx >= (size_t)Ptot * N) return;
+  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const size_t P = pb.P;
+  double x[4], u[2], fo[4], fxo[16], fuo[8];
+  for (int e = 0; e < 4; ++e) x[e] = (j == 0) ? pb.x0[(size_t)e * P + g] : pb.Xp[((size_t)(j - 1) * 4 + e) * P + g];
+  for (int e = 0; e < 2; ++e) u[e] = pb.Up[((size_t)j * 2 + e) * P + g];
+  dubins_f_fx_fu(x, u, pb.dynp[g], pb.dynp[P + g], pb.dynp[2 * P + g], pb.dyn_eps, fo, fxo, fuo);
+  for (int r = 0; r < 4; ++r) {
+    f[((size_t)g * N + j) * 4 + r] = fo[r];
+    for (int t = 0; t < 4; ++t) fx[((size_t)g * N + j) * 16 + t * 4 + r] = fxo[r * 4 + t];
+    for (int t = 0; t < 2; ++t) fu[((size_t)g * N + j) * 8 + t * 4 + r] = fuo[r * 2 + t];
+  }
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int nblk(size_t n, int t = 256) { return (int)((n + t - 1) / t); }
+
+static bool has_nan(const double* p, size_t n) {
+  if (!p) return true;
+  for (size_t i = 0; i < n; ++i)
+    if (p[i] != p[i]) return true;
+  return false;
+}
+
+extern "C" {
+
+void pmpc_default_settings(pmpc_settings* s) {
+  s->rho0 = 1.0;
+  s->alpha = 1.6;
+  s->eps_abs = 1e-9;
+  s->eps_rel = 1e-9;
+  s->kkt_tol = 1e-9;
+  s->adapt_tol = 3.0;
+  s->max_admm_iter = 4000;
+  s->check_every = 10;
+  s->polish = 1;
+  s->polish_iters = 8;
+  s->adapt_rho = 1;
+  s->warm_start = 1;
+}
+
+const char* pmpc_last_error(void) { return g_err.c_str(); }
+const char* pmpc_version(void) { return "pmpc_b200 0.1.0 (sm_100a)"; }
+
+int pmpc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static void apply_settings(pmpc_handle_t h) {
+  const pmpc_settings& s = h->settings;
+  DevProb& pb = h->pb;
+  pb.rho0 = s.rho0; pb.alpha = s.alpha; pb.eps_abs = s.eps_abs; pb.eps_rel = s.eps_rel;
+  pb.kkt_tol = s.kkt_tol; pb.adapt_tol = s.adapt_tol; pb.max_admm_iter = s.max_admm_iter;
+  pb.check_every = s.check_every < 1 ? 1 : s.check_every; pb.polish = s.polish;
+  pb.polish_iters = s.polish_iters < 1 ? 1 : s.polish_iters; pb.adapt_rho = s.adapt_rho;
+  pb.warm_start = s.warm_start;
+}
+
+int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, size_t xdim, size_t udim,
+                long long Nc) {
+  if (!out || B < 1 || M < 1 || N < 1 || xdim < 1 || udim < 1) return fail(PMPC_ERR_BAD_ARG, "bad sizes");
+  if (pmpc_device_count() < 1)
+    return fail(PMPC_ERR_NO_DEVICE, "no CUDA device: pmpc_b200 has no CPU fallback");
+  Shape sh;
+  if (!pick_shape((int)xdim, (int)udim, &sh))
+    return fail(PMPC_ERR_UNSUPPORTED, "xdim/udim outside the compiled kernel table (max 32/8)");
+  if (M > 1024) return fail(PMPC_ERR_UNSUPPORTED, "M > 1024 particles per problem per GPU: shard the particles");
+  if (Nc < 0 || Nc > (long long)N) Nc = (long long)N;  // main.jl:127-128
+  pmpc_handle_s* h = new pmpc_handle_s();
+  if (device >= 0) {
+    CU(cudaSetDevice(device));
+    h->device = device;
+  } else {
+    CU(cudaGetDevice(&h->device));
+  }
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  h->shape = sh;
+  h->Nc_orig = Nc;
+  h->Ptot = B * M;
+  DevProb& pb = h->pb;
+  pb.B = (int)B; pb.M = (int)M; pb.N = (int)N; pb.n = (int)xdim; pb.m = (int)udim;
+  pb.Nc = (M == 1) ? 0 : (int)Nc;  // one particle: consensus is vacuous (the Nc==0 quirk is applied at pack time)
+  pb.D = pb.Nc * sh.NU;
+  pb.P = (int)(((h->Ptot + 31) / 32) * 32);
+  pb.hist_len = 128;
+  pmpc_default_settings(&h->settings);
+  apply_settings(h);
+  // ---- carve one slab
+  const size_t P = pb.P, NX = sh.NX, NU = sh.NU, NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2, Nn = N;
+  const int T = (int)(((M + 31) / 32) * 32);
+  const size_t D = pb.D;
+  size_t cols = D < 8 ? D : 8;
+  pb.scratch_stride = std::max<size_t>(D * D, (size_t)T * std::max<size_t>(D * cols, (size_t)ST_COUNT));
+  std::vector<std::pair<double**, size_t>> req;
+  auto want = [&](double** p, size_t cnt) { req.push_back({p, cnt}); };
+  want(&pb.Qs, Nn * NQ * P); want(&pb.Rs, Nn * NR * P); want(&pb.qref, Nn * NX * P); want(&pb.rref, Nn * NU * P);
+  want(&pb.xref, Nn * NX * P); want(&pb.uref, Nn * NU * P);
+  want(&pb.lu, Nn * NU * P); want(&pb.uu, Nn * NU * P); want(&pb.lx, Nn * NX * P); want(&pb.ux, Nn * NX * P);
+  want(&pb.x0, NX * P); want(&pb.slew, P); want(&pb.dynp, 4 * P); want(&pb.rdiag0, P);
+  want(&pb.Xp, Nn * NX * P); want(&pb.Up, Nn * NU * P); want(&pb.A, Nn * NX * NX * P); want(&pb.Bm, Nn * NX * NU * P);
+  want(&pb.c, Nn * NX * P); want(&pb.q, Nn * NX * P); want(&pb.r, Nn * NU * P);
+  for (int k = 0; k < 2; ++k) {
+    FactorSet& F = pb.fs[k];
+    want(&F.K, Nn * NU * NX * P); want(&F.E, Nn * NR * P); want(&F.d, Nn * NX * P); want(&F.e, Nn * NU * P);
+    want(&F.Pc, NX * NX * P); want(&F.Wc, NX * NU * P); want(&F.Zc, NU * NU * P);
+    want(&F.Hc, B * D * D + 1); want(&F.Hci, B * D * D + 1); want(&F.hb, B * D + 1);
+  }
+  want(&pb.kff, Nn * NU * P); want(&pb.X, Nn * NX * P); want(&pb.U, Nn * NU * P);
+  want(&pb.wu, Nn * NU * P); want(&pb.yu, Nn * NU * P); want(&pb.wx, Nn * NX * P); want(&pb.yx, Nn * NX * P);
+  want(&pb.gc, B * D + 1); want(&pb.uc, B * D + 1); want(&pb.muc, B * D + 1);
+  want(&pb.scratch, B * pb.scratch_stride);
+  want(&pb.hist, (size_t)4 * pb.hist_len * B); want(&pb.rho, B);
+  size_t total = 0;
+  for (auto& r : req) total += (r.second + 31) / 32 * 32;
+  const size_t act_bytes = 2 * (Nn * NU * P) + 2 * (B * D + 32) + 64;
+  const size_t info_bytes = 8 * B * sizeof(long long);
+  h->slab_bytes = total * sizeof(double) + act_bytes + info_bytes + 256;
+  cudaError_t e = cudaMalloc(&h->slab, h->slab_bytes);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(PMPC_ERR_CUDA, std::string("cudaMalloc slab: ") + cudaGetErrorString(e));
+  }
+  CU(cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
+  double* cur = (double*)h->slab;
+  for (auto& r : req) {
+    *r.first = cur;
+    cur += (r.second + 31) / 32 * 32;
+  }
+  pb.info = (long long*)cur;
+  signed char* ac = (signed char*)(pb.info + 8 * B);
+  pb.act = ac; ac += Nn * NU * P;
+  pb.actn = ac; ac += Nn * NU * P;
+  pb.actc = ac; ac += B * D + 32;
+  pb.actcn = ac;
+  // staging: the largest raw input is Q or fx: Ptot*N*n*n doubles (+ room for X/U outputs)
+  h->stage_doubles = h->Ptot * N * std::max<size_t>(xdim * xdim, xdim * udim + xdim + 16);
+  CU(cudaMalloc(&h->stage, h->stage_doubles * sizeof(double)));
+  CU(cudaMalloc(&h->lin_f, h->Ptot * N * xdim * sizeof(double)));
+  CU(cudaMalloc(&h->lin_fx, h->Ptot * N * xdim * xdim * sizeof(double)));
+  CU(cudaMalloc(&h->lin_fu, h->Ptot * N * xdim * udim * sizeof(double)));
+  fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);
+  CU(cudaGetLastError());
+  *out = h;
+  return PMPC_OK;
+}
+
+int pmpc_destroy(pmpc_handle_t h) {
+  if (!h) return PMPC_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return PMPC_OK;
+}
+
+int pmpc_set_settings(pmpc_handle_t h, const pmpc_settings* s) {
+  if (!h || !s) return fail(PMPC_ERR_BAD_ARG, "null");
+  h->settings = *s;
+  apply_settings(h);
+  CU(cudaSetDevice(h->device));
+  fill_kernel<<<nblk(h->pb.B), 256, 0, h->stream>>>(h->pb.rho, h->pb.B, h->pb.rho0);
+  CU(cudaGetLastError());
+  return PMPC_OK;
+}
+
+// upload `cnt` doubles into the staging buffer at offset `off` (returns device pointer)
+static int upload(pmpc_handle_t h, const double* src, size_t cnt, size_t off, double** dst) {
+  if (off + cnt > h->stage_doubles) return fail(PMPC_ERR_BAD_ARG, "staging overflow");
+  *dst = h->stage + off;
+  CU(cudaMemcpyAsync(*dst, src, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return PMPC_OK;
+}
+
+static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, int Eo, double fill) {
+  const DevProb& pb = h->pb;
+  double* dev = nullptr;
+  if (host) {
+    int rc = upload(h, host, h->Ptot * pb.N * Ei, 0, &dev);
+    if (rc) return rc;
+  }
+  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, pb.P, pb.N, Ei, Eo, fill);
+  CU(cudaGetLastError());
+  if (host) CU(cudaStreamSynchronize(h->stream));  // staging buffer is reused by the next upload
+  return PMPC_OK;
+}
+
+int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const double* R, const double* X_ref,
+                     const double* U_ref, const double* lx, const double* ux, const double* lu, const double* uu,
+                     double reg_x, double reg_u, const double* slew_reg, const double* slew_reg0,
+                     const double* slew_um1) {
+  if (!h || !x0 || !Q || !R) return fail(PMPC_ERR_BAD_ARG, "x0, Q, R are required");
+  CU(cudaSetDevice(h->device));
+  DevProb& pb = h->pb;
+  const int n = pb.n, m = pb.m, N = pb.N, NX = h->shape.NX, NU = h->shape.NU;
+  const size_t Pt = h->Ptot;
+  // NaN sentinels (c_interface.jl:56-70)
+  const bool xbox = !(has_nan(lx, Pt * N * n) || has_nan(ux, Pt * N * n));
+  const bool ubox = !(has_nan(lu, Pt * N * m) || has_nan(uu, Pt * N * m));
+  const bool slew = !has_nan(slew_reg, Pt);
+  const bool slew0 = !(has_nan(slew_reg0, Pt) || has_nan(slew_um1, Pt * m));
+  pb.has_xbox = xbox; pb.has_ubox = ubox;
+  pb.reg_x = reg_x; pb.reg_u = reg_u;
+  bool any_slew = false;
+  if (slew) for (size_t i = 0; i < Pt; ++i) any_slew |= (slew_reg[i] != 0.0);
+  pb.has_slew = any_slew;
+  // stage raw inputs: [Q | R | Xref | Uref | s | s0 | um1]
+  size_t off = 0;
+  double *dQ, *dR, *dXr = nullptr, *dUr = nullptr, *ds = nullptr, *ds0 = nullptr, *dum1 = nullptr;
+  int rc;
+  if ((rc = upload(h, Q, Pt * N * n * n, off, &dQ))) return rc;
+  off += Pt * N * n * n;
+  // R, refs and slew vectors are small next to Q; they go to a second allocation-free region only
+  // if they fit, otherwise they are packed in separate rounds.
+  const size_t rest = Pt * N * (m * m + n + m) + Pt * (2 + m);
+  std::vector<double> dummy;
+  double* extra = nullptr;
+  CU(cudaMallocAsync((void**)&extra, rest * sizeof(double), h->stream));
+  size_t eo = 0;
+  auto up2 = [&](const double* src, size_t cnt, double** dst) -> int {
+    *dst = extra + eo;
+    eo += cnt;
+    cudaError_t e = cudaMemcpyAsync(*dst, src, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    return e == cudaSuccess ? 0 : fail(PMPC_ERR_CUDA, cudaGetErrorString(e));
+  };
+  if ((rc = up2(R, Pt * N * m * m, &dR))) return rc;
+  if (X_ref && (rc = up2(X_ref, Pt * N * n, &dXr))) return rc;
+  if (U_ref && (rc = up2(U_ref, Pt * N * m, &dUr))) return rc;
+  if (slew && (rc = up2(slew_reg, Pt, &ds))) return rc;
+  if (slew0 && (rc = up2(slew_reg0, Pt, &ds0))) return rc;
+  if (slew0 && (rc = up2(slew_um1, Pt * m, &dum1))) return rc;
+  pack_cost_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, dQ, dR, dXr, dUr, ds, ds0, dum1, (int)Pt,
+                                                         h->Nc_orig >= 1 ? 1 : 0);
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(extra, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(nullptr, pb.x0, (int)Pt, pb.P, 0, NX, 0.0);
+  {
+    double* d;
+    if ((rc = upload(h, x0, Pt * n, 0, &d))) return rc;
+    pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(d, pb.x0, (int)Pt, pb.P, n, NX, 0.0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  const double inf = INFINITY;
+  if ((rc = pack_vec(h, ubox ? lu : nullptr, pb.lu, m, NU, -inf))) return rc;
+  if ((rc = pack_vec(h, ubox ? uu : nullptr, pb.uu, m, NU, inf))) return rc;
+  if ((rc = pack_vec(h, xbox ? lx : nullptr, pb.lx, n, NX, -inf))) return rc;
+  if ((rc = pack_vec(h, xbox ? ux : nullptr, pb.ux, n, NX, inf))) return rc;
+  h->have_problem = true;
+  return pmpc_set_warm_start(h, nullptr, nullptr);
+}
+
+int pmpc_set_warm_start(pmpc_handle_t h, const double* X_prev, const double* U_prev) {
+  if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  DevProb& pb = h->pb;
+  int rc;
+  if ((rc = pack_vec(h, X_prev, pb.Xp, pb.n, h->shape.NX, 0.0))) return rc;
+  if ((rc = pack_vec(h, U_prev, pb.Up, pb.m, h->shape.NU, 0.0))) return rc;
+  // reset ADMM / active-set state
+  const size_t P = pb.P, N = pb.N, NX = h->shape.NX, NU = h->shape.NU;
+  CU(cudaMemsetAsync(pb.wu, 0, N * NU * P * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(pb.yu, 0, N * NU * P * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(pb.wx, 0, N * NX * P * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(pb.yx, 0, N * NX * P * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(pb.act, 0, N * NU * P, h->stream));
+  CU(cudaMemsetAsync(pb.actn, 0, N * NU * P, h->stream));
+  CU(cudaMemsetAsync(pb.actc, 0, (size_t)pb.B * pb.D + 32, h->stream));
+  CU(cudaMemsetAsync(pb.actcn, 0, (size_t)pb.B * pb.D + 32, h->stream));
+  fill_kernel<<<nblk(pb.B), 256, 0, h->stream>>>(pb.rho, pb.B, pb.rho0);
+  CU(cudaGetLastError());
+  return PMPC_OK;
+}
+
+int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double* params, size_t nparam, double eps) {
+  if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  DevProb& pb = h->pb;
+  if (kind == PMPC_DYN_DUBINS) {
+    if (pb.n != 4 || pb.m != 2 || nparam != 3 || !params)
+      return fail(PMPC_ERR_BAD_ARG, "Dubins car needs xdim=4, udim=2, params (3, B*M)");
+    double* d;
+    int rc;
+    if ((rc = upload(h, params, h->Ptot * 3, 0, &d))) return rc;
+    pack_particle_kernel<<<nblk(h->Ptot), 256, 0, h->stream>>>(d, pb.dynp, (int)h->Ptot, pb.P, 3, 4, 0.0);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    pb.dyn_kind = DYN_DUBINS;
+    pb.dyn_eps = eps;
+    h->have_dyn = true;
+    return PMPC_OK;
+  }
+  return fail(PMPC_ERR_BAD_ARG, "unknown dynamics kind (use pmpc_set_linearization / pmpc_set_ltv for AFFINE)");
+}
+
+static int set_affine(pmpc_handle_t h, const double* f, const double* fx, const double* fu, int c_is_f) {
+  if (!h || !fx || !fu) return fail(PMPC_ERR_BAD_ARG, "fx, fu required");
+  CU(cudaSetDevice(h->device));
+  DevProb& pb = h->pb;
+  const size_t Pt = h->Ptot, N = pb.N, n = pb.n, m = pb.m;
+  double *dfx, *dfu, *df = nullptr;
+  int rc;
+  if ((rc = upload(h, fx, Pt * N * n * n, 0, &dfx))) return rc;
+  // f and fu go through the persistent lin_* buffers (sized exactly)
+  CU(cudaMemcpyAsync(h->lin_fu, fu, Pt * N * n * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  dfu = h->lin_fu;
+  if (f) {
+    CU(cudaMemcpyAsync(h->lin_f, f, Pt * N * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    df = h->lin_f;
+  }
+  pack_lin_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, h->shape.NX, h->shape.NU, df, dfx, dfu, (int)Pt, c_is_f);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  pb.dyn_kind = DYN_AFFINE;
+  h->have_dyn = true;
+  return PMPC_OK;
+}
+
+int pmpc_set_linearization(pmpc_handle_t h, const double* f, const double* fx, const double* fu) {
+  if (!f) return fail(PMPC_ERR_BAD_ARG, "f required");
+  return set_affine(h, f, fx, fu, 0);
+}
+
+int pmpc_set_ltv(pmpc_handle_t h, const double* A, const double* Bm, const double* c) {
+  return set_affine(h, c, A, Bm, 1);
+}
+
+int pmpc_linearize(pmpc_handle_t h) {
+  if (!h || !h->have_problem || !h->have_dyn) return fail(PMPC_ERR_STATE, "set problem and dynamics first");
+  if (h->pb.dyn_kind != DYN_DUBINS) return fail(PMPC_ERR_STATE, "pmpc_linearize needs built-in dynamics");
+  CU(cudaSetDevice(h->device));
+  linearize_dubins_kernel<<<nblk(h->Ptot * h->pb.N), 256, 0, h->stream>>>(h->pb, h->lin_f, h->lin_fx, h->lin_fu,
+                                                                           (int)h->Ptot);
+  CU(cudaGetLastError());
+  return PMPC_OK;
+}
+
+int pmpc_get_linearization(pmpc_handle_t h, double* f, double* fx, double* fu) {
+  if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  const size_t Pt = h->Ptot, N = h->pb.N, n = h->pb.n, m = h->pb.m;
+  if (f) CU(cudaMemcpyAsync(f, h->lin_f, Pt * N * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (fx) CU(cudaMemcpyAsync(fx, h->lin_fx, Pt * N * n * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (fu) CU(cudaMemcpyAsync(fu, h->lin_fu, Pt * N * n * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return PMPC_OK;
+}
+
+static int launch(pmpc_handle_t h) {
+  const DevProb& pb = h->pb;
+  cudaError_t e = cudaErrorUnknown;
+  const int key = h->shape.NX * 100 + h->shape.NU;
+  CU(cudaEventRecord(h->ev0, h->stream));
+  switch (key) {
+    case 201: e = launch_scp<2, 1>(pb, h->stream); break;
+    case 402: e = launch_scp<4, 2>(pb, h->stream); break;
+    case 804: e = launch_scp<8, 4>(pb, h->stream); break;
+    case 1204: e = launch_scp<12, 4>(pb, h->stream); break;
+    case 1608: e = launch_scp<16, 8>(pb, h->stream); break;
+    case 3208: e = launch_scp<32, 8>(pb, h->stream); break;
+    default: return fail(PMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+  }
+  if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  CU(cudaEventRecord(h->ev1, h->stream));
+  h->solved = true;
+  return PMPC_OK;
+}
+
+int pmpc_scp_solve_async(pmpc_handle_t h, int max_it, double res_tol) {
+  if (!h || !h->have_problem || !h->have_dyn) return fail(PMPC_ERR_STATE, "set problem and dynamics first");
+  if (max_it < 1) return fail(PMPC_ERR_BAD_ARG, "max_it < 1");
+  CU(cudaSetDevice(h->device));
+  h->pb.max_it = max_it;
+  h->pb.res_tol = res_tol;
+  h->pb.keep_prev = 0;
+  if (max_it > h->pb.hist_len) {
+    // hist buffer is fixed-size; iterations beyond it are simply not recorded
+  }
+  return launch(h);
+}
+
+int pmpc_sync(pmpc_handle_t h) {
+  if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->solved) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return PMPC_OK;
+}
+
+int pmpc_scp_solve(pmpc_handle_t h, int max_it, double res_tol) {
+  int rc = pmpc_scp_solve_async(h, max_it, res_tol);
+  if (rc) return rc;
+  return pmpc_sync(h);
+}
+
+int pmpc_qp_solve(pmpc_handle_t h, int keep_prev) {
+  if (!h || !h->have_problem || !h->have_dyn) return fail(PMPC_ERR_STATE, "set problem and linearisation first");
+  CU(cudaSetDevice(h->device));
+  const int kind = h->pb.dyn_kind;
+  // one sub-problem at the *given* linearisation: for built-in dynamics linearize_prep recomputes it
+  // at (X_prev, U_prev), which is the same point.
+  h->pb.max_it = 1;
+  h->pb.res_tol = -1.0;
+  h->pb.keep_prev = keep_prev;
+  int rc = launch(h);
+  h->pb.dyn_kind = kind;
+  if (rc) return rc;
+  return pmpc_sync(h);
+}
+
+int pmpc_get_solution(pmpc_handle_t h, double* X, double* U) {
+  if (!h || !h->solved) return fail(PMPC_ERR_STATE, "no solution yet");
+  CU(cudaSetDevice(h->device));
+  const DevProb& pb = h->pb;
+  const size_t Pt = h->Ptot, N = pb.N;
+  double* dX = h->stage;
+  double* dU = h->stage + Pt * N * pb.n;
+  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, pb.P, pb.N, h->shape.NX, pb.n);
+  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.U, dU, (int)Pt, pb.P, pb.N, h->shape.NU, pb.m);
+  CU(cudaGetLastError());
+  if (X) CU(cudaMemcpyAsync(X, dX, Pt * N * pb.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (U) CU(cudaMemcpyAsync(U, dU, Pt * N * pb.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return PMPC_OK;
+}
+
+int pmpc_get_info(pmpc_handle_t h, long long* info) {
+  if (!h || !info) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  const size_t B = h->pb.B;
+  std::vector<long long> tmp(8 * B);
+  CU(cudaMemcpyAsync(tmp.data(), h->pb.info, 8 * B * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (size_t b = 0; b < B; ++b)
+    for (int k = 0; k < 8; ++k) info[b * 8 + k] = tmp[(size_t)k * B + b];
+  return PMPC_OK;
+}
+
+int pmpc_get_hist(pmpc_handle_t h, double* hist, int max_it) {
+  if (!h || !hist) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  const size_t B = h->pb.B, L = h->pb.hist_len;
+  std::vector<double> tmp(4 * L * B);
+  CU(cudaMemcpyAsync(tmp.data(), h->pb.hist, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 4; ++k)
+    for (int it = 0; it < max_it; ++it)
+      for (size_t b = 0; b < B; ++b)
+        hist[((size_t)k * max_it + it) * B + b] = (it < (int)L) ? tmp[((size_t)k * L + it) * B + b] : NAN;
+  return PMPC_OK;
+}
+
+int pmpc_last_kernel_ms(pmpc_handle_t h, float* ms) {
+  if (!h || !ms) return fail(PMPC_ERR_BAD_ARG, "null");
+  *ms = h->last_ms;
+  return PMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compat entry points.  Handles are cached per shape so repeated calls (one per SCP iteration from
+// the Python loop) do not pay for cudaMalloc.
+static std::mutex g_cache_mu;
+static std::map<std::tuple<size_t, size_t, size_t, size_t, long long>, pmpc_handle_t> g_cache;
+
+int pmpc_lqp_solve(double* X_out, double* U_out, size_t xdim, size_t udim, size_t N, size_t M, long long Nc,
+                   const double* x0, const double* f, const double* fx, const double* fu, const double* X_prev,
+                   const double* U_prev, const double* Q, const double* R, const double* X_ref, const double* U_ref,
+                   const double* lx, const double* ux, const double* lu, const double* uu, double reg_x,
+                   double reg_u, const double* slew_reg, const double* slew_reg0, const double* slew_um1,
+                   const pmpc_settings* settings, long long* info8) {
+  if (!X_out || !U_out) return fail(PMPC_ERR_BAD_ARG, "null outputs");
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  const long long Nce = (Nc < 0 || Nc > (long long)N) ? (long long)N : Nc;
+  auto key = std::make_tuple(xdim, udim, N, M, Nce);
+  pmpc_handle_t h = nullptr;
+  auto it = g_cache.find(key);
+  if (it == g_cache.end()) {
+    int rc = pmpc_create(&h, -1, 1, M, N, xdim, udim, Nce);
+    if (rc) return rc;
+    if (g_cache.size() >= 8) {
+      for (auto& kv : g_cache) pmpc_destroy(kv.second);
+      g_cache.clear();
+    }
+    g_cache[key] = h;
+  } else {
+    h = it->second;
+  }
+  int rc;
+  pmpc_settings s;
+  if (settings) s = *settings; else pmpc_default_settings(&s);
+  if ((rc = pmpc_set_settings(h, &s))) return rc;
+  if ((rc = pmpc_set_problem(h, x0, Q, R, X_ref, U_ref, lx, ux, lu, uu, reg_x, reg_u, slew_reg, slew_reg0, slew_um1)))
+    return rc;
+  if ((rc = pmpc_set_warm_start(h, X_prev, U_prev))) return rc;
+  if ((rc = pmpc_set_linearization(h, f, fx, fu))) return rc;
+  if ((rc = pmpc_qp_solve(h, 1))) return rc;
+  if ((rc = pmpc_get_solution(h, X_out, U_out))) return rc;
+  if (info8 && (rc = pmpc_get_info(h, info8))) return rc;
+  return PMPC_OK;
+}
+
+static void nan_fill(double* p, size_t n) {
+  if (p) for (size_t i = 0; i < n; ++i) p[i] = NAN;
+}
+
+void c_lqp_solve(double* X_out, double* U_out, size_t xdim, size_t udim, size_t N, size_t M, long long Nc, double* x0,
+                 double* f, double* fx, double* fu, double* X_prev, double* U_prev, double* Q, double* R,
+                 double* X_ref, double* U_ref, double* lx, double* ux, double* lu, double* uu, double reg_x,
+                 double reg_u, double* slew_reg, double* slew_reg0, double* slew_um1, long long verbose) {
+  long long info[8] = {0};
+  int rc = pmpc_lqp_solve(X_out, U_out, xdim, udim, N, M, Nc, x0, f, fx, fu, X_prev, U_prev, Q, R, X_ref, U_ref, lx,
+                          ux, lu, uu, reg_x, reg_u, slew_reg, slew_reg0, slew_um1, nullptr, info);
+  if (rc != PMPC_OK) {
+    if (verbose) fprintf(stderr, "pmpc_b200: c_lqp_solve failed: %s\n", pmpc_last_error());
+    nan_fill(X_out, xdim * N * M);
+    nan_fill(U_out, udim * N * M);
+  } else if (verbose) {
+    fprintf(stderr, "pmpc_b200: admm_iters=%lld factorizations=%lld polish_passes=%lld status=%lld\n", info[1],
+            info[2], info[3], info[4]);
+  }
+}
+
+void c_lcone_solve(double* X_out, double* U_out, size_t xdim, size_t udim, size_t N, size_t M, long long Nc,
+                   double* x0, double* f, double* fx, double* fu, double* X_prev, double* U_prev, double* Q,
+                   double* R, double* X_ref, double* U_ref, double* lx, double* ux, double* lu, double* uu,
+                   double reg_x, double reg_u, double* slew_reg, double* slew_reg0, double* slew_um1,
+                   long long verbose, double smooth_alpha, char* solver) {
+  (void)solver;
+  // The epigraph objective of the cone route (main.jl:204-227) has the QP's minimiser only for
+  // M == 1 with hard constraints (smooth_alpha NaN); anything else is out of scope -> NaN.
+  if (M == 1 && smooth_alpha != smooth_alpha) {
+    c_lqp_solve(X_out, U_out, xdim, udim, N, M, Nc, x0, f, fx, fu, X_prev, U_prev, Q, R, X_ref, U_ref, lx, ux, lu, uu,
+                reg_x, reg_u, slew_reg, slew_reg0, slew_um1, verbose);
+    return;
+  }
+  if (verbose) fprintf(stderr, "pmpc_b200: c_lcone_solve: M>1 / smoothed cone route is not provided\n");
+  nan_fill(X_out, xdim * N * M);
+  nan_fill(U_out, udim * N * M);
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""Python face of the handle API (``pmpc_create`` ... ``pmpc_destroy``, include/pmpc_b200.h).
+
+Arrays use the Python layout of ``pmpc.solve`` with an optional leading batch axis:
+vectors ``([B,] M, N, d)``, matrices ``([B,] M, N, rows, cols)``.  They are re-laid out to the
+reference C-ABI memory order (column-major blocks, ``c_interface.jl:28-46``) before the call,
+exactly what ``static_backend.lqp_solve`` does with ``py2jl`` + ``asfortranarray``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, dptr, f64c, mat_cm
+
+INFO_FIELDS = ("scp_iters", "admm_iters", "factorizations", "polish_passes", "status", "qp_by_polish", "qp_by_admm",
+               "reserved")
+
+
+class DeviceSolver:
+    def __init__(self, M: int, N: int, xdim: int, udim: int, Nc: int = -1, B: int = 1, device: int = -1,
+                 settings: Optional[dict] = None):
+        self.lib = _lib.load()
+        self.B, self.M, self.N, self.n, self.m = int(B), int(M), int(N), int(xdim), int(udim)
+        self.Nc = int(Nc)
+        self._h = C.c_void_p()
+        check(self.lib.pmpc_create(C.byref(self._h), device, self.B, self.M, self.N, self.n, self.m, self.Nc), "create")
+        if settings:
+            self.set_settings(**settings)
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _vec(self, a, d):
+        if a is None:
+            return None
+        a = f64c(a)
+        assert a.size == self.B * self.M * self.N * d, (a.shape, (self.B, self.M, self.N, d))
+        return a.reshape(self.B * self.M, self.N, d)
+
+    def _mat(self, a, r, c):
+        if a is None:
+            return None
+        a = np.asarray(a, dtype=np.float64)
+        assert a.size == self.B * self.M * self.N * r * c, (a.shape, (self.B, self.M, self.N, r, c))
+        return mat_cm(a.reshape(self.B * self.M, self.N, r, c))
+
+    def _per_particle(self, a, d=None):
+        if a is None:
+            return None
+        a = f64c(a)
+        P = self.B * self.M
+        if d is None:
+            return np.ascontiguousarray(np.broadcast_to(a.reshape(-1) if a.size > 1 else a.reshape(1), (P,)))
+        assert a.size == P * d, (a.shape, P, d)
+        return a.reshape(P, d)
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_settings(self, **kw):
+        s = _lib.default_settings(**kw)
+        check(self.lib.pmpc_set_settings(self._h, C.byref(s)), "set_settings")
+        self.settings = s
+
+    def set_problem(self, x0, Q, R, X_ref=None, U_ref=None, x_l=None, x_u=None, u_l=None, u_u=None, reg_x=1.0,
+                    reg_u=1e-2, slew_reg=None, slew_reg0=None, slew_um1=None):
+        n, m = self.n, self.m
+        absent = lambda z: z is None or np.size(z) == 0
+        keep = [  # keep references alive for the duration of the call
+            f64c(np.asarray(x0, float).reshape(self.B * self.M, n)), self._mat(Q, n, n), self._mat(R, m, m),
+            self._vec(X_ref, n), self._vec(U_ref, m),
+            None if absent(x_l) else self._vec(x_l, n), None if absent(x_u) else self._vec(x_u, n),
+            None if absent(u_l) else self._vec(u_l, m), None if absent(u_u) else self._vec(u_u, m),
+        ]
+        sl = [self._per_particle(slew_reg), self._per_particle(slew_reg0), self._per_particle(slew_um1, m)]
+        check(self.lib.pmpc_set_problem(self._h, *[dptr(a) for a in keep], float(reg_x), float(reg_u),
+                                        *[dptr(a) for a in sl]), "set_problem")
+
+    def set_warm_start(self, X_prev=None, U_prev=None):
+        a, b = self._vec(X_prev, self.n), self._vec(U_prev, self.m)
+        check(self.lib.pmpc_set_warm_start(self._h, dptr(a), dptr(b)), "set_warm_start")
+
+    def set_dubins(self, p, eps=1e-6):
+        """p: (3,) | (M,3) | (B,M,3) = (v_scale, w_scale, T) — reference tests/dubins_car.py:60."""
+        p = np.asarray(p, dtype=np.float64)
+        p = np.ascontiguousarray(np.broadcast_to(p, (self.B, self.M, 3)) if p.ndim < 3 else p).reshape(self.B * self.M, 3)
+        check(self.lib.pmpc_set_dynamics(self._h, 1, dptr(p), 3, float(eps)), "set_dynamics")
+
+    def set_linearization(self, f, fx, fu):
+        n, m = self.n, self.m
+        a, b, c = self._vec(f, n), self._mat(fx, n, n), self._mat(fu, n, m)
+        check(self.lib.pmpc_set_linearization(self._h, dptr(a), dptr(b), dptr(c)), "set_linearization")
+
+    def set_ltv(self, A, Bm, c=None):
+        n, m = self.n, self.m
+        a, b, cc = self._mat(A, n, n), self._mat(Bm, n, m), self._vec(c, n)
+        check(self.lib.pmpc_set_ltv(self._h, dptr(a), dptr(b), dptr(cc)), "set_ltv")
+
+    # -- compute -------------------------------------------------------------------------------
+    def linearize(self):
+        """Device linearisation (kernel K1) about the handle's (X_prev, U_prev): f, fx, fu."""
+        check(self.lib.pmpc_linearize(self._h), "linearize")
+        P, N, n, m = self.B * self.M, self.N, self.n, self.m
+        f, fx, fu = np.empty((P, N, n)), np.empty((P, N, n, n)), np.empty((P, N, m, n))
+        check(self.lib.pmpc_get_linearization(self._h, dptr(f), dptr(fx), dptr(fu)), "get_linearization")
+        shp = (self.B, self.M, N) if self.B > 1 else (self.M, N)
+        return f.reshape(shp + (n,)), np.swapaxes(fx, -1, -2).reshape(shp + (n, n)), np.swapaxes(fu, -1, -2).reshape(shp + (n, m))
+
+    def qp_solve(self, keep_prev=False):
+        check(self.lib.pmpc_qp_solve(self._h, int(keep_prev)), "qp_solve")
+
+    def scp_solve(self, max_it=100, res_tol=1e-5):
+        check(self.lib.pmpc_scp_solve(self._h, int(max_it), float(res_tol)), "scp_solve")
+
+    def scp_solve_async(self, max_it=100, res_tol=1e-5):
+        check(self.lib.pmpc_scp_solve_async(self._h, int(max_it), float(res_tol)), "scp_solve_async")
+
+    def sync(self):
+        check(self.lib.pmpc_sync(self._h), "sync")
+
+    # -- results -------------------------------------------------------------------------------
+    def solution(self):
+        P, N = self.B * self.M, self.N
+        X, U = np.empty((P, N, self.n)), np.empty((P, N, self.m))
+        check(self.lib.pmpc_get_solution(self._h, dptr(X), dptr(U)), "get_solution")
+        shp = (self.B, self.M, N) if self.B > 1 else (self.M, N)
+        return X.reshape(shp + (self.n,)), U.reshape(shp + (self.m,))
+
+    def info(self):
+        buf = np.zeros((self.B, 8), dtype=np.int64)
+        check(self.lib.pmpc_get_info(self._h, buf.ctypes.data_as(_lib.c_ll_p)), "get_info")
+        return {k: buf[:, i].copy() for i, k in enumerate(INFO_FIELDS)}
+
+    def hist(self, max_it):
+        buf = np.empty((4, int(max_it), self.B))
+        check(self.lib.pmpc_get_hist(self._h, dptr(buf), int(max_it)), "get_hist")
+        return dict(obj=buf[0], resid=buf[1], admm_iters=buf[2], kkt=buf[3])
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(self.lib.pmpc_last_kernel_ms(self._h, C.byref(ms)), "last_kernel_ms")
+        return float(ms.value)
