@@ -1,0 +1,112 @@
+"""Batched front-end: many independent problems in one device launch (BASELINE config 3).
+
+Counterpart of the reference's ``solve_problems`` (serial, ``scp_mpc.py:504-511``) and of the
+ZeroMQ task farm ``pmpc.remote.solve_problems`` (``remote.py:391-452``): instead of farming one
+problem per CPU worker, B problems of identical shape become B CTAs of the same kernel.
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+from .dynamics import BuiltinDynamics, DubinsCar, LTV
+from .handle import DeviceSolver
+
+
+def _sig(p: Dict[str, Any]):
+    dyn = p.get("f_fx_fu_fn")
+    if not isinstance(dyn, (DubinsCar, LTV)):
+        return None
+    if any(p.get(k) is not None and p.get(k) != "" for k in ("lin_cost_fn", "extra_cstrs_fns")) or p.get("filter_method", ""):
+        return None
+    x0 = np.asarray(p["x0"])
+    Q, R = np.asarray(p["Q"]), np.asarray(p["R"])
+    ss = p.get("solver_settings") or {}
+    present = tuple(p.get(k) is not None and np.size(p.get(k)) > 0 for k in ("x_l", "x_u", "u_l", "u_u"))
+    return (type(dyn).__name__, getattr(dyn, "eps", None), x0.ndim, Q.shape, R.shape, ss.get("Nc", -1), ss.get("slew_reg"),
+            float(p.get("reg_x", 1.0)), float(p.get("reg_u", 1e-2)), p.get("slew_rate", 0.0), p.get("u0_slew") is None,
+            present, int(p.get("max_it", 100)), float(p.get("res_tol", 1e-5)))
+
+
+def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: Optional[DeviceSolver] = None,
+                     settings: Optional[dict] = None):
+    """All problems must share :func:`_sig`.  Returns ``(list of (X, U, data), DeviceSolver)``."""
+    p0 = problems[0]
+    B = len(problems)
+    single = np.asarray(p0["x0"]).ndim == 1
+    Q0 = np.asarray(p0["Q"])
+    M = 1 if single else Q0.shape[0]
+    N, n = Q0.shape[-3], Q0.shape[-1]
+    m = np.asarray(p0["R"]).shape[-1]
+    ss = p0.get("solver_settings") or {}
+    Nc = ss.get("Nc", -1)
+    max_it, res_tol = int(p0.get("max_it", 100)), float(p0.get("res_tol", 1e-5))
+
+    def stack(key, shape, default=None):
+        vals = [p.get(key) for p in problems]
+        if all(v is None or np.size(v) == 0 for v in vals):
+            return default
+        return np.stack([np.asarray(v, np.float64).reshape(shape) for v in vals])
+
+    ds = solver
+    if ds is None or (ds.B, ds.M, ds.N, ds.n, ds.m, ds.Nc) != (B, M, N, n, m, Nc):
+        ds = DeviceSolver(M, N, n, m, Nc, B=B, device=device, settings=settings)
+    X_ref, U_ref = stack("X_ref", (M, N, n)), stack("U_ref", (M, N, m))
+    slew_rate = p0.get("slew_rate", 0.0)
+    ds.set_problem(stack("x0", (M, n)), stack("Q", (M, N, n, n)), stack("R", (M, N, m, m)), X_ref, U_ref,
+                   stack("x_l", (M, N, n)), stack("x_u", (M, N, n)), stack("u_l", (M, N, m)), stack("u_u", (M, N, m)),
+                   float(p0.get("reg_x", 1.0)), float(p0.get("reg_u", 1e-2)),
+                   None if slew_rate is None else np.full(B * M, float(slew_rate)),
+                   np.full(B * M, float(ss["slew_reg"])) if "slew_reg" in ss else None, stack("u0_slew", (M, m)))
+    # warm start defaults follow scp_mpc.py:313-314 (X_prev = X_ref, U_prev = U_ref)
+    Xp = stack("X_prev", (M, N, n), X_ref)
+    Up = stack("U_prev", (M, N, m), U_ref)
+    ds.set_warm_start(Xp, Up)
+    dyn0 = p0["f_fx_fu_fn"]
+    if isinstance(dyn0, DubinsCar):
+        ds.set_dubins(np.stack([p["f_fx_fu_fn"].params_for(M) for p in problems]), dyn0.eps)
+    else:
+        bc = lambda a, tail: np.stack([np.broadcast_to(np.asarray(getattr(p["f_fx_fu_fn"], a)), (M, N) + tail) for p in problems])
+        ds.set_ltv(bc("A", (n, n)), bc("B", (n, m)), None if dyn0.c is None else bc("c", (n,)))
+    t = time.time()
+    ds.scp_solve(max_it, res_tol)
+    wall = time.time() - t
+    X, U = ds.solution()
+    X, U = X.reshape(B, M, N, n), U.reshape(B, M, N, m)
+    info = ds.info()
+    its_max = int(info["scp_iters"].max())
+    h = ds.hist(max(its_max, 1))
+    x0s = stack("x0", (M, n))
+    out = []
+    for b in range(B):
+        if int(info["status"][b]) & 1:
+            out.append((None, None, None))
+            continue
+        its = int(info["scp_iters"][b])
+        hist = [dict(it=i + 1, elaps=wall * (i + 1) / its, obj=float(h["obj"][i, b]), resid=float(h["resid"][i, b]),
+                     reg_x=float(p0.get("reg_x", 1.0)), reg_u=float(p0.get("reg_u", 1e-2))) for i in range(its)]
+        data = dict(hist=hist, solver_data=[dict(admm_iters=int(h["admm_iters"][i, b])) for i in range(its)],
+                    t_aff_solve=[wall / its] * its, device={k: int(v[b]) for k, v in info.items()})
+        Xb = np.concatenate([x0s[b][:, None, :], X[b]], -2)
+        out.append((Xb[0], U[b][0], data) if single else (Xb, U[b], data))
+    return out, ds
+
+
+def solve_batched(problems: List[Dict[str, Any]], verbose: bool = False, device: int = -1, **kw):
+    from .scp_mpc import solve
+
+    results: List[Any] = [None] * len(problems)
+    groups: Dict[Any, List[int]] = {}
+    for i, p in enumerate(problems):
+        groups.setdefault(_sig(p), []).append(i)
+    for sig, idxs in groups.items():
+        if sig is None:
+            for i in idxs:
+                results[i] = solve(**dict(problems[i], verbose=verbose))
+            continue
+        res, _ = solve_same_shape([problems[i] for i in idxs], device=device)
+        for i, r in zip(idxs, res):
+            results[i] = r
+    return results

@@ -44,28 +44,3 @@ print("scp consensus: its", inf["scp_iters"], "errX %.2e errU %.2e" % (np.abs(X 
       {k: int(v[0]) for k, v in inf.items()}, "ms %.3f" % s.last_kernel_ms())
 print("resid hist", h["resid"][:5, 0], d["hist"][:5, 1])
 
-# C2 timing
-rng = np.random.default_rng(1)
-M, N, n, m = 128, 50, 4, 2
-p = np.stack([rng.uniform(0.7, 1.0, M), rng.uniform(0.7, 1.0, M), np.full(M, 0.3)], -1)
-Q = np.tile(np.eye(n), (M, N, 1, 1)); R = np.tile(1e-2 * np.eye(m), (M, N, 1, 1)); x0 = np.ones((M, n))
-for B in [1, 148, 592]:
-    s = DeviceSolver(M, N, n, m, 1, B=B)
-    t = time.time()
-    s.set_problem(np.tile(x0, (B, 1, 1)), np.tile(Q, (B, 1, 1, 1, 1)), np.tile(R, (B, 1, 1, 1, 1)), None, None, None, None,
-                  -np.ones((B, M, N, m)), np.ones((B, M, N, m)), 1.0, 1e-2)
-    s.set_dubins(np.tile(p, (B, 1, 1)))
-    t_set = time.time() - t
-    for rep in range(3):
-        s.set_warm_start(None, None)
-        t = time.time(); s.scp_solve(100, 1e-5); t_solve = time.time() - t
-    inf = s.info()
-    print("C2 B=%d: set %.3fs solve wall %.3f ms kernel %.3f ms; scp its %d admm %d fact %d status %d -> %.1f solves/s" % (
-        B, t_set, 1e3 * t_solve, s.last_kernel_ms(), inf["scp_iters"][0], inf["admm_iters"][0], inf["factorizations"][0],
-        inf["status"].max(), B / (s.last_kernel_ms() * 1e-3)))
-    if B == 1:
-        X, U = s.solution()
-        ref = np.load("/tmp/c2_proto.npz") if os.path.exists("/tmp/c2_proto.npz") else None
-        if ref is not None:
-            print("  vs proto errX %.2e errU %.2e" % (np.abs(X - ref["X"]).max(), np.abs(U - ref["U"]).max()))
-    s.close()

@@ -1,0 +1,168 @@
+"""CPU tests of the drop-in boundary and host logic: the C-ABI library loads and exports every
+symbol include/pmpc_b200.h declares, the product path fails loudly without a GPU (no CPU
+fallback), the Python API mirrors the reference's signatures, and the N>1 sharding logic works
+under a 2-process gloo group.  No compute calls are made."""
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import pmpc_b200
+from pmpc_b200 import _lib, parallel, static_backend
+from pmpc_b200.utils import TablePrinter
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REF = "/root/reference"
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "pmpc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:void|int|const char \*)\s*\*?\s*((?:pmpc|c)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_functions()
+    assert {"c_lqp_solve", "c_lcone_solve", "pmpc_create", "pmpc_scp_solve", "pmpc_lqp_solve"} <= set(names)
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/pmpc_b200.h but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) == set(names), set(_lib.EXPORTED_SYMBOLS) ^ set(names)
+    assert b"sm_100a" in lib.pmpc_version()
+
+
+def test_settings_struct_matches_the_header_defaults():
+    s = _lib.default_settings()
+    assert (s.rho0, s.alpha, s.max_admm_iter, s.check_every, s.polish, s.warm_start) == (1.0, 1.6, 4000, 10, 1, 1)
+    assert s.eps_abs == 1e-9 and s.kkt_tol == 1e-9
+    with pytest.raises(KeyError):
+        _lib.default_settings(nonsense=1)
+
+
+@pytest.mark.skipif(_lib.load().pmpc_device_count() > 0, reason="a GPU is present")
+def test_product_path_fails_loudly_without_a_gpu():
+    """No CPU fallback: the handle API raises, the void compat entry NaN-fills (reference failure
+    convention, osqp_solver.jl:69-71 -> scp_mpc.py:391-394 returns (None, None, None))."""
+    with pytest.raises(_lib.PmpcError, match="no CUDA device"):
+        pmpc_b200.DeviceSolver(1, 5, 2, 1)
+    M, N, n, m = 1, 4, 2, 1
+    Q, R = np.tile(np.eye(n), (N, 1, 1)), np.tile(np.eye(m), (N, 1, 1))
+    lti = pmpc_b200.LTV(np.tile(np.eye(n), (1, N, 1, 1)), np.ones((1, N, n, m)))
+    out = pmpc_b200.solve(lti, Q, R, np.ones(n), solver_settings=dict(solver="osqp", host_loop=True), max_it=2)
+    assert out == (None, None, None)
+    with pytest.raises(_lib.PmpcError):
+        pmpc_b200.solve(lti, Q, R, np.ones(n), solver_settings=dict(solver="osqp"), max_it=2)
+
+
+def test_solve_signature_matches_reference():
+    ours = list(inspect.signature(pmpc_b200.scp_solve).parameters)
+    assert ours[:12] == ["f_fx_fu_fn", "Q", "R", "x0", "X_ref", "U_ref", "X_prev", "U_prev", "x_l", "x_u", "u_l", "u_u"]
+    d = {k: v.default for k, v in inspect.signature(pmpc_b200.scp_solve).parameters.items()}
+    assert (d["max_it"], d["res_tol"], d["reg_x"], d["reg_u"], d["slew_rate"], d["time_limit"]) == (100, 1e-5, 1.0, 1e-2, 0.0, 1000.0)
+    if os.path.isdir(REF):
+        sys.path.insert(0, REF)
+        import pmpc  # the reference's Python layer imports without Julia
+
+        ref = inspect.signature(pmpc.scp_mpc.scp_solve).parameters
+        assert list(ref) == ours
+        for k in ref:
+            if ref[k].default is not inspect._empty:
+                assert ref[k].default == d[k], k
+        assert pmpc.SOLVE_KWS == pmpc_b200.SOLVE_KWS
+        sys.path.remove(REF)
+
+
+def test_problem_defaults_and_tiling():
+    p = pmpc_b200.Problem(N=5, xdim=4, udim=2, M=3, x0=np.arange(4.0), u_l=-np.ones((5, 2)))
+    p.f_fx_fu_fn = pmpc_b200.DubinsCar()
+    d = p.to_dict()
+    assert d["Q"].shape == (3, 5, 4, 4) and d["R"].shape == (3, 5, 2, 2) and d["x0"].shape == (3, 4)
+    assert d["u_l"].shape == (3, 5, 2) and d["u_u"] is None and d["solver_settings"]["Nc"] == 0
+    assert np.all(d["R"][0, 0] == 0.1 * np.eye(2)) and d["reg_x"] == 1.0 and d["max_it"] == 30 and d["res_tol"] == 1e-6
+    assert set(d) >= {"Q", "R", "x0", "X_ref", "U_ref", "X_prev", "U_prev", "f_fx_fu_fn", "solver_settings"}
+    with pytest.raises(AssertionError):
+        p.Q = np.zeros((5, 3, 3))
+    with pytest.raises(ValueError):
+        pmpc_b200.Problem(N=5, xdim=4)
+    assert dict(**p)["reg_u"] == 1.0  # Mapping protocol: solve(**problem)
+
+
+def test_table_printer_and_filters_match_reference_behaviour():
+    names, fmts = ["it", "elaps", "obj", "resid", "reg_x", "reg_u"], ["%04d", "%8.3e", "%8.3e", "%8.3e", "%8.3e", "%8.3e"]
+    tp = TablePrinter(names, fmts=fmts)
+    row = tp.make_values((3, 0.1234, 1.5, 2e-5, 1.0, 1e-2))
+    assert row.startswith("|") and row.count("|") == 7 and "0003" in row and "2.000e-05" in row
+    rng = np.random.default_rng(0)
+    Fs = [rng.standard_normal(12) for _ in range(4)]
+    for name in ("AA", "smooth", "select"):
+        w = pmpc_b200.FILTER_MAP[name](Fs)
+        assert w.shape == (4,) and abs(w.sum() - 1.0) < 1e-9
+    if os.path.isdir(REF):
+        sys.path.insert(0, REF)
+        import pmpc
+        from pmpc.utils import TablePrinter as RefTP
+
+        rtp = RefTP(names, fmts=fmts)
+        assert rtp.make_header() == tp.make_header() and rtp.make_values((3, 0.1234, 1.5, 2e-5, 1.0, 1e-2)) == row
+        assert rtp.make_footer() == tp.make_footer()
+        for name in ("AA", "smooth", "select"):
+            assert np.allclose(pmpc.scp_mpc.FILTER_MAP[name](Fs), pmpc_b200.FILTER_MAP[name](Fs), atol=1e-9)
+        sys.path.remove(REF)
+
+
+def test_layout_helpers_follow_the_c_abi():
+    """py2jl + asfortranarray (what the reference does, static_backend.py:71-74) and mat_cm (what
+    the handle API does) give the same bytes: column-major blocks, particle slowest."""
+    rng = np.random.default_rng(1)
+    fx = rng.standard_normal((3, 5, 4, 4))
+    a = np.asfortranarray(static_backend.py2jl(fx, 2))
+    assert a.shape == (4, 4, 5, 3)
+    flat_ref = a.ravel(order="K") if a.flags["F_CONTIGUOUS"] else None
+    flat_ref = np.ravel(a, order="F")
+    assert np.array_equal(flat_ref, _lib.mat_cm(fx).ravel())
+    i, j, r, t = 2, 3, 1, 2
+    assert flat_ref[r + 4 * (t + 4 * (j + 5 * i))] == fx[i, j, r, t]
+
+
+def test_shard_bounds_partition():
+    for total in (0, 1, 7, 16384):
+        for world in (1, 2, 3, 8):
+            b = [parallel.shard_bounds(total, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total
+            assert all(b[k][1] == b[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from pmpc_b200 import parallel
+d = parallel.init_process_group("gloo")
+r, w = d.get_rank(), d.get_world_size()
+lo, hi = parallel.shard_bounds(11, r, w)
+parts = parallel.gather_objects(list(range(lo, hi)), d)
+assert [x for p in parts for x in p] == list(range(11)), parts
+assert parallel.reduce_max(float(r + 1), d) == float(w)
+assert parallel.reduce_sum(float(hi - lo), d) == 11.0
+d.barrier(); d.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_two_process_gloo_sharding(tmp_path):
+    """N>1 path on CPU: 2 ranks over gloo shard a batch, gather results in order, max-reduce time."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2

@@ -1,0 +1,256 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs, against the reference-generated golden fixtures, and — at BASELINE sizes — through
+size-independent properties.  Tolerances (BASELINE.json north_star): linearisation 1e-12 relative,
+converged X, U 1e-5 relative, objective 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import pmpc_b200
+from fixtures import config_c1, config_c2, config_c3, config_c4, double_integrator, rand_problem
+from oracle import dubins, lqp, scp as oscp
+from pmpc_b200 import DeviceSolver, DubinsCar, LTV, static_backend
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / max(1.0, np.abs(np.asarray(b)).max())
+
+
+def _aff(args, kw, Nc, solver="osqp"):
+    """One sub-problem through aff_solve -> lqp_solve -> pmpcjl.lqp_solve -> c_lqp_solve (C ABI)."""
+    x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur = args
+    ss = dict(solver=solver, Nc=Nc)
+    slew_rate = None
+    if "slew_reg" in kw and not np.isnan(kw["slew_reg"]).any():
+        slew_rate = float(kw["slew_reg"][0])
+    u_slew = None
+    if "slew_reg0" in kw and not np.isnan(kw["slew_reg0"]).any():
+        ss["slew_reg"] = float(kw["slew_reg0"][0])
+        u_slew = kw["slew_um1"]
+    X, U, _ = static_backend.aff_solve(f, fx, fu, x0, Xp, Up, Q, R, Xr, Ur, kw["reg_x"], kw["reg_u"], slew_rate, u_slew,
+                                       kw.get("lx"), kw.get("ux"), kw.get("lu"), kw.get("uu"), ss)
+    return X[:, 1:], U
+
+
+CASES = [
+    # M, N, n, m, Nc, slew, ubox, xbox
+    (1, 5, 2, 1, 0, True, 0.1, None), (3, 6, 4, 2, 2, True, 0.1, None), (4, 7, 3, 2, -1, True, 0.2, None),
+    (2, 4, 3, 2, 1, False, 0.1, None), (2, 1, 2, 1, 1, True, 0.1, None), (5, 8, 4, 2, 1, True, None, None),
+    (5, 8, 4, 2, 3, False, 0.3, None), (3, 6, 4, 2, 0, True, 0.1, None), (40, 10, 4, 2, 1, True, 0.3, None),
+    (3, 5, 6, 3, 1, True, 0.2, None), (2, 6, 12, 4, 1, True, 0.2, None), (1, 9, 4, 2, 3, True, 0.2, None),
+    (33, 5, 4, 2, 2, True, 0.2, None), (2, 4, 7, 5, 1, False, 0.2, None),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_qp_parity_through_c_abi(gpu, case):
+    """c_lqp_solve vs the exact oracle (uniform per-problem slew, the only kind the Python path can
+    express: static_backend.py:262-267 broadcasts one scalar)."""
+    M, N, n, m, Nc, slew, box, xbox = case
+    rng = np.random.default_rng(100 + sum(x for x in case[:5]))
+    args, kw = rand_problem(rng, M, N, n, m, slew, box, xbox, per_particle_slew=False)
+    if slew:
+        kw["slew_reg0"] = np.full(M, 0.7)
+    Xo, Uo, info = lqp.lqp_solve(*args, Nc=Nc, **kw)
+    X, U = _aff(args, kw, Nc)
+    assert rel(X, Xo) < 1e-7 and rel(U, Uo) < 1e-7  # target 1e-5; the polish is exact to round-off
+    zo = info["z"]
+    obj = lambda Xs, Us: (lambda z: 0.5 * z @ (info["prob"].P @ z) + info["prob"].q @ z)(_pack(info["prob"], Xs, Us))
+    assert abs(obj(X, U) - info["cert"].objective) <= 1e-6 * max(1.0, abs(info["cert"].objective))
+
+
+def _pack(prob, X, U):
+    z = np.zeros(prob.nz)
+    z[prob.ix] = X
+    z[prob.iu] = U
+    return z
+
+
+def test_qp_parity_per_particle_slew_through_handle_api(gpu):
+    """Per-particle slew weights (expressible in the C ABI, c_interface.jl:44-46) and state boxes."""
+    rng = np.random.default_rng(11)
+    for (M, N, n, m, Nc) in [(4, 6, 4, 2, 1), (3, 5, 4, 2, 0)]:
+        args, kw = rand_problem(rng, M, N, n, m, True, 0.2)
+        Xo, Uo, _ = lqp.lqp_solve(*args, Nc=Nc, **kw)
+        x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur = args
+        with DeviceSolver(M, N, n, m, Nc) as s:
+            s.set_problem(x0, Q, R, Xr, Ur, None, None, kw["lu"], kw["uu"], kw["reg_x"], kw["reg_u"], kw["slew_reg"],
+                          kw["slew_reg0"], kw["slew_um1"])
+            s.set_warm_start(Xp, Up)
+            s.set_linearization(f, fx, fu)
+            s.qp_solve(keep_prev=True)
+            X, U = s.solution()
+        assert rel(X, Xo) < 1e-7 and rel(U, Uo) < 1e-7
+
+
+def test_state_box_active_is_solved_by_admm(gpu):
+    rng = np.random.default_rng(100)
+    M, N, n, m, Nc = 3, 6, 4, 2, 1
+    args, kw = rand_problem(rng, M, N, n, m, True, 0.5, per_particle_slew=False)
+    kw["slew_reg0"] = np.full(M, 0.7)
+    Xo, _, _ = lqp.lqp_solve(*args, Nc=Nc, **kw)
+    xb = 0.85 * np.abs(Xo).max()
+    kw.update(lx=-xb * np.ones((M, N, n)), ux=xb * np.ones((M, N, n)))
+    Xo, Uo, info = lqp.lqp_solve(*args, Nc=Nc, **kw)
+    assert np.sum(np.abs(Xo) >= xb - 1e-9) >= 1
+    X, U = _aff(args, kw, Nc)
+    assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+    assert np.abs(X).max() <= xb * (1 + 1e-6)
+
+
+def test_sentinel_sweep_double_integrator(gpu):
+    """Every present/absent (NaN) combination the reference sweeps through c_lqp_solve
+    (c_precompile.jl:52-100), compared with the oracle."""
+    args, kw, Nc = double_integrator(u_limit=0.4)
+    for ub in (False, True):
+        for xb in (False, True):
+            for s0 in (False, True):
+                for s in (False, True):
+                    k = dict(reg_x=kw["reg_x"], reg_u=kw["reg_u"])
+                    if ub:
+                        k.update(lu=kw["lu"], uu=kw["uu"])
+                    if xb:
+                        k.update(lx=kw["lx"], ux=kw["ux"])
+                    k["slew_reg"] = kw["slew_reg"] if s else np.full(1, np.nan)
+                    k["slew_reg0"] = kw["slew_reg0"] if s0 else np.full(1, np.nan)
+                    k["slew_um1"] = kw["slew_um1"] if s0 else np.full((1, 1), np.nan)
+                    Xo, Uo, _ = lqp.lqp_solve(*args, Nc=Nc, **k)
+                    X, U = _aff(args, k, Nc)
+                    assert rel(X, Xo) < 1e-7 and rel(U, Uo) < 1e-7, (ub, xb, s0, s)
+
+
+def test_cone_entry_point_single_particle(gpu):
+    """c_lcone_solve with hard constraints and M = 1 has the QP's minimiser."""
+    args, kw, Nc = double_integrator(u_limit=0.4)
+    Xo, Uo, _ = lqp.lqp_solve(*args, Nc=Nc, **kw)
+    x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur = args
+    j = static_backend.py2jl
+    X, U = static_backend.lcone_solve(Nc, j(x0), j(f), j(fx, 2), j(fu, 2), j(Xp), j(Up), j(Q, 2), j(R, 2), j(Xr), j(Ur),
+                                      j(kw["lx"]), j(kw["ux"]), j(kw["lu"]), j(kw["uu"]), 1.0, 0.1, kw["slew_reg"],
+                                      kw["slew_reg0"], j(kw["slew_um1"]), smooth_alpha=np.nan, solver="ecos")
+    assert rel(X, Xo) < 1e-7 and rel(U, Uo) < 1e-7
+
+
+def test_failure_convention_nan_in_gives_none_out(gpu):
+    d, p = config_c1()
+    d["Q"] = d["Q"].copy()
+    d["Q"][0, 3, 0, 0] = np.nan
+    assert pmpc_b200.solve(DubinsCar(p[0]), **d) == (None, None, None)
+
+
+# ---------------------------------------------------------------------------------------- K1
+def test_linearisation_kernel(gpu):
+    """Device Dubins f, fx, fu: 1e-12 relative vs the oracle everywhere, and vs the reference's own
+    autograd values where those are well conditioned (|u| >= 0.05)."""
+    g = np.load(os.path.join(GOLD, "dubins_lin.npz"))
+    for k in ("generic", "zero_u", "small_u"):
+        X, U, P = g[k + "_X"], g[k + "_U"], g[k + "_p"]
+        car = DubinsCar(P[:, 0, :])
+        f, fx, fu = car(X, U)
+        fo, fxo, fuo = dubins.car_f_fx_fu(X, U, P)
+        assert rel(f, fo) < 1e-12 and rel(fx, fxo) < 1e-12 and rel(fu, fuo) < 1e-12
+        if k == "generic":
+            assert rel(f, g[k + "_f"]) < 1e-12 and rel(fx, g[k + "_fx"]) < 1e-12 and rel(fu, g[k + "_fu"]) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------- SCP
+@pytest.mark.parametrize("name,kw", [
+    ("scp_c1", dict(max_it=10, res_tol=-1.0, solver_settings=dict(solver="osqp"))),
+    ("scp_consensus", dict(max_it=40, res_tol=1e-7, solver_settings=dict(solver="osqp", Nc=1))),
+    ("scp_slew", dict(max_it=60, res_tol=1e-7, slew_rate=0.5, solver_settings=dict(solver="osqp", Nc=2, slew_reg=0.3))),
+])
+def test_host_loop_replays_reference_golden(gpu, name, kw):
+    """pmpc_b200.solve with a Python callable that replays the linearisations the REFERENCE loop
+    consumed must land on the reference loop's X, U and history (golden from make_golden.py)."""
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    it = iter(range(len(d["lin_f"])))
+
+    def replay(X, U):
+        k = next(it)
+        return d["lin_f"][k], d["lin_fx"][k], d["lin_fu"][k]
+
+    extra = {}
+    if name == "scp_slew":
+        extra = dict(u0_slew=0.2 * np.ones((3, 2)), x_l=d["x_l"], x_u=d["x_u"])
+    X, U, data = pmpc_b200.solve(replay, d["Q"], d["R"], d["x0"], d["X_ref"], d["U_ref"], d["X_prev"], d["U_prev"],
+                                 u_l=d["u_l"], u_u=d["u_u"], reg_x=1.0, reg_u=1e-2, **kw, **extra)
+    hist = np.array([[h["obj"], h["resid"]] for h in data["hist"]])
+    assert len(hist) == len(d["hist"])
+    assert rel(X, d["X"]) < 1e-5 and rel(U, d["U"]) < 1e-5
+    assert np.abs(hist[:, 0] - d["hist"][:, 0]).max() <= 1e-6 * np.abs(d["hist"][:, 0]).max()
+
+
+def _oracle_scp(d, p):
+    fn = dubins.make_f_fx_fu_fn(p)
+    kw = {k: d[k] for k in ("X_ref", "U_ref", "X_prev", "U_prev", "u_l", "u_u", "reg_x", "reg_u", "max_it", "res_tol")}
+    return oscp.scp_solve(fn, d["Q"], d["R"], d["x0"], solver_settings=d["solver_settings"], **kw)
+
+
+def test_device_scp_loop_c1_matches_oracle(gpu):
+    """BASELINE config 1 fully on the device (linearise + QP + bookkeeping in one launch)."""
+    d, p = config_c1()
+    Xo, Uo, do = _oracle_scp(d, p)
+    X, U, data = pmpc_b200.solve(DubinsCar(p[0]), **{k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in d.items()})
+    assert X.shape == (21, 4) and U.shape == (20, 2) and len(data["hist"]) == 10
+    assert rel(X, Xo[0]) < 1e-5 and rel(U, Uo[0]) < 1e-5
+    ho = np.array([[h["obj"], h["resid"]] for h in do["hist"]])
+    h = np.array([[h["obj"], h["resid"]] for h in data["hist"]])
+    assert np.abs(h[:, 0] - ho[:, 0]).max() <= 1e-6 * np.abs(ho[:, 0]).max()
+    assert np.abs(h[:, 1] - ho[:, 1]).max() <= 1e-6 * np.abs(ho[:, 1]).max()
+
+
+def test_device_scp_consensus_matches_oracle_and_host_loop(gpu):
+    d, p = config_c2(M=8, N=15)
+    d.update(res_tol=1e-7, max_it=60)
+    Xo, Uo, do = _oracle_scp(d, p)
+    X, U, data = pmpc_b200.solve(DubinsCar(p), **d)
+    assert len(data["hist"]) == len(do["hist"])
+    assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+    assert abs(data["hist"][-1]["obj"] - do["hist"][-1]["obj"]) <= 1e-6 * abs(do["hist"][-1]["obj"])
+    assert np.all(U[:, :1] == U[0:1, :1])  # consensus on the first Nc controls
+    Xh, Uh, dh = pmpc_b200.solve(DubinsCar(p), **dict(d, solver_settings=dict(d["solver_settings"], host_loop=True)))
+    assert rel(Xh, X) < 1e-9 and rel(Uh, U) < 1e-9 and len(dh["hist"]) == len(data["hist"])
+
+
+def test_full_size_c2_properties(gpu):
+    """BASELINE config 2 at full size (M=128, N=50): properties that do not need the oracle."""
+    d, p = config_c2()
+    car = DubinsCar(p)
+    X, U, data = pmpc_b200.solve(car, **d)
+    dev = data["device"]
+    assert dev["status"] == 0 and data["hist"][-1]["resid"] < 1e-5
+    assert np.all(U[:, 0] == U[0, 0])                                   # consensus
+    assert U.max() <= 1 + 1e-9 and U.min() >= -1 - 1e-9                 # box
+    assert max(sd["kkt"] for sd in data["solver_data"]) < 1e-8          # every QP certified on device
+    # fixed point: the converged trajectory satisfies the true nonlinear dynamics to ~res_tol
+    f, _, _ = car(X[:, :-1], U)
+    assert np.abs(f - X[:, 1:]).max() < 1e-4
+    # idempotence: restarting from the solution converges immediately to the same point
+    X2, U2, data2 = pmpc_b200.solve(car, **dict(d, X_prev=X[:, 1:], U_prev=U))
+    assert len(data2["hist"]) <= 2 and rel(X2, X) < 1e-4
+
+
+def test_batched_equals_individual(gpu):
+    """BASELINE config 3 (reduced B): B problems in one launch == B separate solves."""
+    B = 6
+    d, p = config_c3(B=B)
+    probs = [dict({k: (v[b] if isinstance(v, np.ndarray) and v.shape[0] == B else v) for k, v in d.items()},
+                  f_fx_fu_fn=DubinsCar(p[b])) for b in range(B)]
+    res = pmpc_b200.solve_problems(probs)
+    for b in (0, 3, 5):
+        X, U, data = pmpc_b200.solve(**probs[b])
+        assert rel(res[b][0], X) < 1e-12 and rel(res[b][1], U) < 1e-12
+        assert len(res[b][2]["hist"]) == len(data["hist"])
+
+
+def test_ltv_c4_reduced_matches_oracle(gpu):
+    """BASELINE config 4 (reduced M, N): 12-state LTV, slew, control + state boxes, Nc=1."""
+    d, A, Bm = config_c4(M=3, N=12)
+    fn = LTV(A, Bm)
+    X, U, data = pmpc_b200.solve(fn, **d)
+    Xo, Uo, do = oscp.scp_solve(lambda X_, U_: fn(X_, U_), d["Q"], d["R"], d["x0"], X_ref=d["X_ref"], U_ref=d["U_ref"],
+                                X_prev=d["X_prev"], U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"], x_l=d["x_l"],
+                                x_u=d["x_u"], reg_x=d["reg_x"], reg_u=d["reg_u"], slew_rate=d["slew_rate"],
+                                max_it=d["max_it"], res_tol=d["res_tol"], solver_settings=d["solver_settings"])
+    assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5

@@ -1,0 +1,163 @@
+"""CPU tests of the oracle (test infrastructure) against the reference-generated golden files and
+against itself (solver-independent KKT certificate).  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from fixtures import double_integrator, rand_problem
+from oracle import dubins, lqp, riccati_admm, scp
+from oracle.osqp_port import osqp_solve
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _direct_cost(args, kw, X, U, Nc):
+    x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur = args
+    M, N, n = f.shape
+    m = fu.shape[-1]
+    s, s0 = kw.get("slew_reg", np.zeros(M)), kw.get("slew_reg0", np.zeros(M))
+    um1 = kw.get("slew_um1", np.zeros((M, m)))
+    J = 0.0
+    for i in range(M):
+        for j in range(N):
+            dx, du = X[i, j] - Xr[i, j], U[i, j] - Ur[i, j]
+            J += 0.5 * dx @ Q[i, j] @ dx + 0.5 * kw["reg_x"] * np.sum((X[i, j] - Xp[i, j]) ** 2)
+            J += 0.5 * du @ R[i, j] @ du + 0.5 * kw["reg_u"] * np.sum((U[i, j] - Up[i, j]) ** 2)
+            if j >= 1:
+                J += 0.5 * s[i] * np.sum((U[i, j] - U[i, j - 1]) ** 2)
+        J += 0.5 * s0[i] * np.sum((U[i, 0] - (um1[i] if Nc >= 1 else 0.0)) ** 2)  # Nc == 0 quirk (App. B.6)
+        if N == 1:
+            J += 0.5 * s[i] * np.sum(U[i, 0] ** 2)  # lqp_utils.jl:31-37
+    return J
+
+
+@pytest.mark.parametrize("dims", [(3, 6, 4, 2, 2), (1, 5, 2, 1, 0), (4, 7, 3, 2, -1), (2, 4, 3, 2, 1), (2, 1, 2, 1, 1)])
+def test_assembled_qp_is_the_sum_of_particle_costs(dims):
+    """P, q, A, b built like lqp_repr_Pq/Ab reproduce sum_i J_i and the linearised dynamics."""
+    M, N, n, m, Nc = dims
+    rng = np.random.default_rng(sum(dims))
+    args, kw = rand_problem(rng, M, N, n, m)
+    prob = lqp.build_lqp(*args, Nc=Nc, **kw)
+    Nce = N if Nc < 0 else Nc
+    z1, z2 = rng.standard_normal(prob.nz), rng.standard_normal(prob.nz)
+    cost = lambda z: 0.5 * z @ (prob.P @ z) + prob.q @ z
+    (X1, U1), (X2, U2) = lqp.split_vars(prob, z1), lqp.split_vars(prob, z2)
+    d_qp = cost(z1) - cost(z2)
+    d_dir = _direct_cost(args, kw, X1, U1, Nce) - _direct_cost(args, kw, X2, U2, Nce)
+    assert abs(d_qp - d_dir) <= 1e-10 * max(1.0, abs(d_dir))
+    x0, f, fx, fu, Xp, Up = args[:6]
+    pred = f + np.einsum("ijrt,ijt->ijr", fu, U1 - Up)
+    pred[:, 1:] += np.einsum("ijrt,ijt->ijr", fx[:, 1:], X1[:, :-1] - Xp[:, :-1])
+    assert np.abs((prob.A @ z1 - prob.b) - (pred - X1).ravel()).max() < 1e-12
+    # consensus: the first Nc controls are literally shared
+    assert np.all(U1[:, :Nce] == U1[0:1, :Nce])
+
+
+def test_exact_solver_certificate_and_osqp_port_agree():
+    rng = np.random.default_rng(5)
+    args, kw = rand_problem(rng, 4, 8, 4, 2, box=0.15)
+    X, U, info = lqp.lqp_solve(*args, Nc=2, **kw)
+    cert = info["cert"]
+    assert cert.worst < 1e-9
+    assert np.sum(np.abs(U) > 0.15 - 1e-12) > 5  # constraints really are active
+    res = osqp_solve(info["prob"])  # reference settings: eps 1e-3
+    assert res.status == "solved"
+    assert np.abs(res.x - info["z"]).max() < 5e-2
+    res = osqp_solve(info["prob"], eps_abs=1e-9, eps_rel=1e-9, max_iter=100000)
+    assert np.abs(res.x - info["z"]).max() < 1e-6
+
+
+def test_sentinel_sweep_double_integrator():
+    """The reference sweeps present/absent combinations of every optional argument through its C
+    ABI (c_precompile.jl:52-100); same sweep through the oracle: each result must certify."""
+    args, kw, Nc = double_integrator(u_limit=0.4)
+    for ub in (False, True):
+        for xb in (False, True):
+            for s0 in (False, True):
+                for s in (False, True):
+                    k = dict(reg_x=kw["reg_x"], reg_u=kw["reg_u"])
+                    if ub:
+                        k.update(lu=kw["lu"], uu=kw["uu"])
+                    if xb:
+                        k.update(lx=kw["lx"], ux=kw["ux"])
+                    k["slew_reg"] = kw["slew_reg"] if s else np.full(1, np.nan)
+                    k["slew_reg0"] = kw["slew_reg0"] if s0 else np.full(1, np.nan)
+                    k["slew_um1"] = kw["slew_um1"] if s0 else np.full((1, 1), np.nan)
+                    X, U, info = lqp.lqp_solve(*args, Nc=Nc, **k)
+                    assert info["cert"].worst < 1e-9
+                    if ub:
+                        assert np.abs(U).max() <= 0.4 + 1e-9
+
+
+def test_dubins_matches_reference_autograd_where_well_conditioned():
+    """oracle/dubins.py vs the reference's torch-autograd values (golden): 1e-12 relative for
+    |u| >= 0.05; for tiny |u| the REFERENCE's own values are noise: the stable form
+    must stay within the reference's conditioning bound ~1e-16/|a|^3."""
+    g = np.load(os.path.join(GOLD, "dubins_lin.npz"))
+    rel = lambda a, b: np.abs(a - b).max() / max(1.0, np.abs(b).max())
+    f, fx, fu = dubins.car_f_fx_fu(g["generic_X"], g["generic_U"], g["generic_p"])
+    assert rel(f, g["generic_f"]) < 1e-12 and rel(fx, g["generic_fx"]) < 1e-12 and rel(fu, g["generic_fu"]) < 1e-12
+    fn, fxn, fun = dubins.car_f_fx_fu_naive(g["generic_X"], g["generic_U"], g["generic_p"])
+    assert rel(fn, g["generic_f"]) < 1e-12 and rel(fun, g["generic_fu"]) < 1e-12
+    for k, tol_x, tol_u in (("small_u", 1e-8, 1e-3), ("zero_u", 1e-8, 1e-1)):
+        f, fx, fu = dubins.car_f_fx_fu(g[k + "_X"], g[k + "_U"], g[k + "_p"])
+        assert rel(f, g[k + "_f"]) < tol_x and rel(fx, g[k + "_fx"]) < tol_x and rel(fu, g[k + "_fu"]) < tol_u
+
+
+def test_dubins_stable_form_against_high_precision():
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    rng = np.random.default_rng(3)
+    for u2 in (0.7, 1e-3, 1e-6, 0.0):
+        x, u, p = rng.standard_normal(4), np.array([0.3, u2]), np.array([0.9, 0.8, 0.3])
+        f, fx, fu = dubins.car_f_fx_fu(x, u, p)
+        vs, ws, T = [mp.mpf(float(v)) for v in p]
+        b, a = vs * mp.mpf(float(u[0])) + mp.mpf(1e-6), ws * (-mp.mpf(float(u[1])))
+        a = a + (mp.mpf(1e-6) if a >= 0 else -mp.mpf(1e-6))
+        x0, y0, v0, th = [mp.mpf(float(v)) for v in x]
+        ph = T * a + th
+        xp1 = x0 + (a * mp.sin(ph) * v0 + T * b * a * mp.sin(ph) + b * mp.cos(ph)) / a**2 - (mp.sin(th) * a * v0 + mp.cos(th) * b) / a**2
+        xp2 = y0 - (a * mp.cos(ph) * v0 - b * mp.sin(ph) + T * b * a * mp.cos(ph)) / a**2 + (mp.cos(th) * a * v0 - mp.sin(th) * b) / a**2
+        assert abs(float(xp1) - f[0]) < 1e-14 and abs(float(xp2) - f[1]) < 1e-14
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("scp_c1", dict(max_it=10, res_tol=-1.0)),
+    ("scp_consensus", dict(max_it=40, res_tol=1e-7, solver_settings=dict(Nc=1))),
+    ("scp_slew", dict(max_it=60, res_tol=1e-7, slew_rate=0.5, solver_settings=dict(Nc=2, slew_reg=0.3))),
+])
+def test_scp_loop_replays_reference_loop(name, kw):
+    """oracle.scp.scp_solve fed with the linearisations the REFERENCE loop consumed must reproduce
+    the reference loop's X, U and (obj, resid) history (golden generated by make_golden.py)."""
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    it = iter(range(len(d["lin_f"])))
+
+    def replay(X, U):
+        k = next(it)
+        return d["lin_f"][k], d["lin_fx"][k], d["lin_fu"][k]
+
+    extra = {}
+    if name == "scp_slew":
+        extra = dict(u0_slew=0.2 * np.ones((3, 2)), x_l=d["x_l"], x_u=d["x_u"])
+    X, U, data = scp.scp_solve(replay, d["Q"], d["R"], d["x0"], X_ref=d["X_ref"], U_ref=d["U_ref"], X_prev=d["X_prev"],
+                               U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"], reg_x=1.0, reg_u=1e-2, **kw, **extra)
+    hist = np.array([[h["obj"], h["resid"]] for h in data["hist"]])
+    assert len(hist) == len(d["hist"])
+    assert np.abs(X - d["X"]).max() < 1e-9 and np.abs(U - d["U"]).max() < 1e-9
+    assert np.abs(hist - d["hist"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("dims", [(3, 6, 4, 2, 2, True, 0.1), (1, 5, 2, 1, 0, True, 0.1), (4, 7, 3, 2, -1, True, 0.2),
+                                  (5, 8, 4, 2, 3, False, 0.3), (3, 6, 4, 2, 0, True, 0.1), (5, 8, 4, 2, 1, True, None)])
+def test_port_of_device_algorithm_matches_exact_oracle(dims):
+    """The NumPy port of the Riccati-ADMM + polish algorithm (what the kernels implement) reaches
+    the exact QP solution."""
+    M, N, n, m, Nc, slew, box = dims
+    rng = np.random.default_rng(7 + sum(dims[:5]))
+    args, kw = rand_problem(rng, M, N, n, m, slew, box)
+    Xo, Uo, _ = lqp.lqp_solve(*args, Nc=Nc, **kw)
+    X, U, info = riccati_admm.lqp_solve(*args, Nc=Nc, **kw)
+    assert np.abs(X - Xo).max() < 1e-8 and np.abs(U - Uo).max() < 1e-8
+    X, U, info = riccati_admm.lqp_solve(*args, Nc=Nc, settings=riccati_admm.Settings(polish=False), **kw)
+    assert np.abs(X - Xo).max() < 1e-6 and np.abs(U - Uo).max() < 1e-6
