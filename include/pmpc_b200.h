@@ -142,6 +142,16 @@ int pmpc_get_hist(pmpc_handle_t h, double *hist, int max_it);
 /* Device-time of the last solve kernel in milliseconds (CUDA events on the handle stream). */
 int pmpc_last_kernel_ms(pmpc_handle_t h, float *ms);
 
+/* Measurement helpers (bench.py): CUDA events recorded on the handle's own stream (torch's
+ * events do not see it), the number of kernels this library has launched in this process, and
+ * two micro-benchmarks that measure the roofline denominators on the device at hand:
+ * kind 0 = HBM copy bandwidth in GB/s (read + write bytes of a 1 GiB device-to-device copy
+ * kernel), kind 1 = fp64 FMA throughput in TFLOP/s (register-resident DFMA chains). */
+int pmpc_timer_start(pmpc_handle_t h);
+int pmpc_timer_stop(pmpc_handle_t h, float *ms);
+long long pmpc_launch_count(void);
+int pmpc_microbench(int device, int kind, double *result);
+
 /* ------------------------------------------------------------------------------------------
  * 3. int-returning variant of the compat entry with explicit settings and statistics.
  * ------------------------------------------------------------------------------------------ */

@@ -69,6 +69,10 @@ _SIG = {
     "pmpc_get_info": (C.c_int, [C.c_void_p, c_ll_p]),
     "pmpc_get_hist": (C.c_int, [C.c_void_p, _DP, C.c_int]),
     "pmpc_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pmpc_timer_start": (C.c_int, [C.c_void_p]),
+    "pmpc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pmpc_launch_count": (C.c_longlong, []),
+    "pmpc_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pmpc_lqp_solve": (C.c_int, [_DP, _DP, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_longlong] + [_DP] * 14
                        + [C.c_double, C.c_double] + [_DP] * 3 + [C.POINTER(Settings), c_ll_p]),
     "c_lqp_solve": (None, [_DP, _DP, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_longlong] + [_DP] * 14

@@ -15,6 +15,9 @@
 #include "../../include/pmpc_b200.h"
 #include "kernels.cuh"
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};  // kernels launched by this library (pmpc_launch_count)
+
 using namespace pmpc;
 
 namespace pmpc {
@@ -52,6 +55,7 @@ struct pmpc_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // pmpc_timer_start / pmpc_timer_stop
   DevProb pb{};
   Shape shape{};
   long long Nc_orig = 0;
@@ -158,9 +162,11 @@ __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __rest
   for (int r = 0; r < NX; ++r) {
     double cv = (r < n && fb) ? fb[r] : 0.0;
     for (int t = 0; t < NX; ++t) {
-      const double a = (r < n && t < n && j >= 1) ? fxb[(size_t)t * n + r] : 0.0;
+      const double a0 = (r < n && t < n) ? fxb[(size_t)t * n + r] : 0.0;
+      const double a = (j >= 1) ? a0 : 0.0;  // stage 1 is linearised at x0 itself: no fx term (lqp_utils.jl:288-296)
       pb.A[((size_t)j * NX * NX + r * NX + t) * P + g] = a;
       if (!c_is_f && j >= 1) cv -= a * pb.Xp[((size_t)(j - 1) * NX + t) * P + g];
+      if (c_is_f && j == 0) cv += a0 * pb.x0[(size_t)t * P + g];  // LTV: f_1 = A_1 x0 + B_1 u + c_1
     }
     for (int t = 0; t < NU; ++t) {
       const double b = (r < n && t < m) ? fub[(size_t)t * n + r] : 0.0;
@@ -264,6 +270,8 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
+  CU(cudaEventCreate(&h->tev0));
+  CU(cudaEventCreate(&h->tev1));
   h->shape = sh;
   h->Nc_orig = Nc;
   h->Ptot = B * M;
@@ -329,6 +337,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaMalloc(&h->lin_fx, h->Ptot * N * xdim * xdim * sizeof(double)));
   CU(cudaMalloc(&h->lin_fu, h->Ptot * N * xdim * udim * sizeof(double)));
   fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);
+  ++g_launches;
   CU(cudaGetLastError());
   *out = h;
   return PMPC_OK;
@@ -340,6 +349,7 @@ int pmpc_destroy(pmpc_handle_t h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->tev0); cudaEventDestroy(h->tev1);
   cudaStreamDestroy(h->stream);
   delete h;
   return PMPC_OK;
@@ -351,6 +361,7 @@ int pmpc_set_settings(pmpc_handle_t h, const pmpc_settings* s) {
   apply_settings(h);
   CU(cudaSetDevice(h->device));
   fill_kernel<<<nblk(h->pb.B), 256, 0, h->stream>>>(h->pb.rho, h->pb.B, h->pb.rho0);
+  ++g_launches;
   CU(cudaGetLastError());
   return PMPC_OK;
 }
@@ -371,6 +382,7 @@ static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, in
     if (rc) return rc;
   }
   pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, pb.P, pb.N, Ei, Eo, fill);
+  ++g_launches;
   CU(cudaGetLastError());
   if (host) CU(cudaStreamSynchronize(h->stream));  // staging buffer is reused by the next upload
   return PMPC_OK;
@@ -422,14 +434,17 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   if (slew0 && (rc = up2(slew_um1, Pt * m, &dum1))) return rc;
   pack_cost_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, dQ, dR, dXr, dUr, ds, ds0, dum1, (int)Pt,
                                                          h->Nc_orig >= 1 ? 1 : 0);
+  ++g_launches;
   CU(cudaGetLastError());
   CU(cudaFreeAsync(extra, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(nullptr, pb.x0, (int)Pt, pb.P, 0, NX, 0.0);
+  ++g_launches;
   {
     double* d;
     if ((rc = upload(h, x0, Pt * n, 0, &d))) return rc;
     pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(d, pb.x0, (int)Pt, pb.P, n, NX, 0.0);
+    ++g_launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
   }
@@ -460,6 +475,7 @@ int pmpc_set_warm_start(pmpc_handle_t h, const double* X_prev, const double* U_p
   CU(cudaMemsetAsync(pb.actc, 0, (size_t)pb.B * pb.D + 32, h->stream));
   CU(cudaMemsetAsync(pb.actcn, 0, (size_t)pb.B * pb.D + 32, h->stream));
   fill_kernel<<<nblk(pb.B), 256, 0, h->stream>>>(pb.rho, pb.B, pb.rho0);
+  ++g_launches;
   CU(cudaGetLastError());
   return PMPC_OK;
 }
@@ -475,6 +491,7 @@ int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double* params, size_t np
     int rc;
     if ((rc = upload(h, params, h->Ptot * 3, 0, &d))) return rc;
     pack_particle_kernel<<<nblk(h->Ptot), 256, 0, h->stream>>>(d, pb.dynp, (int)h->Ptot, pb.P, 3, 4, 0.0);
+    ++g_launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     pb.dyn_kind = DYN_DUBINS;
@@ -487,6 +504,7 @@ int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double* params, size_t np
 
 static int set_affine(pmpc_handle_t h, const double* f, const double* fx, const double* fu, int c_is_f) {
   if (!h || !fx || !fu) return fail(PMPC_ERR_BAD_ARG, "fx, fu required");
+  if (!h->have_problem) return fail(PMPC_ERR_STATE, "pmpc_set_problem first (the linearisation is packed against x0, X_prev, U_prev)");
   CU(cudaSetDevice(h->device));
   DevProb& pb = h->pb;
   const size_t Pt = h->Ptot, N = pb.N, n = pb.n, m = pb.m;
@@ -501,6 +519,7 @@ static int set_affine(pmpc_handle_t h, const double* f, const double* fx, const 
     df = h->lin_f;
   }
   pack_lin_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, h->shape.NX, h->shape.NU, df, dfx, dfu, (int)Pt, c_is_f);
+  ++g_launches;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   pb.dyn_kind = DYN_AFFINE;
@@ -523,6 +542,7 @@ int pmpc_linearize(pmpc_handle_t h) {
   CU(cudaSetDevice(h->device));
   linearize_dubins_kernel<<<nblk(h->Ptot * h->pb.N), 256, 0, h->stream>>>(h->pb, h->lin_f, h->lin_fx, h->lin_fu,
                                                                            (int)h->Ptot);
+  ++g_launches;
   CU(cudaGetLastError());
   return PMPC_OK;
 }
@@ -553,6 +573,7 @@ static int launch(pmpc_handle_t h) {
     default: return fail(PMPC_ERR_UNSUPPORTED, "no kernel for this shape");
   }
   if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  ++g_launches;
   CU(cudaEventRecord(h->ev1, h->stream));
   h->solved = true;
   return PMPC_OK;
@@ -608,7 +629,9 @@ int pmpc_get_solution(pmpc_handle_t h, double* X, double* U) {
   double* dX = h->stage;
   double* dU = h->stage + Pt * N * pb.n;
   unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, pb.P, pb.N, h->shape.NX, pb.n);
+  ++g_launches;
   unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.U, dU, (int)Pt, pb.P, pb.N, h->shape.NU, pb.m);
+  ++g_launches;
   CU(cudaGetLastError());
   if (X) CU(cudaMemcpyAsync(X, dX, Pt * N * pb.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (U) CU(cudaMemcpyAsync(U, dU, Pt * N * pb.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -645,6 +668,24 @@ int pmpc_get_hist(pmpc_handle_t h, double* hist, int max_it) {
 int pmpc_last_kernel_ms(pmpc_handle_t h, float* ms) {
   if (!h || !ms) return fail(PMPC_ERR_BAD_ARG, "null");
   *ms = h->last_ms;
+  return PMPC_OK;
+}
+
+long long pmpc_launch_count(void) { return g_launches.load(); }
+
+int pmpc_timer_start(pmpc_handle_t h) {
+  if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->tev0, h->stream));
+  return PMPC_OK;
+}
+
+int pmpc_timer_stop(pmpc_handle_t h, float* ms) {
+  if (!h || !ms) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->tev1, h->stream));
+  CU(cudaEventSynchronize(h->tev1));
+  CU(cudaEventElapsedTime(ms, h->tev0, h->tev1));
   return PMPC_OK;
 }
 

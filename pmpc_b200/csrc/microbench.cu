@@ -1,0 +1,79 @@
+// Roofline denominators measured on the device at hand (pmpc_microbench, include/pmpc_b200.h):
+// a STREAM-style copy for HBM bandwidth and register-resident DFMA chains for the fp64 pipe.
+#include <cuda_runtime.h>
+
+#include "../../include/pmpc_b200.h"
+
+namespace {
+
+__global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+
+// 8 independent FMA chains per thread: enough ILP to cover the DFMA latency at 8+ warps per SMSP.
+__global__ void dfma_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace
+
+extern "C" int pmpc_microbench(int device, int kind, double* result) {
+  if (!result) return PMPC_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return PMPC_ERR_NO_DEVICE; }
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PMPC_ERR_CUDA;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  int rc = PMPC_OK;
+  if (kind == 0) {
+    const size_t bytes = (size_t)1 << 30, n = bytes / sizeof(double2);
+    double2 *a = nullptr, *b = nullptr;
+    if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&b, bytes) != cudaSuccess) { cudaFree(a); return PMPC_ERR_CUDA; }
+    cudaMemset(a, 1, bytes);
+    for (int rep = 0; rep < 8; ++rep) {
+      cudaEventRecord(e0);
+      copy_kernel<<<prop.multiProcessorCount * 16, 512>>>(a, b, n);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep >= 2 && ms < best) best = ms;
+    }
+    *result = 2.0 * (double)bytes / (best * 1e-3) / 1e9;
+    cudaFree(a);
+    cudaFree(b);
+  } else if (kind == 1) {
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 14;
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return PMPC_ERR_CUDA;
+    for (int rep = 0; rep < 6; ++rep) {
+      cudaEventRecord(e0);
+      dfma_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep >= 2 && ms < best) best = ms;
+    }
+    *result = 2.0 * 8.0 * (double)iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    cudaFree(out);
+  } else {
+    rc = PMPC_ERR_BAD_ARG;
+  }
+  if (cudaGetLastError() != cudaSuccess) rc = PMPC_ERR_CUDA;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}

@@ -153,6 +153,16 @@ class DeviceSolver:
         check(self.lib.pmpc_get_hist(self._h, dptr(buf), int(max_it)), "get_hist")
         return dict(obj=buf[0], resid=buf[1], admm_iters=buf[2], kkt=buf[3])
 
+    def timer_start(self):
+        """CUDA event on the handle's stream (the stream every kernel of this handle runs on)."""
+        check(self.lib.pmpc_timer_start(self._h), "timer_start")
+
+    def timer_stop(self) -> float:
+        """Milliseconds of device time since :meth:`timer_start` (records, synchronises)."""
+        ms = C.c_float()
+        check(self.lib.pmpc_timer_stop(self._h, C.byref(ms)), "timer_stop")
+        return float(ms.value)
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         check(self.lib.pmpc_last_kernel_ms(self._h, C.byref(ms)), "last_kernel_ms")
