@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-SCP solve path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPUs
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): Dubins car, xdim=4, udim=2, N=50, M=128
+perturbed-dynamics particles, Nc=1 shared control, box control limits, res_tol=1e-5, max_it=100.
+One *step* = one batch of B independent C2 problems (problem 0 is exactly the seed-1 fixture, the
+others perturb x0 and the particle parameters) solved to the stop rule; the unit is "solves".
+Under torchrun every rank owns its own batch of B problems (weak scaling, no data-path collective:
+SURVEY.md 8e case 1).
+
+`value`  : solves/s with the inputs already resident in HBM (per step: device-side warm-start reset
+           + the SCP kernel), timed with CUDA events on the solver's stream, max over ranks.
+`e2e`    : the same batch through the public API `pmpc_b200.solve_batch` with HOST arrays: H2D of
+           every input, the solve, D2H of X, U and the per-problem counters, wall clock, max over ranks.
+`roofline`: the SCP kernel against the measured HBM bandwidth, algorithmic bytes per DESIGN.md.
+`cpu_baseline`: the reference algorithm restated (oracle/, OSQP port at the reference's default
+           settings) on ONE host core, bounded sample — reported beside, not the target.
+Only the cpu_baseline / --impl reference legs touch `oracle/`; the product path has no CPU fallback.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+M, N, NX, NU, NC = 128, 50, 4, 2, 1
+MAX_IT, RES_TOL = 100, 1e-5
+METRIC = "particle-SCP solves/sec (Dubins N=50 M=128 Nc=1, box control limits, res_tol 1e-5)"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def c2_iters_fixture():
+    with open(os.path.join(ROOT, "tests", "golden", "c2_reference_iters.json")) as fh:
+        return json.load(fh)
+
+
+def make_batch(B: int, seed: int):
+    """B C2-shaped problems as host arrays (Python layout of pmpc.solve with a leading B axis)."""
+    from fixtures import config_c2
+
+    d0, p0 = config_c2(M, N)
+    rng = np.random.default_rng(1000 + seed)
+    p = np.stack([rng.uniform(0.7, 1.0, (B, M)), rng.uniform(0.7, 1.0, (B, M)), np.full((B, M), 0.3)], -1)
+    x0 = np.repeat(1.0 + 0.05 * rng.standard_normal((B, 1, NX)), M, axis=1)
+    if seed == 0:
+        p[0], x0[0] = p0, d0["x0"]
+    tile = lambda a: np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))
+    arrs = dict(Q=tile(d0["Q"]), R=tile(d0["R"]), x0=np.ascontiguousarray(x0), X_ref=tile(d0["X_ref"]),
+                U_ref=tile(d0["U_ref"]), X_prev=tile(d0["X_prev"]), U_prev=tile(d0["U_prev"]), u_l=tile(d0["u_l"]),
+                u_u=tile(d0["u_u"]))
+    return arrs, np.ascontiguousarray(p), d0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                d = json.load(fh)
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic work per (particle, stage), SURVEY.md 8(d) / DESIGN.md "roofline"
+def alg_bytes_flops(info, n=NX, m=NU, nparam=3):
+    """Streaming model: every (re)factorisation streams Q, fx, fu, R in and K, P-sized factors out; every
+    vector pass (ADMM iteration or polish solve) streams fx, fu, K, E and the stage vectors; every SCP
+    iteration streams the linearisation in/out once."""
+    F = info["factorizations"].astype(np.float64)
+    I = (info["admm_iters"] + info["polish_passes"]).astype(np.float64)
+    S = info["scp_iters"].astype(np.float64)
+    b_fac = 8 * (3 * n * n + 2 * n * m + m * m)
+    b_vec = 8 * (n * n + 2 * n * m + m * m) + 16 * (n + m)
+    b_lin = 8 * (n + m + nparam) + 8 * (n + n * n + n * m)
+    f_fac = 4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0
+    f_vec = 6 * n * n + 8 * n * m + 2 * m * m
+    per = M * N
+    return float(per * (F * b_fac + I * b_vec + S * b_lin).sum()), float(per * (F * f_fac + I * f_vec).sum())
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_sample(seed_and_its):
+    """Worker of the CPU legs: the first `its` SCP iterations of one C2 problem with the reference's
+    solver restated (oracle.osqp_port at OSQP 0.6.2 defaults).  Returns seconds."""
+    seed, its = seed_and_its
+    from oracle import dubins, scp as oscp
+
+    arrs, p, d0 = make_batch(1, seed)
+    t = time.perf_counter()
+    X, U, data = oscp.scp_solve(dubins.make_f_fx_fu_fn(p[0]), arrs["Q"][0], arrs["R"][0], arrs["x0"][0],
+                                X_ref=arrs["X_ref"][0], U_ref=arrs["U_ref"][0], X_prev=arrs["X_prev"][0],
+                                U_prev=arrs["U_prev"][0], u_l=arrs["u_l"][0], u_u=arrs["u_u"][0], reg_x=d0["reg_x"],
+                                reg_u=d0["reg_u"], max_it=its, res_tol=RES_TOL, solver_settings=d0["solver_settings"],
+                                qp="osqp")
+    assert X is not None and len(data["hist"]) == its
+    return time.perf_counter() - t
+
+
+def reference_arm(args):
+    """The reference's CPU algorithm for the path (oracle port; the Julia/OSQP stack itself is not
+    buildable in this image: DESIGN.md) on all host cores.  Each step: every worker process runs the
+    first `sample_its` SCP iterations of its own C2 problem; a full solve takes `full_its` iterations
+    (tests/golden/c2_reference_iters.json, measured with the same code), so
+    solves/s = workers * (sample_its / full_its) / step_time."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    cores = os.cpu_count() or 1
+    full_its = c2_iters_fixture()["osqp_port_scp_iters"]
+    sample_its = args.ref_sample_its
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        run = lambda: (lambda t0: (pool.map(cpu_sample, [(s, sample_its) for s in range(cores)]), time.perf_counter() - t0))(time.perf_counter())
+        for _ in range(args.warmup):
+            run()
+        times = [run()[1] for _ in range(args.steps)]
+    step = float(np.mean(times))
+    value = cores * (sample_its / full_its) / step
+    sample = (f"{cores} worker processes, each the first {sample_its} of {full_its} SCP iterations of one C2 problem "
+              f"(OSQP restated at reference defaults eps=1e-3), scaled to full solves")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 Dubins N=50 M=128 Nc=1 particle consensus", "host_cores": cores,
+                       "reference": "restated CPU baseline (oracle/), not PMPC.jl: Julia/OSQP absent from the image"},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=592, help="independent C2 problems per GPU per step")
+    ap.add_argument("--latency-solves", type=int, default=20)
+    ap.add_argument("--cpu-sample-its", type=int, default=8)
+    ap.add_argument("--ref-sample-its", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    import pmpc_b200
+    from pmpc_b200 import DeviceSolver, _lib, parallel
+
+    lib = _lib.load()
+    if lib.pmpc_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — pmpc_b200 has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch
+
+        torch.cuda.set_device(local)
+        dist = parallel.init_process_group("nccl")
+    dev_t = None
+    if dist is not None:
+        import torch
+
+        dev_t = torch.device("cuda", local)
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    arrs, p, d0 = make_batch(B, rank)
+    ds = DeviceSolver(M, N, NX, NU, NC, B=B, device=local)
+    ds.set_problem(arrs["x0"], arrs["Q"], arrs["R"], arrs["X_ref"], arrs["U_ref"], None, None, arrs["u_l"], arrs["u_u"],
+                   d0["reg_x"], d0["reg_u"], np.zeros(B * M))
+    ds.set_dubins(p)
+
+    def device_step():
+        ds.set_warm_start(None, None)  # X_prev = U_prev = 0 (the fixture's start), ADMM/active-set state reset
+        ds.scp_solve_async(MAX_IT, RES_TOL)
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for _ in range(W):
+        device_step()
+    ds.sync()
+    barrier()
+    launches0 = lib.pmpc_launch_count()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        ds.timer_start()
+        kernel_ms = []
+        for _ in range(K):
+            device_step()
+        ms = ds.timer_stop()
+        wall = time.perf_counter() - t0
+    launches = lib.pmpc_launch_count() - launches0
+    barrier()
+    ms = parallel.reduce_max(ms, dist, dev_t)
+    launches = int(parallel.reduce_sum(launches, dist, dev_t))
+    info = ds.info()
+    X, U = ds.solution()
+    hist = ds.hist(int(info["scp_iters"].max()))
+    last_res = np.array([hist["resid"][info["scp_iters"][b] - 1, b] for b in range(B)])
+    ok = bool((info["status"] == 0).all() and (last_res < RES_TOL).all() and np.isfinite(X).all()
+              and np.abs(U).max() <= 1 + 1e-9 and np.all(U[:, :, 0] == U[:, :1, 0]))
+    kernel_ms = ds.last_kernel_ms()  # the last step's SCP kernel alone
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the SCP kernel) -----------------------------------------
+    peak, peak_src = hbm_peak()
+    abytes, aflops = alg_bytes_flops(info)
+    roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scp_kernel<4,2,grouped>",
+                "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,
+                "fp64_tflops_achieved": aflops / (kernel_ms * 1e-3) / 1e12}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            tr = json.load(fh)
+        if tr.get("batch") == B:
+            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+    if rank == 0:
+        for kind, key in ((0, "hbm_copy_gbs_here"), (1, "fp64_fma_tflops_here")):
+            r = C.c_double()
+            if lib.pmpc_microbench(local, kind, C.byref(r)) == 0:
+                roofline[key] = r.value
+
+    # ---- end to end through the public API with host buffers ---------------------------------------
+    def e2e_step(solver):
+        return pmpc_b200.solve_batch(p, arrs["Q"], arrs["R"], arrs["x0"], arrs["X_ref"], arrs["U_ref"], arrs["X_prev"],
+                                     arrs["U_prev"], None, None, arrs["u_l"], arrs["u_u"], max_it=MAX_IT, res_tol=RES_TOL,
+                                     reg_x=d0["reg_x"], reg_u=d0["reg_u"], slew_rate=0.0, Nc=NC, device=local, solver=solver)
+
+    for _ in range(min(W, 2)):
+        Xe, Ue, infoe, ds = e2e_step(ds)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        Xe, Ue, infoe, ds = e2e_step(ds)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = parallel.reduce_max(e2e_s, dist, dev_t)
+    h2d = sum(a.nbytes for a in arrs.values()) + p.nbytes + 8 * B * M  # inputs + params + slew vector
+    d2h = Xe[:, :, 1:].nbytes + Ue.nbytes + 8 * 8 * B
+    e2e = {"value": world * B * K / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": 1e3 * e2e_s / K, "api": "pmpc_b200.solve_batch (host numpy arrays in, host arrays out)"}
+    ok = ok and np.array_equal(Xe[:, :, 1:], X.reshape(Xe[:, :, 1:].shape)) and bool((infoe["status"] == 0).all())
+
+    # ---- single-solve latency through pmpc_b200.solve (the call a reference user makes) -----------
+    lat = []
+    if rank == 0 and args.latency_solves > 0:
+        car = pmpc_b200.DubinsCar(p[0])
+        kw = dict(X_ref=arrs["X_ref"][0], U_ref=arrs["U_ref"][0], X_prev=arrs["X_prev"][0], U_prev=arrs["U_prev"][0],
+                  u_l=arrs["u_l"][0], u_u=arrs["u_u"][0], reg_x=d0["reg_x"], reg_u=d0["reg_u"], max_it=MAX_IT,
+                  res_tol=RES_TOL, solver_settings=dict(d0["solver_settings"]))
+        for i in range(args.latency_solves + 3):
+            t0 = time.perf_counter()
+            X1, U1, data1 = pmpc_b200.solve(car, arrs["Q"][0], arrs["R"][0], arrs["x0"][0], **kw)
+            dt = time.perf_counter() - t0
+            kw["solver_settings"]["_device_solver"] = data1["device_solver"]
+            if i >= 3:
+                lat.append(dt)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fx = c2_iters_fixture()
+        its = args.cpu_sample_its
+        sec = cpu_sample((0, its))
+        cpu = {"value": 1.0 / (sec * fx["osqp_port_scp_iters"] / its), "unit": "solves/s", "cores": 1, "kind": "port",
+               "sample": f"first {its} of {fx['osqp_port_scp_iters']} SCP iterations of C2 problem 0 with the reference's "
+                         f"solver restated (oracle.osqp_port, OSQP 0.6.2 defaults), {sec:.1f} s, scaled to a full solve"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "C2 Dubins N=50 M=128 Nc=1 particle consensus", "problems_per_gpu_per_step": B,
+                           "max_it": MAX_IT, "res_tol": RES_TOL, "l2": "working set %.1f GB per GPU > 126 MB L2" % (
+                               B * M * N * 135 * 8 / 1e9), "parallelism": "problem batch sharded, no collective"},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu, "parity_ok": ok,
+                "scp_iters": {"min": int(info["scp_iters"].min()), "max": int(info["scp_iters"].max()),
+                              "problem0": int(info["scp_iters"][0]), "reference_port": c2_iters_fixture()},
+                "qp_passes_per_solve": {"factorizations": float(info["factorizations"].mean()),
+                                        "polish": float(info["polish_passes"].mean()), "admm": float(info["admm_iters"].mean())},
+                "latency_ms": ({"p50": 1e3 * float(np.median(lat)), "min": 1e3 * float(min(lat)), "n": len(lat),
+                                "api": "pmpc_b200.solve, one C2 problem, host arrays"} if lat else None),
+                "wall_ms_per_step": 1e3 * wall / K}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -10,6 +10,7 @@ from .scp_mpc import (  # noqa: F401
 from .static_backend import aff_solve, is_precompiled_backend_available, lqp_solve  # noqa: F401
 from .dynamics import BuiltinDynamics, DubinsCar, LTV  # noqa: F401
 from .handle import DeviceSolver  # noqa: F401
+from .batch import solve_batch  # noqa: F401
 from .problem_struct import Problem  # noqa: F401
 
 """Keyword-compatible arguments in the solver scp solve call (reference pmpc/__init__.py:4-33)."""

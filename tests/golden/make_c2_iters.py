@@ -1,0 +1,25 @@
+"""Generates tests/golden/c2_reference_iters.json: how many SCP iterations the CPU restatement of the
+reference needs on BASELINE config C2 (Dubins N=50 M=128 Nc=1, seed 1) to reach res_tol=1e-5, with
+(a) the reference's solver restated at its default settings (oracle.osqp_port, eps=1e-3) and
+(b) the exact QP oracle (oracle.lqp).  bench.py scales its bounded CPU samples with (a).
+Takes ~2 x 110 s on one core:  python tests/golden/make_c2_iters.py"""
+import json, os, sys, time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, os.path.join(HERE, ".."))
+from fixtures import config_c2
+from oracle import dubins, scp as oscp
+
+out = {}
+for key, qp in (("osqp_port", "osqp"), ("exact", "exact")):
+    d, p = config_c2()
+    ss = d.pop("solver_settings")
+    t = time.time()
+    X, U, data = oscp.scp_solve(dubins.make_f_fx_fu_fn(p), d.pop("Q"), d.pop("R"), d.pop("x0"), solver_settings=ss, qp=qp, **d)
+    out[key + "_scp_iters"] = len(data["hist"])
+    out[key + "_seconds_1core"] = round(time.time() - t, 1)
+    out[key + "_final_resid"] = float(data["hist"][-1]["resid"])
+    out[key + "_final_obj"] = float(data["hist"][-1]["obj"])
+json.dump(out, open(os.path.join(HERE, "c2_reference_iters.json"), "w"), indent=1)
+print(out)
