@@ -84,6 +84,7 @@ typedef struct {
   int polish_iters;    /* primal-dual active-set refinements / attempt  (8)            */
   int adapt_rho;       /*                                               (1)            */
   int warm_start;      /* carry (w,y,active set) across SCP iterations  (1)            */
+  int fused;           /* fused 2-sweep polish passes with on-the-fly linearisation (1) */
 } pmpc_settings;
 
 void pmpc_default_settings(pmpc_settings *s);
@@ -134,7 +135,7 @@ int pmpc_sync(pmpc_handle_t h);
 int pmpc_get_solution(pmpc_handle_t h, double *X, double *U);
 /* Per problem b: info[b*8 + k], k = 0 scp_iters, 1 total ADMM iterations, 2 factorisations,
  * 3 polish passes, 4 status (0 ok, 1 NaN failure, 2 ADMM hit max_iter in some QP),
- * 5 QPs finished by polish, 6 QPs finished by ADMM tolerance, 7 reserved. */
+ * 5 QPs finished by polish, 6 QPs finished by ADMM tolerance, 7 sweeps over the horizon. */
 int pmpc_get_info(pmpc_handle_t h, long long *info);
 /* hist (4, max_it, B): obj, resid, admm_iters(it), kkt_violation of the accepted QP solution. */
 int pmpc_get_hist(pmpc_handle_t h, double *hist, int max_it);

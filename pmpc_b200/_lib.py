@@ -35,6 +35,7 @@ class Settings(C.Structure):
         ("polish_iters", C.c_int),
         ("adapt_rho", C.c_int),
         ("warm_start", C.c_int),
+        ("fused", C.c_int),
     ]
 
 

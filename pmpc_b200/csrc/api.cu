@@ -226,6 +226,7 @@ void pmpc_default_settings(pmpc_settings* s) {
   s->polish_iters = 8;
   s->adapt_rho = 1;
   s->warm_start = 1;
+  s->fused = 1;
 }
 
 const char* pmpc_last_error(void) { return g_err.c_str(); }
@@ -248,6 +249,7 @@ static void apply_settings(pmpc_handle_t h) {
   pb.check_every = s.check_every < 1 ? 1 : s.check_every; pb.polish = s.polish;
   pb.polish_iters = s.polish_iters < 1 ? 1 : s.polish_iters; pb.adapt_rho = s.adapt_rho;
   pb.warm_start = s.warm_start;
+  pb.fused = s.fused;
 }
 
 int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, size_t xdim, size_t udim,

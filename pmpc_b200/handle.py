@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import check, dptr, f64c, mat_cm
 
 INFO_FIELDS = ("scp_iters", "admm_iters", "factorizations", "polish_passes", "status", "qp_by_polish", "qp_by_admm",
-               "reserved")
+               "sweeps")
 
 
 class DeviceSolver:
