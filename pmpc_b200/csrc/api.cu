@@ -71,33 +71,45 @@ struct pmpc_handle_s {
 };
 
 // ---------------------------------------------------------------------------------------------
-// packing kernels: reference layout (particle-major, column-major blocks) -> SoA [j][e][P]
-// one thread per (g, j); g fastest so the SoA stores are coalesced.
-__global__ void pack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, int N,
-                                int Ei, int Eo, double fill) {
+// packing kernels: reference layout (particle-major, column-major blocks) -> warp-tiled SoA
+// (solver.cuh "DATA LAYOUT").  One thread per (flat particle gf = b*M + i, stage j), gf fastest so
+// that the tile stores are coalesced.
+struct Lay { int M, Mpad, N; };
+__device__ __forceinline__ size_t slot_of(int gf, Lay L) { return (size_t)(gf / L.M) * L.Mpad + (size_t)(gf % L.M); }
+__device__ __forceinline__ size_t tix(size_t slot, Lay L, int j, int E, int e) {
+  return (((slot >> 5) * (size_t)L.N + (size_t)j) * (size_t)E + (size_t)e) * 32 + (slot & 31);
+}
+
+__global__ void pack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, Lay L, int Ei, int Eo,
+                                double fill) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = L.N;
   if (idx >= (size_t)Ptot * N) return;
-  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const size_t sl = slot_of(gf, L);
   for (int e = 0; e < Eo; ++e) {
     double v = fill;
-    if (in != nullptr && e < Ei) v = in[((size_t)g * N + j) * Ei + e];
-    out[((size_t)j * Eo + e) * P + g] = v;
+    if (in != nullptr && e < Ei) v = in[((size_t)gf * N + j) * Ei + e];
+    out[tix(sl, L, j, Eo, e)] = v;
   }
 }
 
-__global__ void unpack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, int N,
-                                  int Ei, int Eo) {
+__global__ void unpack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, Lay L, int Ei,
+                                  int Eo) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = L.N;
   if (idx >= (size_t)Ptot * N) return;
-  const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
-  for (int e = 0; e < Eo; ++e) out[((size_t)g * N + j) * Eo + e] = in[((size_t)j * Ei + e) * P + g];
+  const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const size_t sl = slot_of(gf, L);
+  for (int e = 0; e < Eo; ++e) out[((size_t)gf * N + j) * Eo + e] = in[tix(sl, L, j, Ei, e)];
 }
 
-__global__ void pack_particle_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, int Ei,
-                                     int Eo, double fill) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= Ptot) return;
-  for (int e = 0; e < Eo; ++e) out[(size_t)e * P + g] = (in != nullptr && e < Ei) ? in[(size_t)g * Ei + e] : fill;
+__global__ void pack_particle_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, Lay L,
+                                     int Ei, int Eo, double fill) {
+  const int gf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gf >= Ptot) return;
+  const size_t sl = slot_of(gf, L);
+  for (int e = 0; e < Eo; ++e) out[(size_t)e * P + sl] = (in != nullptr && e < Ei) ? in[(size_t)gf * Ei + e] : fill;
 }
 
 // cost terms (lqp_utils.jl:26-40, 130-142, 164-214): Qs = triu(Q) mirrored + reg_x I, etc.
@@ -109,6 +121,8 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
   const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const Lay L{pb.M, pb.Mpad, pb.N};
+  const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
   const double* Qb = Q + ((size_t)g * N + j) * n * n;  // column-major: Q[r,t] = Qb[t*n + r]
   const double* Rb = R + ((size_t)g * N + j) * m * m;
@@ -119,13 +133,13 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
     for (int t = r; t < NX; ++t) {
       double v = (r < n && t < n) ? Qb[(size_t)t * n + r] : 0.0;
       if (r == t) v += (r < n) ? pb.reg_x : 1.0;
-      pb.Qs[((size_t)j * NQ + pk(r, t, NX)) * P + g] = v;
+      pb.Qs[tix(sl, L, j, NQ, pk(r, t, NX))] = v;
     }
     double acc = 0.0;
     if (r < n && xr)
       for (int t = 0; t < n; ++t) acc += Qb[(size_t)t * n + r] * xr[t];
-    pb.qref[((size_t)j * NX + r) * P + g] = acc;
-    pb.xref[((size_t)j * NX + r) * P + g] = (r < n && xr) ? xr[r] : 0.0;
+    pb.qref[tix(sl, L, j, NX, r)] = acc;
+    pb.xref[tix(sl, L, j, NX, r)] = (r < n && xr) ? xr[r] : 0.0;
   }
   const double sv = s ? s[g] : 0.0, s0v = s0 ? s0[g] : 0.0;
   const double extra = (j == 0 ? s0v : 0.0) + ((N == 1 && j == 0) ? sv : 0.0);  // lqp_utils.jl:31-37
@@ -133,19 +147,20 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
     for (int b = a; b < NU; ++b) {
       double v = (a < m && b < m) ? Rb[(size_t)b * m + a] : 0.0;
       if (a == b) v += (a < m) ? (pb.reg_u + extra) : 1.0;
-      pb.Rs[((size_t)j * NR + pk(a, b, NU)) * P + g] = v;
+      pb.Rs[tix(sl, L, j, NR, pk(a, b, NU))] = v;
     }
     double acc = 0.0;
     if (a < m && ur)
       for (int t = 0; t < m; ++t) acc += Rb[(size_t)t * m + a] * ur[t];
     if (a < m && j == 0 && quirk_keep_um1 && um1) acc += s0v * um1[(size_t)g * m + a];  // lqp_utils.jl:165
-    pb.rref[((size_t)j * NU + a) * P + g] = acc;
-    pb.uref[((size_t)j * NU + a) * P + g] = (a < m && ur) ? ur[a] : 0.0;
+    pb.rref[tix(sl, L, j, NU, a)] = acc;
+    pb.uref[tix(sl, L, j, NU, a)] = (a < m && ur) ? ur[a] : 0.0;
   }
   if (j == 0) {
-    pb.slew[g] = sv;
-    pb.rdiag0[g] = extra;
+    pb.slew[sl] = sv;
+    pb.rdiag0[sl] = extra;
   }
+  (void)P;
 }
 
 // caller-supplied linearisation -> A, B, c   (lqp_utils.jl:231-300: c_j = f_j - fu_j ubar_j - fx_j xbar_{j-1})
@@ -155,6 +170,8 @@ __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __rest
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
   const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const Lay L{pb.M, pb.Mpad, pb.N};
+  const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
   const double* fxb = fx + ((size_t)g * N + j) * n * n;  // fx[r,t] = fxb[t*n + r]
   const double* fub = fu + ((size_t)g * N + j) * n * m;  // fu[r,t] = fub[t*n + r]
@@ -164,16 +181,16 @@ __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __rest
     for (int t = 0; t < NX; ++t) {
       const double a0 = (r < n && t < n) ? fxb[(size_t)t * n + r] : 0.0;
       const double a = (j >= 1) ? a0 : 0.0;  // stage 1 is linearised at x0 itself: no fx term (lqp_utils.jl:288-296)
-      pb.A[((size_t)j * NX * NX + r * NX + t) * P + g] = a;
-      if (!c_is_f && j >= 1) cv -= a * pb.Xp[((size_t)(j - 1) * NX + t) * P + g];
-      if (c_is_f && j == 0) cv += a0 * pb.x0[(size_t)t * P + g];  // LTV: f_1 = A_1 x0 + B_1 u + c_1
+      pb.A[tix(sl, L, j, NX * NX, r * NX + t)] = a;
+      if (!c_is_f && j >= 1) cv -= a * pb.Xp[tix(sl, L, j - 1, NX, t)];
+      if (c_is_f && j == 0) cv += a0 * pb.x0[(size_t)t * P + sl];  // LTV: f_1 = A_1 x0 + B_1 u + c_1
     }
     for (int t = 0; t < NU; ++t) {
       const double b = (r < n && t < m) ? fub[(size_t)t * n + r] : 0.0;
-      pb.Bm[((size_t)j * NX * NU + r * NU + t) * P + g] = b;
-      if (!c_is_f) cv -= b * pb.Up[((size_t)j * NU + t) * P + g];
+      pb.Bm[tix(sl, L, j, NX * NU, r * NU + t)] = b;
+      if (!c_is_f) cv -= b * pb.Up[tix(sl, L, j, NU, t)];
     }
-    pb.c[((size_t)j * NX + r) * P + g] = cv;
+    pb.c[tix(sl, L, j, NX, r)] = cv;
   }
 }
 
@@ -184,11 +201,13 @@ __global__ void linearize_dubins_kernel(DevProb pb, double* __restrict__ f, doub
   const int N = pb.N;
   if (idx >= (size_t)Ptot * N) return;
   const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  const Lay L{pb.M, pb.Mpad, pb.N};
+  const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
   double x[4], u[2], fo[4], fxo[16], fuo[8];
-  for (int e = 0; e < 4; ++e) x[e] = (j == 0) ? pb.x0[(size_t)e * P + g] : pb.Xp[((size_t)(j - 1) * 4 + e) * P + g];
-  for (int e = 0; e < 2; ++e) u[e] = pb.Up[((size_t)j * 2 + e) * P + g];
-  dubins_f_fx_fu(x, u, pb.dynp[g], pb.dynp[P + g], pb.dynp[2 * P + g], pb.dyn_eps, fo, fxo, fuo);
+  for (int e = 0; e < 4; ++e) x[e] = (j == 0) ? pb.x0[(size_t)e * P + sl] : pb.Xp[tix(sl, L, j - 1, 4, e)];
+  for (int e = 0; e < 2; ++e) u[e] = pb.Up[tix(sl, L, j, 2, e)];
+  dubins_f_fx_fu(x, u, pb.dynp[sl], pb.dynp[P + sl], pb.dynp[2 * P + sl], pb.dyn_eps, fo, fxo, fuo);
   for (int r = 0; r < 4; ++r) {
     f[((size_t)g * N + j) * 4 + r] = fo[r];
     for (int t = 0; t < 4; ++t) fx[((size_t)g * N + j) * 16 + t * 4 + r] = fxo[r * 4 + t];
@@ -281,7 +300,8 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   pb.B = (int)B; pb.M = (int)M; pb.N = (int)N; pb.n = (int)xdim; pb.m = (int)udim;
   pb.Nc = (M == 1) ? 0 : (int)Nc;  // one particle: consensus is vacuous (the Nc==0 quirk is applied at pack time)
   pb.D = pb.Nc * sh.NU;
-  pb.P = (int)(((h->Ptot + 31) / 32) * 32);
+  pb.Mpad = (M == 1) ? 1 : (int)(((M + 31) / 32) * 32);
+  pb.P = (int)((((size_t)B * pb.Mpad + 31) / 32) * 32);
   pb.hist_len = 128;
   pmpc_default_settings(&h->settings);
   apply_settings(h);
@@ -383,7 +403,7 @@ static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, in
     int rc = upload(h, host, h->Ptot * pb.N * Ei, 0, &dev);
     if (rc) return rc;
   }
-  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, pb.P, pb.N, Ei, Eo, fill);
+  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, Lay{pb.M, pb.Mpad, pb.N}, Ei, Eo, fill);
   ++g_launches;
   CU(cudaGetLastError());
   if (host) CU(cudaStreamSynchronize(h->stream));  // staging buffer is reused by the next upload
@@ -440,12 +460,12 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   CU(cudaGetLastError());
   CU(cudaFreeAsync(extra, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(nullptr, pb.x0, (int)Pt, pb.P, 0, NX, 0.0);
+  pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(nullptr, pb.x0, (int)Pt, pb.P, Lay{pb.M, pb.Mpad, pb.N}, 0, NX, 0.0);
   ++g_launches;
   {
     double* d;
     if ((rc = upload(h, x0, Pt * n, 0, &d))) return rc;
-    pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(d, pb.x0, (int)Pt, pb.P, n, NX, 0.0);
+    pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(d, pb.x0, (int)Pt, pb.P, Lay{pb.M, pb.Mpad, pb.N}, n, NX, 0.0);
     ++g_launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
@@ -492,7 +512,7 @@ int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double* params, size_t np
     double* d;
     int rc;
     if ((rc = upload(h, params, h->Ptot * 3, 0, &d))) return rc;
-    pack_particle_kernel<<<nblk(h->Ptot), 256, 0, h->stream>>>(d, pb.dynp, (int)h->Ptot, pb.P, 3, 4, 0.0);
+    pack_particle_kernel<<<nblk(h->Ptot), 256, 0, h->stream>>>(d, pb.dynp, (int)h->Ptot, pb.P, Lay{pb.M, pb.Mpad, pb.N}, 3, 4, 0.0);
     ++g_launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
@@ -630,9 +650,9 @@ int pmpc_get_solution(pmpc_handle_t h, double* X, double* U) {
   const size_t Pt = h->Ptot, N = pb.N;
   double* dX = h->stage;
   double* dU = h->stage + Pt * N * pb.n;
-  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, pb.P, pb.N, h->shape.NX, pb.n);
+  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, Lay{pb.M, pb.Mpad, pb.N}, h->shape.NX, pb.n);
   ++g_launches;
-  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.U, dU, (int)Pt, pb.P, pb.N, h->shape.NU, pb.m);
+  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.U, dU, (int)Pt, Lay{pb.M, pb.Mpad, pb.N}, h->shape.NU, pb.m);
   ++g_launches;
   CU(cudaGetLastError());
   if (X) CU(cudaMemcpyAsync(X, dX, Pt * N * pb.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

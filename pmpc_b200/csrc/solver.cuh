@@ -5,9 +5,14 @@
 //   PMPC.jl/src/lqp_utils.jl:2-393 (QP assembly) + osqp_solver.jl:34-72 (OSQP)  ->  Riccati-ADMM + polish
 // See DESIGN.md for the maths and the data layout.
 //
-// DATA LAYOUT (HBM): structure-of-arrays with the particle index fastest:
-//     arr[(j * E + e) * P + g]      j = stage, e = element, g = b*M + i global particle, P = stride
-// so the 32 lanes of a warp (32 consecutive particles) touch 256 contiguous bytes per access.
+// DATA LAYOUT (HBM): warp-tiled structure-of-arrays.  Particle i of problem b owns slot
+// g = b*Mpad + i (Mpad = M rounded up to a warp for M > 1, so a warp never straddles two problems);
+// per-(particle, stage) arrays are stored as
+//     arr[(((g / 32) * N + j) * E + e) * 32 + g % 32]     j = stage, e = element of E
+// i.e. for every warp of 32 particles the E elements of a stage form ONE contiguous block of E*256
+// bytes (one bulk async copy), consecutive stages are adjacent, and each lane access is a fully
+// coalesced 256-byte row at a compile-time offset from the warp's stage pointer.  Per-particle arrays
+// (x0, dynamics parameters, boundary value function) are arr[e * P + g].
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -30,7 +35,8 @@ struct FactorSet {
 
 struct DevProb {
   int B, M, N, n, m, Nc, D;   // logical sizes; D = Nc * NU (padded control dim)
-  int P;                      // SoA stride (padded number of particles)
+  int Mpad;                   // particle slots per problem (M == 1 ? 1 : M rounded up to 32)
+  int P;                      // number of particle slots, B * Mpad rounded up to 32
   int dyn_kind;
   int has_ubox, has_xbox, has_slew;
   double reg_x, reg_u, dyn_eps;
@@ -149,7 +155,7 @@ struct Solver {
     if (GROUPED) {
       prob = blockIdx.x;
       valid = tid < pb.M;
-      g = prob * pb.M + (valid ? tid : pb.M - 1);
+      g = prob * pb.Mpad + (valid ? tid : pb.M - 1);
     } else {
       const int idx = blockIdx.x * blockDim.x + threadIdx.x;
       valid = idx < pb.B * pb.M;
@@ -159,8 +165,13 @@ struct Solver {
     s = pb.has_slew ? pb.slew[g] : 0.0;
   }
 
-  __device__ __forceinline__ double& at(double* a, int j, int E, int e) const { return a[((size_t)j * E + e) * P + g]; }
-  __device__ __forceinline__ double ld(const double* a, int j, int E, int e) const { return a[((size_t)j * E + e) * P + g]; }
+  // warp-tile SoA index of element e (of E) of stage j for particle slot gg (see DATA LAYOUT above)
+  __device__ __forceinline__ size_t ixg(int j, int E, int e, size_t gg) const {
+    return (((gg >> 5) * (size_t)N + (size_t)j) * (size_t)E + (size_t)e) * 32 + (gg & 31);
+  }
+  __device__ __forceinline__ size_t ix(int j, int E, int e) const { return ixg(j, E, e, (size_t)g); }
+  __device__ __forceinline__ double& at(double* a, int j, int E, int e) const { return a[ix(j, E, e)]; }
+  __device__ __forceinline__ double ld(const double* a, int j, int E, int e) const { return a[ix(j, E, e)]; }
   __device__ __forceinline__ double ldp(const double* a, int e) const { return a[(size_t)e * P + g]; }
   __device__ __forceinline__ double* scr() const { return pb.scratch + (size_t)prob * pb.scratch_stride; }
 
@@ -293,7 +304,7 @@ struct Solver {
       if (mode == MODE_POLISH && pb.has_ubox) {
 #pragma unroll UNR
         for (int t = 0; t < NU; ++t) {
-          const signed char a = pb.act[((size_t)j * NU + t) * P + g];
+          const signed char a = pb.act[ix(j, NU, t)];
           if (a != 0) {
             fixed[t] = true;
             ufix[t] = (a > 0) ? ld(pb.uu, j, NU, t) : ld(pb.lu, j, NU, t);
@@ -461,7 +472,7 @@ struct Solver {
       for (int a = 0; a < NU; ++a) {
         double acc = 0.0;
         if (mode == MODE_POLISH && pb.has_ubox) {
-          const signed char ac = pb.act[((size_t)j * NU + a) * P + g];
+          const signed char ac = pb.act[ix(j, NU, a)];
           if (ac != 0) acc = (ac > 0) ? ld(pb.uu, j, NU, a) : ld(pb.lu, j, NU, a);
         }
 #pragma unroll UNR
@@ -656,8 +667,8 @@ struct Solver {
           const signed char ac = actc[b];
           if (ac != 0) {
             const int j = b / NU, t = b % NU;
-            const size_t g0 = (size_t)prob * pb.M;  // particle 0 of the problem owns the shared bounds
-            const double beta = (ac > 0) ? pb.uu[((size_t)j * NU + t) * P + g0] : pb.lu[((size_t)j * NU + t) * P + g0];
+            const size_t g0 = (size_t)prob * pb.Mpad;  // particle 0 of the problem owns the shared bounds
+            const double beta = (ac > 0) ? pb.uu[ixg(j, NU, t, g0)] : pb.lu[ixg(j, NU, t, g0)];
             acc += Hc[(size_t)a * D + b] * beta;
           }
         }
@@ -719,17 +730,17 @@ struct Solver {
     const double* Hi = F.Hci + (size_t)prob * D * D;
     const double* hb = F.hb + (size_t)prob * D;
     const signed char* actc = pb.actc + (size_t)prob * D;
-    const size_t g0 = (size_t)prob * pb.M;
+    const size_t g0 = (size_t)prob * pb.Mpad;
     for (int a = tid; a < D; a += T) {
       double acc = 0.0;
       const int ja = a / NU, ta = a % NU;
       if (mode == MODE_POLISH && pb.has_ubox && actc[a] != 0)
-        acc = (actc[a] > 0) ? pb.uu[((size_t)ja * NU + ta) * P + g0] : pb.lu[((size_t)ja * NU + ta) * P + g0];
+        acc = (actc[a] > 0) ? pb.uu[ixg(ja, NU, ta, g0)] : pb.lu[ixg(ja, NU, ta, g0)];
       for (int b = 0; b < D; ++b) {
         double gb = gc[b] + hb[b];
         if (mode == MODE_ADMM && pb.has_ubox) {
           const int j = b / NU, t = b % NU;
-          gb += -rho_u * pb.wu[((size_t)j * NU + t) * P + g0] + pb.yu[((size_t)j * NU + t) * P + g0];
+          gb += -rho_u * pb.wu[ixg(j, NU, t, g0)] + pb.yu[ixg(j, NU, t, g0)];
         }
         acc -= Hi[(size_t)a * D + b] * gb;
       }
@@ -789,11 +800,11 @@ struct Solver {
       if (mode == MODE_ADMM) {
         if (pb.has_ubox) {
           // shared stages: one multiplier per problem, owned by particle 0's slot / thread 0
-          const size_t gs = (j < Nc) ? (size_t)prob * pb.M : (size_t)g;
+          const size_t gs = (j < Nc) ? (size_t)prob * pb.Mpad : (size_t)g;
           if (j >= Nc || tid == 0) {
 #pragma unroll UNR
           for (int a = 0; a < NU; ++a) {
-            const size_t o = ((size_t)j * NU + a) * P + gs;
+            const size_t o = ixg(j, NU, a, gs);
             const double w = pb.wu[o], y = pb.yu[o];
             const double zr = alpha * u[a] + (1.0 - alpha) * w;
             const double lo = pb.lu[o], hi = pb.uu[o];
@@ -813,7 +824,7 @@ struct Solver {
         if (pb.has_xbox) {
 #pragma unroll UNR
           for (int r = 0; r < NX; ++r) {
-            const size_t o = ((size_t)j * NX + r) * P + g;
+            const size_t o = ix(j, NX, r);
             const double w = pb.wx[o], y = pb.yx[o];
             const double zr = alpha * xn[r] + (1.0 - alpha) * w;
             const double wn = fmin(fmax(zr + y / rho, pb.lx[o]), pb.ux[o]);
@@ -921,7 +932,7 @@ struct Solver {
             signed char na = 0;
             if (mu + (ub - hi) > 0.0 && hi < INFINITY) na = 1;
             else if (mu + (ub - lo) < 0.0 && lo > -INFINITY) na = -1;
-            const size_t o = ((size_t)j * NU + b) * P + g;
+            const size_t o = ix(j, NU, b);
             if (valid) {
               if (na != pb.act[o]) changed += 1.0;
               pb.actn[o] = na;
@@ -938,7 +949,7 @@ struct Solver {
     if (GROUPED && Nc >= 1) {
       double* muc = pb.muc + (size_t)prob * D;
       reduce(D, muc);  // muc = sum_i reduced gradient on the shared block
-      const size_t g0 = (size_t)prob * pb.M;
+      const size_t g0 = (size_t)prob * pb.Mpad;
       const double* uc = pb.uc + (size_t)prob * D;
       const signed char* actc = pb.actc + (size_t)prob * D;
       signed char* actcn = pb.actcn + (size_t)prob * D;
@@ -947,8 +958,8 @@ struct Solver {
         const double acc = muc[k], mu = -acc, ub = uc[k];
         double lo = -INFINITY, hi = INFINITY;
         if (pb.has_ubox) {
-          lo = pb.lu[((size_t)j * NU + b) * P + g0];
-          hi = pb.uu[((size_t)j * NU + b) * P + g0];
+          lo = pb.lu[ixg(j, NU, b, g0)];
+          hi = pb.uu[ixg(j, NU, b, g0)];
         }
         st[ST_UVIOL] = fmax(st[ST_UVIOL], fmax(ub - hi, lo - ub));
         const bool at_hi = ub >= hi - 1e-12 * fmax(1.0, fabs(hi));
@@ -979,7 +990,7 @@ struct Solver {
     for (int j = 0; j < N; ++j) {
 #pragma unroll UNR
       for (int b = 0; b < NU; ++b) {
-        const size_t o = ((size_t)j * NU + b) * P + g;
+        const size_t o = ix(j, NU, b);
         const double u = ld(Uc, j, NU, b);
         if (valid && (j >= Nc || tid == 0)) {
           pb.wu[o] = fmin(fmax(u, pb.lu[o]), pb.uu[o]);
@@ -1058,7 +1069,7 @@ struct Solver {
     for (int j = Nc; j < N; ++j) {
 #pragma unroll UNR
       for (int b = 0; b < NU; ++b) {
-        const size_t o = ((size_t)j * NU + b) * P + g;
+        const size_t o = ix(j, NU, b);
         const double w = pb.wu[o], y = pb.yu[o];
         signed char na = 0;
         if (pb.uu[o] - w < y) na = 1;
@@ -1070,11 +1081,11 @@ struct Solver {
       }
     }
     if (GROUPED && Nc >= 1) {
-      const size_t g0 = (size_t)prob * pb.M;
+      const size_t g0 = (size_t)prob * pb.Mpad;
       signed char* actc = pb.actc + (size_t)prob * D;
       __syncthreads();
       for (int k = tid; k < D; k += T) {
-        const size_t o = (size_t)k * P + g0;  // (j*NU + b) * P + g0
+        const size_t o = ixg(k / NU, NU, k % NU, g0);
         const double w = pb.wu[o], y = pb.yu[o];
         signed char na = 0;
         if (pb.uu[o] - w < y) na = 1;
@@ -1092,7 +1103,7 @@ struct Solver {
     for (int j = Nc; j < N; ++j) {
 #pragma unroll UNR
       for (int b = 0; b < NU; ++b) {
-        const size_t o = ((size_t)j * NU + b) * P + g;
+        const size_t o = ix(j, NU, b);
         if (valid) pb.act[o] = pb.actn[o];
       }
     }
@@ -1202,7 +1213,7 @@ struct Solver {
       }
       signed char act[NU];
 #pragma unroll UNR
-      for (int t = 0; t < NU; ++t) act[t] = (pb.has_ubox && j >= Nc) ? pb.act[((size_t)j * NU + t) * P + g] : 0;
+      for (int t = 0; t < NU; ++t) act[t] = (pb.has_ubox && j >= Nc) ? pb.act[ix(j, NU, t)] : 0;
       double xs[NX], us[NU], ups[NU];
       if (KKT) {
 #pragma unroll UNR
@@ -1264,7 +1275,7 @@ struct Solver {
               if (na != act[b]) {
                 changed += 1.0;
                 act[b] = na;
-                if (valid) pb.act[((size_t)j * NU + b) * P + g] = na;
+                if (valid) pb.act[ix(j, NU, b)] = na;
               }
             }
           }
@@ -1466,7 +1477,7 @@ struct Solver {
         // shared block: summed reduced gradient -> multipliers / proposed active set (kkt_sweep tail)
         double* muc = pb.muc + (size_t)prob * D;
         reduce(D, muc);
-        const size_t g0 = (size_t)prob * pb.M;
+        const size_t g0 = (size_t)prob * pb.Mpad;
         const double* uc = pb.uc + (size_t)prob * D;
         signed char* actc = pb.actc + (size_t)prob * D;
         double ch = 0.0, kk = 0.0, uv = 0.0;
@@ -1475,8 +1486,8 @@ struct Solver {
           const double acc = muc[k], mu = -acc, ubv = uc[k];
           double lo = -INFINITY, hi = INFINITY;
           if (pb.has_ubox) {
-            lo = pb.lu[((size_t)jj * NU + b) * P + g0];
-            hi = pb.uu[((size_t)jj * NU + b) * P + g0];
+            lo = pb.lu[ixg(jj, NU, b, g0)];
+            hi = pb.uu[ixg(jj, NU, b, g0)];
           }
           uv = fmax(uv, fmax(ubv - hi, lo - ubv));
           const bool at_hi = ubv >= hi - 1e-12 * fmax(1.0, fabs(hi));
