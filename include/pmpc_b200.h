@@ -85,6 +85,7 @@ typedef struct {
   int adapt_rho;       /*                                               (1)            */
   int warm_start;      /* carry (w,y,active set) across SCP iterations  (1)            */
   int fused;           /* fused 2-sweep polish passes with on-the-fly linearisation (1) */
+  int ring;            /* bulk-async (TMA) prefetch ring in shared memory for the fused sweeps (1) */
 } pmpc_settings;
 
 void pmpc_default_settings(pmpc_settings *s);

@@ -36,6 +36,7 @@ class Settings(C.Structure):
         ("adapt_rho", C.c_int),
         ("warm_start", C.c_int),
         ("fused", C.c_int),
+        ("ring", C.c_int),
     ]
 
 

@@ -65,6 +65,7 @@ struct pmpc_handle_s {
   double* stage = nullptr;    // device staging for raw (reference-layout) inputs / outputs
   size_t stage_doubles = 0;
   double *lin_f = nullptr, *lin_fx = nullptr, *lin_fu = nullptr;  // reference-layout linearisation
+  int* uniform = nullptr;     // per problem: cost / reference / bound data identical for all particles
   bool have_problem = false, have_dyn = false, solved = false;
   pmpc_settings settings{};
   float last_ms = 0.f;
@@ -215,6 +216,38 @@ __global__ void linearize_dubins_kernel(DevProb pb, double* __restrict__ f, doub
   }
 }
 
+// flags[b] = 0 when any particle of problem b differs from particle 0 in its packed cost, reference
+// or bound data (flags pre-set to 1).  One thread per (flat particle, stage).
+__global__ void uniform_check_kernel(DevProb pb, int NX, int NU, int* flags, int Ptot) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = pb.N;
+  if (idx >= (size_t)Ptot * N) return;
+  const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
+  if (gf % pb.M == 0) return;
+  const Lay L{pb.M, pb.Mpad, pb.N};
+  const size_t sl = slot_of(gf, L), s0 = slot_of(gf - gf % pb.M, L);
+  const int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2;
+  bool same = pb.rdiag0[sl] == pb.rdiag0[s0];
+  for (int e = 0; e < NQ; ++e) same &= pb.Qs[tix(sl, L, j, NQ, e)] == pb.Qs[tix(s0, L, j, NQ, e)];
+  for (int e = 0; e < NR; ++e) same &= pb.Rs[tix(sl, L, j, NR, e)] == pb.Rs[tix(s0, L, j, NR, e)];
+  for (int e = 0; e < NX; ++e) {
+    same &= pb.qref[tix(sl, L, j, NX, e)] == pb.qref[tix(s0, L, j, NX, e)];
+    same &= pb.xref[tix(sl, L, j, NX, e)] == pb.xref[tix(s0, L, j, NX, e)];
+  }
+  for (int e = 0; e < NU; ++e) {
+    same &= pb.rref[tix(sl, L, j, NU, e)] == pb.rref[tix(s0, L, j, NU, e)];
+    same &= pb.uref[tix(sl, L, j, NU, e)] == pb.uref[tix(s0, L, j, NU, e)];
+    same &= pb.lu[tix(sl, L, j, NU, e)] == pb.lu[tix(s0, L, j, NU, e)];
+    same &= pb.uu[tix(sl, L, j, NU, e)] == pb.uu[tix(s0, L, j, NU, e)];
+  }
+  if (!same) flags[gf / pb.M] = 0;
+}
+
+__global__ void fill_int_kernel(int* p, size_t n, int v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 __global__ void fill_kernel(double* p, size_t n, double v) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -246,6 +279,7 @@ void pmpc_default_settings(pmpc_settings* s) {
   s->adapt_rho = 1;
   s->warm_start = 1;
   s->fused = 1;
+  s->ring = 1;
 }
 
 const char* pmpc_last_error(void) { return g_err.c_str(); }
@@ -269,6 +303,7 @@ static void apply_settings(pmpc_handle_t h) {
   pb.polish_iters = s.polish_iters < 1 ? 1 : s.polish_iters; pb.adapt_rho = s.adapt_rho;
   pb.warm_start = s.warm_start;
   pb.fused = s.fused;
+  pb.ring = s.ring;
 }
 
 int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, size_t xdim, size_t udim,
@@ -358,6 +393,9 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaMalloc(&h->lin_f, h->Ptot * N * xdim * sizeof(double)));
   CU(cudaMalloc(&h->lin_fx, h->Ptot * N * xdim * xdim * sizeof(double)));
   CU(cudaMalloc(&h->lin_fu, h->Ptot * N * xdim * udim * sizeof(double)));
+  CU(cudaMalloc(&h->uniform, B * sizeof(int)));
+  CU(cudaMemsetAsync(h->uniform, 0, B * sizeof(int), h->stream));
+  pb.uniform = h->uniform;
   fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);
   ++g_launches;
   CU(cudaGetLastError());
@@ -370,6 +408,7 @@ int pmpc_destroy(pmpc_handle_t h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
+  cudaFree(h->uniform);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->tev0); cudaEventDestroy(h->tev1);
   cudaStreamDestroy(h->stream);
@@ -475,6 +514,11 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   if ((rc = pack_vec(h, ubox ? uu : nullptr, pb.uu, m, NU, inf))) return rc;
   if ((rc = pack_vec(h, xbox ? lx : nullptr, pb.lx, n, NX, -inf))) return rc;
   if ((rc = pack_vec(h, xbox ? ux : nullptr, pb.ux, n, NX, inf))) return rc;
+  fill_int_kernel<<<nblk(pb.B), 256, 0, h->stream>>>(h->uniform, pb.B, 1);
+  ++g_launches;
+  uniform_check_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, h->uniform, (int)Pt);
+  ++g_launches;
+  CU(cudaGetLastError());
   h->have_problem = true;
   return pmpc_set_warm_start(h, nullptr, nullptr);
 }

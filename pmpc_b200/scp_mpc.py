@@ -27,7 +27,7 @@ from .static_backend import aff_solve
 from .utils import TablePrinter, atleast_nd
 
 _SOLVER_KEYS = ("rho0", "alpha", "eps_abs", "eps_rel", "kkt_tol", "adapt_tol", "max_admm_iter", "check_every", "polish",
-                "polish_iters", "adapt_rho", "warm_start", "fused")
+                "polish_iters", "adapt_rho", "warm_start", "fused", "ring")
 
 
 def print_fn(*args, **kwargs):

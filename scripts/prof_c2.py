@@ -10,7 +10,8 @@ M, N, n, m = 128, 50, 4, 2
 p = np.stack([rng.uniform(0.7, 1.0, M), rng.uniform(0.7, 1.0, M), np.full(M, 0.3)], -1)
 Q = np.tile(np.eye(n), (B, M, N, 1, 1)); R = np.tile(1e-2 * np.eye(m), (B, M, N, 1, 1)); x0 = np.ones((B, M, n))
 x0 = x0 + 0.05 * np.random.default_rng(7).standard_normal((B, 1, n))  # distinct problems
-s = DeviceSolver(M, N, n, m, 1, B=B)
+st = dict((k, int(v)) for k, v in (kv.split('=') for kv in os.environ.get('PMPC_SET', '').split(',') if kv))
+s = DeviceSolver(M, N, n, m, 1, B=B, settings=st or None)
 s.set_problem(x0, Q, R, None, None, None, None, -np.ones((B, M, N, m)), np.ones((B, M, N, m)), 1.0, 1e-2)
 s.set_dubins(np.tile(p, (B, 1, 1)))
 for rep in range(reps):
