@@ -152,6 +152,9 @@ int pmpc_last_kernel_ms(pmpc_handle_t h, float *ms);
 int pmpc_timer_start(pmpc_handle_t h);
 int pmpc_timer_stop(pmpc_handle_t h, float *ms);
 long long pmpc_launch_count(void);
+/* Resident CTAs per SM of the solve kernel this handle would launch, and the SM count: batch sizes
+ * that are multiples of ctas_per_sm * num_sms fill the GPU in whole waves (one CTA = one problem). */
+int pmpc_get_occupancy(pmpc_handle_t h, int *ctas_per_sm, int *num_sms);
 int pmpc_microbench(int device, int kind, double *result);
 
 /* ------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmpc_b200.so")
+LIB_PATH = os.environ.get("PMPC_B200_LIB", os.path.join(_HERE, "libpmpc_b200.so"))  # override: A/B builds
 
 c_double_p = C.POINTER(C.c_double)
 c_ll_p = C.POINTER(C.c_longlong)
@@ -74,6 +74,7 @@ _SIG = {
     "pmpc_timer_start": (C.c_int, [C.c_void_p]),
     "pmpc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pmpc_launch_count": (C.c_longlong, []),
+    "pmpc_get_occupancy": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pmpc_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pmpc_lqp_solve": (C.c_int, [_DP, _DP, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_longlong] + [_DP] * 14
                        + [C.c_double, C.c_double] + [_DP] * 3 + [C.POINTER(Settings), c_ll_p]),

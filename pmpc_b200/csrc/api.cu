@@ -20,14 +20,21 @@ static std::atomic<long long> g_launches{0};  // kernels launched by this librar
 
 using namespace pmpc;
 
+#include "variants.h"
 namespace pmpc {
-template <> cudaError_t launch_scp<2, 1>(const DevProb&, cudaStream_t);
-template <> cudaError_t launch_scp<4, 2>(const DevProb&, cudaStream_t);
-template <> cudaError_t launch_scp<8, 4>(const DevProb&, cudaStream_t);
-template <> cudaError_t launch_scp<12, 4>(const DevProb&, cudaStream_t);
-template <> cudaError_t launch_scp<16, 8>(const DevProb&, cudaStream_t);
-template <> cudaError_t launch_scp<32, 8>(const DevProb&, cudaStream_t);
+#define PMPC_DECL(nx, nu, kind, var) \
+  cudaError_t launch_##nx##_##nu##_##kind##_##var(const DevProb&, int blocks, int threads, cudaStream_t, int*);
+PMPC_VARIANTS(PMPC_DECL)
+#undef PMPC_DECL
 }  // namespace pmpc
+
+typedef cudaError_t (*launch_fn)(const DevProb&, int, int, cudaStream_t, int*);
+struct VariantEntry { int nx, nu, kind, var; launch_fn fn; };
+static const VariantEntry kVariants[] = {
+#define PMPC_ENTRY(nx, nu, kind, var) {nx, nu, kind, var, &pmpc::launch_##nx##_##nu##_##kind##_##var},
+    PMPC_VARIANTS(PMPC_ENTRY)
+#undef PMPC_ENTRY
+};
 
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -360,7 +367,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
     want(&F.Pc, NX * NX * P); want(&F.Wc, NX * NU * P); want(&F.Zc, NU * NU * P);
     want(&F.Hc, B * D * D + 1); want(&F.Hci, B * D * D + 1); want(&F.hb, B * D + 1);
   }
-  want(&pb.kff, Nn * NU * P); want(&pb.X, Nn * NX * P); want(&pb.U, Nn * NU * P);
+  want(&pb.kff, Nn * NU * P); want(&pb.Hs, Nn * NR * P); want(&pb.X, Nn * NX * P); want(&pb.U, Nn * NU * P);
   want(&pb.wu, Nn * NU * P); want(&pb.yu, Nn * NU * P); want(&pb.wx, Nn * NX * P); want(&pb.yx, Nn * NX * P);
   want(&pb.gc, B * D + 1); want(&pb.uc, B * D + 1); want(&pb.muc, B * D + 1);
   want(&pb.scratch, B * pb.scratch_stride);
@@ -624,20 +631,27 @@ int pmpc_get_linearization(pmpc_handle_t h, double* f, double* fx, double* fu) {
   return PMPC_OK;
 }
 
-static int launch(pmpc_handle_t h) {
+static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
   const DevProb& pb = h->pb;
-  cudaError_t e = cudaErrorUnknown;
-  const int key = h->shape.NX * 100 + h->shape.NU;
-  CU(cudaEventRecord(h->ev0, h->stream));
-  switch (key) {
-    case 201: e = launch_scp<2, 1>(pb, h->stream); break;
-    case 402: e = launch_scp<4, 2>(pb, h->stream); break;
-    case 804: e = launch_scp<8, 4>(pb, h->stream); break;
-    case 1204: e = launch_scp<12, 4>(pb, h->stream); break;
-    case 1608: e = launch_scp<16, 8>(pb, h->stream); break;
-    case 3208: e = launch_scp<32, 8>(pb, h->stream); break;
-    default: return fail(PMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+  // CTA kind: one thread per single-particle problem, or one CTA per problem (one thread per particle)
+  const int threads = (pb.M == 1) ? 128 : ((pb.M + 31) / 32) * 32;
+  const int kind = (pb.M == 1) ? 0 : (threads <= 128 ? 1 : 2);
+  const int blocks = (pb.M == 1) ? (pb.B + threads - 1) / threads : pb.B;
+  // fused-path variant: bit 0 = on-the-fly Dubins linearisation, bit 1 = lean (no slew penalty)
+  const int NX = h->shape.NX, NU = h->shape.NU;
+  int var = 0;
+  if (NX == 4 && NU == 2 && pb.dyn_kind == DYN_DUBINS) var |= 1;
+  if (NX <= 4 && !pb.has_slew) var |= 2;
+  launch_fn fn = nullptr;
+  for (const VariantEntry& v : kVariants)
+    if (v.nx == NX && v.nu == NU && v.kind == kind && v.var == var) fn = v.fn;
+  if (!fn) return fail(PMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+  if (occ_out) {
+    cudaError_t e = fn(pb, blocks, threads, h->stream, occ_out);
+    return e == cudaSuccess ? PMPC_OK : fail(PMPC_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
   }
+  CU(cudaEventRecord(h->ev0, h->stream));
+  cudaError_t e = fn(pb, blocks, threads, h->stream, nullptr);
   if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   ++g_launches;
   CU(cudaEventRecord(h->ev1, h->stream));
@@ -738,6 +752,14 @@ int pmpc_last_kernel_ms(pmpc_handle_t h, float* ms) {
 }
 
 long long pmpc_launch_count(void) { return g_launches.load(); }
+
+int pmpc_get_occupancy(pmpc_handle_t h, int* ctas_per_sm, int* num_sms) {
+  if (!h || !ctas_per_sm || !num_sms) return fail(PMPC_ERR_BAD_ARG, "null");
+  if (!h->have_problem || !h->have_dyn) return fail(PMPC_ERR_STATE, "set problem and dynamics first (they select the kernel)");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  return launch(h, ctas_per_sm);
+}
 
 int pmpc_timer_start(pmpc_handle_t h) {
   if (!h) return fail(PMPC_ERR_BAD_ARG, "null");

@@ -1,13 +1,16 @@
   // =============================================================================================
   // FUSED PATH (textually included inside struct Solver).
   //
-  // One backward sweep does, per stage: (optionally) the adjoint/KKT check of the current iterate
-  // with the primal-dual active-set update, the linearisation (recomputed on the fly for built-in
-  // dynamics instead of streaming f, fx, fu through HBM), the masked Riccati matrix step and the
-  // vector step.  One forward sweep does the rollout and the SCP residual/objective bookkeeping
-  // (scp_mpc.py:397-405).  A polish pass is 2 sweeps over the horizon (the unfused path needs 4,
-  // plus 2 per SCP iteration for linearise and X_prev <- X); the only per-(particle, stage) state
-  // that lives in HBM between sweeps is K, k, X, U, X_prev, U_prev and the active set.
+  // An active-set (polish) pass is TWO sweeps over the horizon:
+  //   bsweep  backward: linearisation (recomputed on the fly for built-in dynamics instead of
+  //           streaming f, fx, fu through HBM), masked Riccati matrix step and vector step;
+  //   fsweep  forward: rollout of the feedback policy, multipliers of the fixed controls from the
+  //           stage Q-function gradient  mu = -(H u + G x + h0 - s u_{j-1}), primal-dual active-set
+  //           update, and the SCP residual / objective bookkeeping (scp_mpc.py:397-405).
+  // A QP whose active set is already right therefore costs exactly one pass; every change of the
+  // active set costs one more.  Between the sweeps only K, k, H (and E with a slew penalty), X, U,
+  // X_prev, U_prev and the active set live in HBM.  For a fixed control a the slots K[a,:], k[a]
+  // (which would be 0 and the bound) carry G[a,:], h0[a] for the multiplier.
   //
   // Streaming: every warp owns 32 particle slots whose stage blocks are contiguous (warp-tiled SoA),
   // so lane 0 prefetches them DEPTH stages ahead with bulk asynchronous copies (TMA engine,
@@ -19,11 +22,10 @@
   // =============================================================================================
   static constexpr bool RING_SHAPE = (NX <= 4);
   static constexpr int DEPTH = 3;
-  // ring slot layout (doubles): backward sweep [Xp | Up | X | U | act], forward sweep [Xp | Up | K | k]
-  static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_X = R_UP + NU * 32, R_U = R_X + NX * 32,
-                       R_ACT = R_U + NU * 32, R_K = R_UP + NU * 32, R_KF = R_K + NU * NX * 32;
-  static constexpr int SLOT_B = R_ACT + NU * 4, SLOT_F = R_KF + NU * 32;
-  static constexpr int SLOT = SLOT_B > SLOT_F ? SLOT_B : SLOT_F;
+  // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | act]
+  static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_K = R_UP + NU * 32, R_KF = R_K + NU * NX * 32,
+                       R_H = R_KF + NU * 32, R_ACTF = R_H + NR * 32, R_ACTB = R_UP + NU * 32;
+  static constexpr int SLOT = R_ACTF + NU * 4;
   // uniform cost table row: [Qs | Rs | qref | rref | xref | uref | lu | uu]
   static constexpr int T_QS = 0, T_RS = T_QS + NQ, T_QR = T_RS + NR, T_RR = T_QR + NX, T_XR = T_RR + NU,
                        T_UR = T_XR + NX, T_LU = T_UR + NU, T_UU = T_LU + NU, TW = T_UU + NU;
@@ -31,14 +33,25 @@
   __host__ __device__ static constexpr int table_doubles(int N_) { return N_ * TW; }
   __host__ __device__ static constexpr int ring_doubles(int nwarps) { return nwarps * DEPTH * SLOT; }
 
-  __device__ __forceinline__ double symQ(const double* Qp, int r, int t) const {
-    return Qp[r <= t ? pk(r, t, NX) : pk(t, r, NX)];
+  // shared-memory view rebuilt from the kernel's own dynamic-smem base inside every sweep, so that the
+  // accesses compile to LDS / mbarrier on shared addresses (pointers kept in the Solver object are generic)
+  struct Sm {
+    const double* tab;
+    double* ring;
+    uint64_t* bars;
+  };
+  __device__ __forceinline__ Sm smem_view(const DevProb& pb, unsigned char* smem) const {
+    double* base = reinterpret_cast<double*>(smem);
+    Sm v;
+    v.tab = has_tab ? base : nullptr;
+    v.ring = pb.ring ? base + pb.tab_doubles + (size_t)wid * DEPTH * SLOT : nullptr;
+    v.bars = pb.ring ? reinterpret_cast<uint64_t*>(base + pb.tab_doubles + (size_t)(T >> 5) * DEPTH * SLOT) + wid * DEPTH : nullptr;
+    return v;
   }
-  __device__ __forceinline__ double symR(const double* Rp, int a, int b) const {
-    return Rp[a <= b ? pk(a, b, NU) : pk(b, a, NU)];
-  }
+
   // element 0 of the warp's stage-j block of an E-element array (no lane offset): bulk-copy source
-  __device__ __forceinline__ const double* blk(const double* a, int j, int E) const {
+  template <typename Tp>
+  __device__ __forceinline__ const Tp* blk(const Tp* a, int j, int E) const {
     return a + (((size_t)(g >> 5) * (size_t)N + (size_t)j) * (size_t)E) * 32;
   }
 
@@ -51,6 +64,7 @@
     ring = nullptr;
     bars = nullptr;
     tab = nullptr;
+    has_tab = false;
     double* base = reinterpret_cast<double*>(smem);
     const int nw = T >> 5;
     double* tb = base;
@@ -79,148 +93,126 @@
         tb[idx] = v;
       }
       tab = tb;
+      has_tab = true;
     }
     __syncthreads();
   }
 
-  // per-stage cost / reference / bound data into registers, from the table or from HBM
-  __device__ __forceinline__ void stage_cost(int j, double* Qp, double* Rp, double* qr, double* rr, double* lo,
-                                             double* hi) const {
+  // one field (E doubles at table offset `off`) of the stage's cost / reference / bound data
+  __device__ __forceinline__ void cost_field(const double* tab, int j, int off, int E, const double* arr, double* out) const {
     if (tab != nullptr) {
-      const double* t = tab + j * TW;
+      const double* t = tab + j * TW + off;
 #pragma unroll UNR
-      for (int e = 0; e < NQ; ++e) Qp[e] = t[T_QS + e];
-#pragma unroll UNR
-      for (int e = 0; e < NR; ++e) Rp[e] = t[T_RS + e];
-#pragma unroll UNR
-      for (int e = 0; e < NX; ++e) qr[e] = t[T_QR + e];
-#pragma unroll UNR
-      for (int e = 0; e < NU; ++e) {
-        rr[e] = t[T_RR + e];
-        lo[e] = t[T_LU + e];
-        hi[e] = t[T_UU + e];
-      }
+      for (int e = 0; e < E; ++e) out[e] = t[e];
     } else {
 #pragma unroll UNR
-      for (int e = 0; e < NQ; ++e) Qp[e] = ld(pb.Qs, j, NQ, e);
-#pragma unroll UNR
-      for (int e = 0; e < NR; ++e) Rp[e] = ld(pb.Rs, j, NR, e);
-#pragma unroll UNR
-      for (int e = 0; e < NX; ++e) qr[e] = ld(pb.qref, j, NX, e);
-#pragma unroll UNR
-      for (int e = 0; e < NU; ++e) {
-        rr[e] = ld(pb.rref, j, NU, e);
-        lo[e] = ld(pb.lu, j, NU, e);
-        hi[e] = ld(pb.uu, j, NU, e);
-      }
-    }
-    if (!pb.has_ubox) {
-#pragma unroll UNR
-      for (int e = 0; e < NU; ++e) {
-        lo[e] = -INFINITY;
-        hi[e] = INFINITY;
-      }
+      for (int e = 0; e < E; ++e) out[e] = ld(arr, j, E, e);
     }
   }
 
   // x_j = A x_{j-1} + B u_j + c about (xm1 = X_[j], ub = U_prev[j]); A_0 = 0 (lqp_utils.jl:288-296)
-  __device__ __forceinline__ void lin_stage(int j, const double* xm1, const double* ub, const double* dp, double* A,
+  template <bool DUB>
+  __device__ __forceinline__ void lin_stage(const DevProb& pb, int j, const double* xm1, const double* ub, const double* dp, double* A,
                                             double* Bm, double* c) const {
-    if constexpr (NX == 4 && NU == 2) {
-      if (pb.dyn_kind == DYN_DUBINS) {
-        double f[4], fx[16], fu[8];
-        dubins_f_fx_fu(xm1, ub, dp[0], dp[1], dp[2], pb.dyn_eps, f, fx, fu);
+    if constexpr (DUB && NX == 4 && NU == 2) {
+      double f[4], fx[16], fu[8];
+      dubins_f_fx_fu(xm1, ub, dp[0], dp[1], dp[2], pb.dyn_eps, f, fx, fu);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          double v = f[r];
+      for (int r = 0; r < 4; ++r) {
+        double v = f[r];
 #pragma unroll
-          for (int t = 0; t < 2; ++t) v -= fu[r * 2 + t] * ub[t];
-          if (j >= 1) {
+        for (int t = 0; t < 2; ++t) v -= fu[r * 2 + t] * ub[t];
+        if (j >= 1) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) v -= fx[r * 4 + t] * xm1[t];
-          }
-          c[r] = v;
+          for (int t = 0; t < 4; ++t) v -= fx[r * 4 + t] * xm1[t];
         }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) A[e] = (j >= 1) ? fx[e] : 0.0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Bm[e] = fu[e];
-        return;
+        c[r] = v;
       }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) A[e] = (j >= 1) ? fx[e] : 0.0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Bm[e] = fu[e];
+    } else {
+#pragma unroll UNR
+      for (int e = 0; e < NX * NX; ++e) A[e] = ld(pb.A, j, NX * NX, e);
+#pragma unroll UNR
+      for (int e = 0; e < NX * NU; ++e) Bm[e] = ld(pb.Bm, j, NX * NU, e);
+#pragma unroll UNR
+      for (int e = 0; e < NX; ++e) c[e] = ld(pb.c, j, NX, e);
     }
-#pragma unroll UNR
-    for (int e = 0; e < NX * NX; ++e) A[e] = ld(pb.A, j, NX * NX, e);
-#pragma unroll UNR
-    for (int e = 0; e < NX * NU; ++e) Bm[e] = ld(pb.Bm, j, NX * NU, e);
-#pragma unroll UNR
-    for (int e = 0; e < NX; ++e) c[e] = ld(pb.c, j, NX, e);
   }
 
   // lane 0: stream the backward-sweep inputs of stage jj into ring slot `sl`
-  __device__ __forceinline__ void issue_b(int jj, int sl, bool kkt) {
-    double* dst = ring + sl * SLOT;
-    uint64_t* bar = bars + sl;
+  template <bool UBOX>
+  __device__ __forceinline__ void issue_b(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl) {
+    double* dst = sm.ring + sl * SLOT;
+    uint64_t* bar = sm.bars + sl;
     uint32_t bytes = NU * 256;
     if (jj >= 1) bytes += NX * 256;
-    if (kkt) bytes += (NX + NU) * 256;
-    if (pb.has_ubox) bytes += NU * 32;
+    if (UBOX) bytes += NU * 32;
     mbar_expect_tx(bar, bytes);
     if (jj >= 1) bulk_g2s(dst + R_XP, blk(Xpv, jj - 1, NX), NX * 256, bar);
     bulk_g2s(dst + R_UP, blk(Upv, jj, NU), NU * 256, bar);
-    if (kkt) {
-      bulk_g2s(dst + R_X, blk(Xc, jj, NX), NX * 256, bar);
-      bulk_g2s(dst + R_U, blk(Uc, jj, NU), NU * 256, bar);
-    }
-    if (pb.has_ubox)
-      bulk_g2s(dst + R_ACT, pb.act + (((size_t)(g >> 5) * (size_t)N + (size_t)jj) * NU) * 32, NU * 32, bar);
+    if (UBOX) bulk_g2s(dst + R_ACTB, blk(pb.act, jj, NU), NU * 32, bar);
   }
-  __device__ __forceinline__ void issue_f(int jj, int sl) {
-    double* dst = ring + sl * SLOT;
-    uint64_t* bar = bars + sl;
+  template <bool UBOX>
+  __device__ __forceinline__ void issue_f(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl) {
+    double* dst = sm.ring + sl * SLOT;
+    uint64_t* bar = sm.bars + sl;
     const FactorSet& F = pb.fs[MODE_POLISH];
     uint32_t bytes = (NX + NU) * 256;
-    if (jj >= Nc) bytes += (NU * NX + NU) * 256;
+    if (jj >= Nc) bytes += (NU * NX + NU) * 256 + (UBOX ? NR * 256 + NU * 32 : 0);
     mbar_expect_tx(bar, bytes);
     bulk_g2s(dst + R_XP, blk(Xpv, jj, NX), NX * 256, bar);
     bulk_g2s(dst + R_UP, blk(Upv, jj, NU), NU * 256, bar);
     if (jj >= Nc) {
       bulk_g2s(dst + R_K, blk(F.K, jj, NU * NX), NU * NX * 256, bar);
       bulk_g2s(dst + R_KF, blk(pb.kff, jj, NU), NU * 256, bar);
+      if (UBOX) {
+        bulk_g2s(dst + R_H, blk(pb.Hs, jj, NR), NR * 256, bar);
+        bulk_g2s(dst + R_ACTF, blk(pb.act, jj, NU), NU * 32, bar);
+      }
     }
   }
 
-  // Backward sweep.  kkt: check the iterate (Xc, Uc) and move to the proposed active set on the fly.
-  // first: the linearisation point changed since the last sweep (store the shared-stage data).
-  __device__ __forceinline__ void bsweep(bool kkt, bool first, double* st, double* pc, double* zc) {
+  // Backward sweep over the stages j = N-1 .. (first ? 0 : Nc).  Free stages (j >= Nc): masked
+  // Riccati matrix + vector step; shared stages (j < Nc, only when the linearisation point changed
+  // since the last sweep): store the stage data the consensus Schur step (K3) reads.
+  template <bool SLEW, bool UBOX, bool DUB>
+  __device__ __forceinline__ void bsweep(const DevProb& pb, unsigned char* smem, bool first, double* pc, double* zc) {
     const FactorSet& F = pb.fs[MODE_POLISH];
-    const bool on_the_fly = (NX == 4 && NU == 2 && pb.dyn_kind == DYN_DUBINS);
-    const bool use_ring = RING_SHAPE && ring != nullptr;
+    const Sm sm = smem_view(pb, smem);
+    const bool use_ring = RING_SHAPE && sm.ring != nullptr;
+    const int jmin = first ? 0 : Nc;
+    // linearisation point, re-derived from the kernel parameter (global-memory pointers, not the generic members)
+    const double* const Xpv = flip ? pb.X : pb.Xp;
+    const double* const Upv = flip ? pb.U : pb.Up;
     double dp[3] = {0.0, 0.0, 0.0};
-    if (on_the_fly) {
+    if (DUB) {
       dp[0] = ldp(pb.dynp, 0); dp[1] = ldp(pb.dynp, 1); dp[2] = ldp(pb.dynp, 2);
     }
-    double Pm[NX * NX], W[NX * NU], Z[NU * NU], p[NX], z[NU], Ata[NX], un[NU], xq[NX];
+    double Pm[NQ], W[SLEW ? NX * NU : 1], Z[SLEW ? NU * NU : 1], p[NX], z[SLEW ? NU : 1], xq[NX];
 #pragma unroll UNR
-    for (int e = 0; e < NX * NX; ++e) Pm[e] = 0.0;
+    for (int e = 0; e < NQ; ++e) Pm[e] = 0.0;
+    if (SLEW) {
 #pragma unroll UNR
-    for (int e = 0; e < NX * NU; ++e) W[e] = 0.0;
+      for (int e = 0; e < NX * NU; ++e) W[e] = 0.0;
 #pragma unroll UNR
-    for (int e = 0; e < NU * NU; ++e) Z[e] = 0.0;
+      for (int e = 0; e < NU * NU; ++e) Z[e] = 0.0;
 #pragma unroll UNR
-    for (int e = 0; e < NX; ++e) { p[e] = 0.0; Ata[e] = 0.0; }
+      for (int e = 0; e < NU; ++e) z[e] = 0.0;
+    }
 #pragma unroll UNR
-    for (int e = 0; e < NU; ++e) { z[e] = 0.0; un[e] = 0.0; }
+    for (int e = 0; e < NX; ++e) p[e] = 0.0;
     if (use_ring) {
       __syncwarp();
       if (lane == 0) {
         for (int d = 0; d < DEPTH; ++d)
-          if (N - 1 - d >= 0) issue_b(N - 1 - d, (rcount + d) % DEPTH, kkt);
+          if (N - 1 - d >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, N - 1 - d, (rcount + d) % DEPTH);
       }
     }
 #pragma unroll UNR
     for (int e = 0; e < NX; ++e) xq[e] = ld(Xpv, N - 1, NX, e);
-    double kkt_v = 0.0, uviol = 0.0, xviol = 0.0, changed = 0.0, gscale = 1.0, zscale = 1.0, nanf = 0.0;
-    double* sc = scr();
 #pragma unroll UNR
     for (int e = 0; e < NX; ++e) pc[e] = 0.0;
 #pragma unroll UNR
@@ -233,183 +225,133 @@
 #pragma unroll UNR
       for (int e = 0; e < NU * NU; ++e) F.Zc[(size_t)e * P + g] = 0.0;
     }
-    for (int j = N - 1; j >= 0; --j) {
+    for (int j = N - 1; j >= jmin; --j) {
       // ---- stage inputs
-      double xm1[NX], ub[NU], xs[NX], us[NU], ups[NU];
+      double xm1[NX], ub[NU];
       signed char act[NU];
       if (use_ring) {
         const int sl = rcount % DEPTH;
-        mbar_wait(bars + sl, (rcount / DEPTH) & 1);
-        const double* b = ring + sl * SLOT + col;
+        mbar_wait(sm.bars + sl, (rcount / DEPTH) & 1);
+        const double* b = sm.ring + sl * SLOT + col;
 #pragma unroll UNR
         for (int e = 0; e < NX; ++e) xm1[e] = (j >= 1) ? b[R_XP + e * 32] : ldp(pb.x0, e);
 #pragma unroll UNR
         for (int e = 0; e < NU; ++e) ub[e] = b[R_UP + e * 32];
-        if (kkt) {
+        if (UBOX) {
+          const signed char* ab = reinterpret_cast<const signed char*>(sm.ring + sl * SLOT + R_ACTB) + col;
 #pragma unroll UNR
-          for (int e = 0; e < NX; ++e) xs[e] = b[R_X + e * 32];
-#pragma unroll UNR
-          for (int e = 0; e < NU; ++e) us[e] = b[R_U + e * 32];
+          for (int t = 0; t < NU; ++t) act[t] = (j >= Nc) ? ab[t * 32] : 0;
         }
-        const signed char* ab = reinterpret_cast<const signed char*>(ring + sl * SLOT + R_ACT) + col;
-#pragma unroll UNR
-        for (int t = 0; t < NU; ++t) act[t] = (pb.has_ubox && j >= Nc) ? ab[t * 32] : 0;
         __syncwarp();
-        if (lane == 0 && j - DEPTH >= 0) issue_b(j - DEPTH, sl, kkt);
+        if (lane == 0 && j - DEPTH >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, j - DEPTH, sl);
         ++rcount;
       } else {
 #pragma unroll UNR
         for (int e = 0; e < NX; ++e) xm1[e] = (j >= 1) ? ld(Xpv, j - 1, NX, e) : ldp(pb.x0, e);
 #pragma unroll UNR
         for (int e = 0; e < NU; ++e) ub[e] = ld(Upv, j, NU, e);
-        if (kkt) {
+        if (UBOX) {
 #pragma unroll UNR
-          for (int e = 0; e < NX; ++e) xs[e] = ld(Xc, j, NX, e);
-#pragma unroll UNR
-          for (int e = 0; e < NU; ++e) us[e] = ld(Uc, j, NU, e);
+          for (int t = 0; t < NU; ++t) act[t] = (j >= Nc) ? pb.act[ix(j, NU, t)] : 0;
         }
-#pragma unroll UNR
-        for (int t = 0; t < NU; ++t) act[t] = (pb.has_ubox && j >= Nc) ? pb.act[ix(j, NU, t)] : 0;
       }
-      if (kkt) {
-#pragma unroll UNR
-        for (int e = 0; e < NU; ++e) ups[e] = (pb.has_slew && j >= 1) ? ld(Uc, j - 1, NU, e) : 0.0;
-      }
-      double Qp[NQ], Rp[NR], q[NX], r[NU], lo[NU], hi[NU];
-      stage_cost(j, Qp, Rp, q, r, lo, hi);
+      double A[NX * NX], Bm[NX * NU], cv[NX];
+      lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
+      // proximal / reference linear terms (lqp_utils.jl:164-214)
+      double q[NX], r[NU];
+      cost_field(sm.tab, j, T_QR, NX, pb.qref, q);
+      cost_field(sm.tab, j, T_RR, NU, pb.rref, r);
 #pragma unroll UNR
       for (int e = 0; e < NX; ++e) q[e] = -q[e] - pb.reg_x * xq[e];
 #pragma unroll UNR
       for (int e = 0; e < NU; ++e) r[e] = -r[e] - pb.reg_u * ub[e];
-      double A[NX * NX], Bm[NX * NU], cv[NX];
-      lin_stage(j, xm1, ub, dp, A, Bm, cv);
-      // ---- adjoint / KKT of the current iterate (kkt_sweep, fused)
-      if (kkt) {
-        double a[NX];
+      if (j >= Nc) {
+        // ---- Riccati step with the stage's active set.  S = Qs + P (symmetric, packed)
+        double S[NQ];
+        cost_field(sm.tab, j, T_QS, NQ, pb.Qs, S);
+#pragma unroll UNR
+        for (int e = 0; e < NQ; ++e) S[e] += Pm[e];
+        // wv = S c + q + p
+        double wv[NX];
 #pragma unroll UNR
         for (int rr = 0; rr < NX; ++rr) {
-          double acc = q[rr] + Ata[rr];
-          gscale = fmax(gscale, fabs(q[rr]));
-          zscale = fmax(zscale, fabs(xs[rr]));
-          if (!(xs[rr] == xs[rr])) nanf = 1.0;
+          double acc = q[rr] + p[rr];
 #pragma unroll UNR
-          for (int t = 0; t < NX; ++t) acc += symQ(Qp, rr, t) * xs[t];
-          a[rr] = acc;
+          for (int k = 0; k < NX; ++k) acc += S[rr <= k ? pk(rr, k, NX) : pk(k, rr, NX)] * cv[k];
+          wv[rr] = acc;
         }
-        if (pb.has_xbox) {
-#pragma unroll UNR
-          for (int rr = 0; rr < NX; ++rr)
-            xviol = fmax(xviol, fmax(xs[rr] - ld(pb.ux, j, NX, rr), ld(pb.lx, j, NX, rr) - xs[rr]));
-        }
-#pragma unroll UNR
-        for (int b = 0; b < NU; ++b) {
-          double acc = r[b];
-          gscale = fmax(gscale, fabs(r[b]));
-          zscale = fmax(zscale, fabs(us[b]));
-          if (!(us[b] == us[b])) nanf = 1.0;
-#pragma unroll UNR
-          for (int t = 0; t < NU; ++t) acc += symR(Rp, b, t) * us[t];
-#pragma unroll UNR
-          for (int rr = 0; rr < NX; ++rr) acc += Bm[rr * NU + b] * a[rr];
-          if (j >= 1) acc += s * (us[b] - ups[b]);
-          if (j < N - 1) acc += s * (us[b] - un[b]);
-          if (j < Nc) {
-            sc[(size_t)(j * NU + b) * T + tid] = valid ? acc : 0.0;
-          } else {
-            const double mu = -acc, ubv = us[b];
-            uviol = fmax(uviol, fmax(ubv - hi[b], lo[b] - ubv));
-            const bool at_hi = ubv >= hi[b] - 1e-12 * fmax(1.0, fabs(hi[b]));
-            const bool at_lo = ubv <= lo[b] + 1e-12 * fmax(1.0, fabs(lo[b]));
-            double v;
-            if (at_hi && at_lo) v = 0.0;
-            else if (at_hi) v = fmax(acc, 0.0);
-            else if (at_lo) v = fmax(-acc, 0.0);
-            else v = fabs(acc);
-            kkt_v = fmax(kkt_v, v);
-            if (pb.has_ubox) {
-              signed char na = 0;
-              if (mu + (ubv - hi[b]) > 0.0 && hi[b] < INFINITY) na = 1;
-              else if (mu + (ubv - lo[b]) < 0.0 && lo[b] > -INFINITY) na = -1;
-              if (na != act[b]) {
-                changed += 1.0;
-                act[b] = na;
-                if (valid) pb.act[ix(j, NU, b)] = na;
-              }
-            }
-          }
-        }
-#pragma unroll UNR
-        for (int t = 0; t < NU; ++t) un[t] = us[t];
-#pragma unroll UNR
-        for (int t = 0; t < NX; ++t) {
-          double acc = 0.0;
-#pragma unroll UNR
-          for (int rr = 0; rr < NX; ++rr) acc += A[rr * NX + t] * a[rr];
-          Ata[t] = acc;
-        }
-      }
-      if (j >= Nc) {
-        // ---- Riccati matrix step with the stage's active set, then the vector step
-        double S[NX * NX], SBW[NX * NU], H[NU * NU], E[NU * NU], ufix[NU];
-        bool fixed[NU];
-#pragma unroll UNR
-        for (int rr = 0; rr < NX; ++rr)
-#pragma unroll UNR
-          for (int t = rr; t < NX; ++t) {
-            const double v = Qp[pk(rr, t, NX)] + Pm[rr * NX + t];
-            S[rr * NX + t] = v;
-            S[t * NX + rr] = v;
-          }
+        // SBW = S B + W
+        double SBW[NX * NU];
 #pragma unroll UNR
         for (int rr = 0; rr < NX; ++rr)
 #pragma unroll UNR
           for (int t = 0; t < NU; ++t) {
-            double acc = W[rr * NU + t];
+            double acc = SLEW ? W[rr * NU + t] : 0.0;
 #pragma unroll UNR
-            for (int k = 0; k < NX; ++k) acc += S[rr * NX + k] * Bm[k * NU + t];
+            for (int k = 0; k < NX; ++k) acc += S[rr <= k ? pk(rr, k, NX) : pk(k, rr, NX)] * Bm[k * NU + t];
             SBW[rr * NU + t] = acc;
           }
+        // H = Rs + [j>=1] s I + B'(SB + W) + W'B + Z ;  h0 = r + B'wv + W'c + z
+        double H[NU * NU], h0[NU];
+        {
+          double Rp[NR];
+          cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
 #pragma unroll UNR
-        for (int a = 0; a < NU; ++a)
+          for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
-          for (int b = a; b < NU; ++b) {
-            double acc = Rp[pk(a, b, NU)] + Z[a * NU + b];
-            if (a == b) acc += (j >= 1 ? s : 0.0);
+            for (int b = a; b < NU; ++b) {
+              double acc = Rp[pk(a, b, NU)];
+              if (SLEW) {
+                acc += Z[a * NU + b];
+                if (a == b && j >= 1) acc += s;
+              }
 #pragma unroll UNR
-            for (int k = 0; k < NX; ++k) acc += Bm[k * NU + a] * SBW[k * NU + b] + W[k * NU + a] * Bm[k * NU + b];
-            H[a * NU + b] = acc;
-            H[b * NU + a] = acc;
-          }
-#pragma unroll UNR
-        for (int t = 0; t < NU; ++t) {
-          fixed[t] = act[t] != 0;
-          ufix[t] = (act[t] > 0) ? hi[t] : ((act[t] < 0) ? lo[t] : 0.0);
+              for (int k = 0; k < NX; ++k) {
+                acc += Bm[k * NU + a] * SBW[k * NU + b];
+                if (SLEW) acc += W[k * NU + a] * Bm[k * NU + b];
+              }
+              H[a * NU + b] = acc;
+              H[b * NU + a] = acc;
+            }
         }
-        masked_spd_inverse<NU>(H, fixed, E);
-        double tk[NX], eta[NX], h[NU], kv[NU];
-#pragma unroll UNR
-        for (int rr = 0; rr < NX; ++rr) {
-          double acc = 0.0;
-#pragma unroll UNR
-          for (int t = 0; t < NU; ++t) acc += SBW[rr * NU + t] * ufix[t];
-          tk[rr] = acc;
-        }
-        // eta = S c + SBW ufix + q + p
-#pragma unroll UNR
-        for (int rr = 0; rr < NX; ++rr) {
-          double acc = tk[rr] + q[rr] + p[rr];
-#pragma unroll UNR
-          for (int k = 0; k < NX; ++k) acc += S[rr * NX + k] * cv[k];
-          eta[rr] = acc;
-        }
-        // h = r + [W'c - B' tk + H ufix] + z + B' eta
 #pragma unroll UNR
         for (int a = 0; a < NU; ++a) {
-          double acc = r[a] + z[a];
+          double acc = r[a] + (SLEW ? z[a] : 0.0);
 #pragma unroll UNR
-          for (int k = 0; k < NX; ++k) acc += W[k * NU + a] * cv[k] + Bm[k * NU + a] * (eta[k] - tk[k]);
+          for (int k = 0; k < NX; ++k) {
+            acc += Bm[k * NU + a] * wv[k];
+            if (SLEW) acc += W[k * NU + a] * cv[k];
+          }
+          h0[a] = acc;
+        }
+        bool fixed[NU];
+        double ufix[NU], E[NU * NU];
 #pragma unroll UNR
-          for (int t = 0; t < NU; ++t) acc += H[a * NU + t] * ufix[t];
+        for (int t = 0; t < NU; ++t) {
+          fixed[t] = false;
+          ufix[t] = 0.0;
+        }
+        if (UBOX) {
+          double lo[NU], hi[NU];
+          cost_field(sm.tab, j, T_LU, NU, pb.lu, lo);
+          cost_field(sm.tab, j, T_UU, NU, pb.uu, hi);
+#pragma unroll UNR
+          for (int t = 0; t < NU; ++t) {
+            fixed[t] = act[t] != 0;
+            ufix[t] = (act[t] > 0) ? hi[t] : ((act[t] < 0) ? lo[t] : 0.0);
+          }
+        }
+        masked_spd_inverse<NU>(H, fixed, E);
+        // h = h0 + H ufix ; k = ufix - E h ; eta = wv + SBW k_full ... (the value-function recursion uses the
+        // closed-loop form below, so only h and k are needed)
+        double h[NU], kv[NU];
+#pragma unroll UNR
+        for (int a = 0; a < NU; ++a) {
+          double acc = h0[a];
+          if (UBOX) {
+#pragma unroll UNR
+            for (int t = 0; t < NU; ++t) acc += H[a * NU + t] * ufix[t];
+          }
           h[a] = acc;
         }
 #pragma unroll UNR
@@ -419,9 +361,9 @@
           for (int b = 0; b < NU; ++b) acc -= E[a * NU + b] * h[b];
           kv[a] = acc;
         }
-        double K[NU * NX];
+        double K[NU * NX], G[NU * NX];
         if (j >= 1) {
-          double G[NU * NX], SA[NX * NX];
+          // G = (SB + W)' A ;  K = -E G
 #pragma unroll UNR
           for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
@@ -440,64 +382,102 @@
               for (int b = 0; b < NU; ++b) acc -= E[a * NU + b] * G[b * NX + t];
               K[a * NX + t] = acc;
             }
-#pragma unroll UNR
-          for (int rr = 0; rr < NX; ++rr)
-#pragma unroll UNR
-            for (int t = 0; t < NX; ++t) {
-              double acc = 0.0;
-#pragma unroll UNR
-              for (int k = 0; k < NX; ++k) acc += S[rr * NX + k] * A[k * NX + t];
-              SA[rr * NX + t] = acc;
-            }
-#pragma unroll UNR
-          for (int rr = 0; rr < NX; ++rr)
-#pragma unroll UNR
-            for (int t = rr; t < NX; ++t) {
-              double acc = 0.0;
-#pragma unroll UNR
-              for (int k = 0; k < NX; ++k) acc += A[k * NX + rr] * SA[k * NX + t];
-#pragma unroll UNR
-              for (int a = 0; a < NU; ++a) acc += G[a * NX + rr] * K[a * NX + t];
-              Pm[rr * NX + t] = acc;
-              Pm[t * NX + rr] = acc;
-            }
-          // p <- A' eta + K' h ; z <- -s k
+          // p <- A'(wv + SBW k) + G'... : with u = K x + k the cost-to-go gradient is
+          //   p' = A' wv + G' k   (+ K'(h0 + H k + ...) = 0 on free comps, and fixed comps have K = 0)
+          double pn[NX];
 #pragma unroll UNR
           for (int t = 0; t < NX; ++t) {
             double acc = 0.0;
 #pragma unroll UNR
-            for (int rr = 0; rr < NX; ++rr) acc += A[rr * NX + t] * eta[rr];
+            for (int rr = 0; rr < NX; ++rr) acc += A[rr * NX + t] * wv[rr];
 #pragma unroll UNR
-            for (int a = 0; a < NU; ++a) acc += K[a * NX + t] * h[a];
-            p[t] = acc;
+            for (int a = 0; a < NU; ++a) acc += G[a * NX + t] * kv[a];
+            pn[t] = acc;
           }
 #pragma unroll UNR
-          for (int a = 0; a < NU; ++a) z[a] = -s * kv[a];
+          for (int t = 0; t < NX; ++t) p[t] = pn[t];
+          // P <- A' S A + G' K   (column t of S A at a time keeps the live set small)
+          double Pn[NQ];
+#pragma unroll UNR
+          for (int t = 0; t < NX; ++t) {
+            double sa[NX];
+#pragma unroll UNR
+            for (int rr = 0; rr < NX; ++rr) {
+              double acc = 0.0;
+#pragma unroll UNR
+              for (int k = 0; k < NX; ++k) acc += S[rr <= k ? pk(rr, k, NX) : pk(k, rr, NX)] * A[k * NX + t];
+              sa[rr] = acc;
+            }
+#pragma unroll UNR
+            for (int rr = 0; rr <= t; ++rr) {
+              double acc = 0.0;
+#pragma unroll UNR
+              for (int k = 0; k < NX; ++k) acc += A[k * NX + rr] * sa[k];
+#pragma unroll UNR
+              for (int a = 0; a < NU; ++a) acc += G[a * NX + rr] * K[a * NX + t];
+              Pn[pk(rr, t, NX)] = acc;
+            }
+          }
+#pragma unroll UNR
+          for (int e = 0; e < NQ; ++e) Pm[e] = Pn[e];
+          if (SLEW) {
+#pragma unroll UNR
+            for (int a = 0; a < NU; ++a) z[a] = -s * kv[a];
+          }
         } else {
 #pragma unroll UNR
-          for (int e = 0; e < NU * NX; ++e) K[e] = 0.0;
+          for (int e = 0; e < NU * NX; ++e) { K[e] = 0.0; G[e] = 0.0; }
         }
+        if (SLEW) {
+          // value-function slew blocks for the previous stage: W = -s K', Z = s I - s^2 E
 #pragma unroll UNR
-        for (int rr = 0; rr < NX; ++rr)
+          for (int rr = 0; rr < NX; ++rr)
 #pragma unroll UNR
-          for (int t = 0; t < NU; ++t) W[rr * NU + t] = -s * K[t * NX + rr];
+            for (int t = 0; t < NU; ++t) W[rr * NU + t] = -s * K[t * NX + rr];
 #pragma unroll UNR
-        for (int a = 0; a < NU; ++a)
+          for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
-          for (int b = 0; b < NU; ++b) Z[a * NU + b] = (a == b ? s : 0.0) - s * s * E[a * NU + b];
+            for (int b = 0; b < NU; ++b) Z[a * NU + b] = (a == b ? s : 0.0) - s * s * E[a * NU + b];
+        }
         if (valid) {
+          // fixed controls: the (otherwise 0 / bound) slots carry G[a,:], h0[a] for the multiplier
 #pragma unroll UNR
-          for (int e = 0; e < NU * NX; ++e) at(F.K, j, NU * NX, e) = K[e];
+          for (int a = 0; a < NU; ++a) {
 #pragma unroll UNR
-          for (int a = 0; a < NU; ++a) at(pb.kff, j, NU, a) = kv[a];
-          if (pb.has_slew) {
+            for (int t = 0; t < NX; ++t) at(F.K, j, NU * NX, a * NX + t) = (UBOX && fixed[a]) ? G[a * NX + t] : K[a * NX + t];
+            at(pb.kff, j, NU, a) = (UBOX && fixed[a]) ? h0[a] : kv[a];
+          }
+          if (UBOX) {
+#pragma unroll UNR
+            for (int a = 0; a < NU; ++a)
+#pragma unroll UNR
+              for (int b = a; b < NU; ++b) at(pb.Hs, j, NR, pk(a, b, NU)) = H[a * NU + b];
+          }
+          if (SLEW) {
 #pragma unroll UNR
             for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
               for (int b = a; b < NU; ++b) at(F.E, j, NR, pk(a, b, NU)) = E[a * NU + b];
           }
         }
-      } else if (first && valid) {
+        if (j == Nc && Nc >= 1) {
+          if (valid) {
+#pragma unroll UNR
+            for (int rr = 0; rr < NX; ++rr)
+#pragma unroll UNR
+              for (int t = 0; t < NX; ++t)
+                F.Pc[(size_t)(rr * NX + t) * P + g] = Pm[rr <= t ? pk(rr, t, NX) : pk(t, rr, NX)];
+#pragma unroll UNR
+            for (int e = 0; e < NX * NU; ++e) F.Wc[(size_t)e * P + g] = SLEW ? W[e] : 0.0;
+#pragma unroll UNR
+            for (int e = 0; e < NU * NU; ++e) F.Zc[(size_t)e * P + g] = SLEW ? Z[e] : 0.0;
+          }
+#pragma unroll UNR
+          for (int e = 0; e < NX; ++e) pc[e] = p[e];
+#pragma unroll UNR
+          for (int e = 0; e < NU; ++e) zc[e] = SLEW ? z[e] : 0.0;
+        }
+      } else if (valid) {
         // shared stages: the consensus Schur step (build_shared_system / solve_shared) reads these
 #pragma unroll UNR
         for (int e = 0; e < NX * NX; ++e) at(pb.A, j, NX * NX, e) = A[e];
@@ -511,84 +491,32 @@
 #pragma unroll UNR
         for (int e = 0; e < NU; ++e) at(pb.r, j, NU, e) = r[e];
       }
-      if (j == Nc && Nc >= 1) {
-        if (valid) {
-#pragma unroll UNR
-          for (int e = 0; e < NX * NX; ++e) F.Pc[(size_t)e * P + g] = Pm[e];
-#pragma unroll UNR
-          for (int e = 0; e < NX * NU; ++e) F.Wc[(size_t)e * P + g] = W[e];
-#pragma unroll UNR
-          for (int e = 0; e < NU * NU; ++e) F.Zc[(size_t)e * P + g] = Z[e];
-        }
-#pragma unroll UNR
-        for (int e = 0; e < NX; ++e) pc[e] = p[e];
-#pragma unroll UNR
-        for (int e = 0; e < NU; ++e) zc[e] = z[e];
-      }
 #pragma unroll UNR
       for (int e = 0; e < NX; ++e) xq[e] = xm1[e];
     }
-    if (use_ring) fence_proxy_async();  // K, k, act written above are bulk-copied by the next sweep
-    if (kkt) {
-      st[ST_KKT] = kkt_v; st[ST_UVIOL] = uviol; st[ST_XVIOL] = xviol; st[ST_CHANGED] = changed;
-      st[ST_GSCALE] = gscale; st[ST_ZSCALE] = zscale; st[ST_NAN] = fmax(st[ST_NAN], nanf);
-      if (GROUPED && Nc >= 1) {
-        // shared block: summed reduced gradient -> multipliers / proposed active set (kkt_sweep tail)
-        double* muc = pb.muc + (size_t)prob * D;
-        reduce(D, muc);
-        const size_t g0 = (size_t)prob * pb.Mpad;
-        const double* uc = pb.uc + (size_t)prob * D;
-        signed char* actc = pb.actc + (size_t)prob * D;
-        double ch = 0.0, kk = 0.0, uv = 0.0;
-        for (int k = 0; k < D; ++k) {  // every thread evaluates the (tiny) shared block identically
-          const int jj = k / NU, b = k % NU;
-          const double acc = muc[k], mu = -acc, ubv = uc[k];
-          double lo = -INFINITY, hi = INFINITY;
-          if (pb.has_ubox) {
-            lo = pb.lu[ixg(jj, NU, b, g0)];
-            hi = pb.uu[ixg(jj, NU, b, g0)];
-          }
-          uv = fmax(uv, fmax(ubv - hi, lo - ubv));
-          const bool at_hi = ubv >= hi - 1e-12 * fmax(1.0, fabs(hi));
-          const bool at_lo = ubv <= lo + 1e-12 * fmax(1.0, fabs(lo));
-          double v;
-          if (at_hi && at_lo) v = 0.0;
-          else if (at_hi) v = fmax(acc, 0.0);
-          else if (at_lo) v = fmax(-acc, 0.0);
-          else v = fabs(acc);
-          kk = fmax(kk, v);
-          signed char na = 0;
-          if (pb.has_ubox) {
-            if (mu + (ubv - hi) > 0.0 && hi < INFINITY) na = 1;
-            else if (mu + (ubv - lo) < 0.0 && lo > -INFINITY) na = -1;
-          }
-          if (na != actc[k]) ch += 1.0;
-          pb.actcn[(size_t)prob * D + k] = na;  // adopted below, after every thread has read actc
-        }
-        st[ST_KKT] = fmax(st[ST_KKT], kk);
-        st[ST_UVIOL] = fmax(st[ST_UVIOL], uv);
-        st[ST_CHANGED] += ch;
-        __syncthreads();
-        for (int k = tid; k < D; k += T) actc[k] = pb.actcn[(size_t)prob * D + k];
-        __syncthreads();
-      }
-    }
+    if (use_ring) fence_proxy_async();  // K, k, H written above are bulk-copied by the next sweep
   }
 
-  // Forward sweep: rollout of the feedback policy + SCP bookkeeping against (Xpv, Upv).
-  __device__ __forceinline__ void fsweep(double* st) {
+  // Forward sweep: rollout of the feedback policy, multipliers + primal-dual active-set update of the
+  // free-stage controls, SCP bookkeeping against (Xpv, Upv).  Fills the per-thread statistics.
+  template <bool SLEW, bool UBOX, bool DUB>
+  __device__ __forceinline__ void fsweep(const DevProb& pb, unsigned char* smem, double* st) {
     const FactorSet& F = pb.fs[MODE_POLISH];
-    const bool on_the_fly = (NX == 4 && NU == 2 && pb.dyn_kind == DYN_DUBINS);
-    const bool use_ring = RING_SHAPE && ring != nullptr;
+    const Sm sm = smem_view(pb, smem);
+    const bool use_ring = RING_SHAPE && sm.ring != nullptr;
+    const double* const Xpv = flip ? pb.X : pb.Xp;
+    const double* const Upv = flip ? pb.U : pb.Up;
+    double* const Xc = flip ? pb.Xp : pb.X;
+    double* const Uc = flip ? pb.Up : pb.U;
     double dp[3] = {0.0, 0.0, 0.0};
-    if (on_the_fly) {
+    if (DUB) {
       dp[0] = ldp(pb.dynp, 0); dp[1] = ldp(pb.dynp, 1); dp[2] = ldp(pb.dynp, 2);
     }
     if (use_ring) {
       __syncwarp();
       if (lane == 0) {
         for (int d = 0; d < DEPTH; ++d)
-          if (d < N) issue_f(d, (rcount + d) % DEPTH);
+          if (d < N) issue_f<UBOX>(pb, sm, Xpv, Upv, d, (rcount + d) % DEPTH);
       }
     }
     const double* uc = (GROUPED && Nc >= 1) ? pb.uc + (size_t)prob * D : nullptr;
@@ -597,14 +525,18 @@
     for (int e = 0; e < NX; ++e) { x[e] = 0.0; xm1[e] = ldp(pb.x0, e); }
 #pragma unroll UNR
     for (int e = 0; e < NU; ++e) up[e] = 0.0;
-    double dxm = 0.0, dum = 0.0, obj = 0.0, nanf = 0.0;
+    double dxm = 0.0, dum = 0.0, obj = 0.0, nanf = 0.0, kkt_v = 0.0, uviol = 0.0, xviol = 0.0, changed = 0.0,
+           gscale = 1.0, zscale = 1.0;
     const double rdiag = pb.rdiag0[g];
     for (int j = 0; j < N; ++j) {
-      double ub[NU], xpj[NX], Kj[NU * NX], kf[NU], u[NU], xn[NX];
+      double ub[NU], xpj[NX], Kj[NU * NX], kf[NU], Hj[NR], u[NU], xn[NX];
+      signed char act[NU];
+#pragma unroll UNR
+      for (int t = 0; t < NU; ++t) act[t] = 0;
       if (use_ring) {
         const int sl = rcount % DEPTH;
-        mbar_wait(bars + sl, (rcount / DEPTH) & 1);
-        const double* b = ring + sl * SLOT + col;
+        mbar_wait(sm.bars + sl, (rcount / DEPTH) & 1);
+        const double* b = sm.ring + sl * SLOT + col;
 #pragma unroll UNR
         for (int e = 0; e < NX; ++e) xpj[e] = b[R_XP + e * 32];
 #pragma unroll UNR
@@ -614,9 +546,16 @@
           for (int e = 0; e < NU * NX; ++e) Kj[e] = b[R_K + e * 32];
 #pragma unroll UNR
           for (int e = 0; e < NU; ++e) kf[e] = b[R_KF + e * 32];
+          if (UBOX) {
+#pragma unroll UNR
+            for (int e = 0; e < NR; ++e) Hj[e] = b[R_H + e * 32];
+            const signed char* ab = reinterpret_cast<const signed char*>(sm.ring + sl * SLOT + R_ACTF) + col;
+#pragma unroll UNR
+            for (int t = 0; t < NU; ++t) act[t] = ab[t * 32];
+          }
         }
         __syncwarp();
-        if (lane == 0 && j + DEPTH < N) issue_f(j + DEPTH, sl);
+        if (lane == 0 && j + DEPTH < N) issue_f<UBOX>(pb, sm, Xpv, Upv, j + DEPTH, sl);
         ++rcount;
       } else {
 #pragma unroll UNR
@@ -628,28 +567,77 @@
           for (int e = 0; e < NU * NX; ++e) Kj[e] = ld(F.K, j, NU * NX, e);
 #pragma unroll UNR
           for (int e = 0; e < NU; ++e) kf[e] = ld(pb.kff, j, NU, e);
+          if (UBOX) {
+#pragma unroll UNR
+            for (int e = 0; e < NR; ++e) Hj[e] = ld(pb.Hs, j, NR, e);
+#pragma unroll UNR
+            for (int t = 0; t < NU; ++t) act[t] = pb.act[ix(j, NU, t)];
+          }
         }
+      }
+      double lo[NU], hi[NU];
+      if (UBOX) {
+        cost_field(sm.tab, j, T_LU, NU, pb.lu, lo);
+        cost_field(sm.tab, j, T_UU, NU, pb.uu, hi);
       }
       if (j < Nc) {
 #pragma unroll UNR
         for (int a = 0; a < NU; ++a) u[a] = uc[j * NU + a];
       } else {
+        // policy on the free controls, bound on the fixed ones; then the multipliers of the fixed ones
+        double gx[NU];  // K x (free) or G x (fixed)
 #pragma unroll UNR
         for (int a = 0; a < NU; ++a) {
-          double acc = kf[a];
+          double acc = 0.0;
           if (j >= 1) {
 #pragma unroll UNR
             for (int t = 0; t < NX; ++t) acc += Kj[a * NX + t] * x[t];
-            if (pb.has_slew) {
+          }
+          gx[a] = acc;
+        }
 #pragma unroll UNR
-              for (int b = 0; b < NU; ++b) acc += s * ld(F.E, j, NR, a <= b ? pk(a, b, NU) : pk(b, a, NU)) * up[b];
-            }
+        for (int a = 0; a < NU; ++a) {
+          double acc = kf[a] + gx[a];
+          if (SLEW && j >= 1) {
+#pragma unroll UNR
+            for (int b = 0; b < NU; ++b) acc += s * ld(F.E, j, NR, a <= b ? pk(a, b, NU) : pk(b, a, NU)) * up[b];
           }
           u[a] = acc;
+          if (UBOX && act[a] != 0) u[a] = (act[a] > 0) ? hi[a] : lo[a];
+        }
+        if (UBOX) {
+#pragma unroll UNR
+          for (int a = 0; a < NU; ++a) {
+            const double ua = u[a];
+            signed char na = 0;
+            if (act[a] != 0) {
+              // dQ/du_a = H[a,:] u + G[a,:] x + h0[a] - s u_{j-1,a}
+              double acc = kf[a] + gx[a];
+#pragma unroll UNR
+              for (int b = 0; b < NU; ++b) acc += Hj[a <= b ? pk(a, b, NU) : pk(b, a, NU)] * u[b];
+              if (SLEW && j >= 1) acc -= s * up[a];
+              const double mu = -acc;
+              if (act[a] > 0) {
+                kkt_v = fmax(kkt_v, fmax(acc, 0.0));
+                if (mu > 0.0) na = 1;
+              } else {
+                kkt_v = fmax(kkt_v, fmax(-acc, 0.0));
+                if (mu < 0.0) na = -1;
+              }
+            } else {
+              uviol = fmax(uviol, fmax(ua - hi[a], lo[a] - ua));
+              if (ua - hi[a] > 0.0 && hi[a] < INFINITY) na = 1;
+              else if (ua - lo[a] < 0.0 && lo[a] > -INFINITY) na = -1;
+            }
+            if (na != act[a]) {
+              changed += 1.0;
+              if (valid) pb.act[ix(j, NU, a)] = na;
+            }
+          }
         }
       }
       double A[NX * NX], Bm[NX * NU], cv[NX];
-      lin_stage(j, xm1, ub, dp, A, Bm, cv);
+      lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
 #pragma unroll UNR
       for (int r = 0; r < NX; ++r) {
         double acc = cv[r];
@@ -667,28 +655,18 @@
 #pragma unroll UNR
         for (int r = 0; r < NX; ++r) at(Xc, j, NX, r) = xn[r];
       }
-      // bookkeeping (scp_bookkeeping, fused)
-      double Qp[NQ], Rp[NR], xr[NX], ur[NU];
-      if (tab != nullptr) {
-        const double* t = tab + j * TW;
+      if (pb.has_xbox) {
 #pragma unroll UNR
-        for (int e = 0; e < NQ; ++e) Qp[e] = t[T_QS + e];
-#pragma unroll UNR
-        for (int e = 0; e < NR; ++e) Rp[e] = t[T_RS + e];
-#pragma unroll UNR
-        for (int e = 0; e < NX; ++e) xr[e] = t[T_XR + e];
-#pragma unroll UNR
-        for (int e = 0; e < NU; ++e) ur[e] = t[T_UR + e];
-      } else {
-#pragma unroll UNR
-        for (int e = 0; e < NQ; ++e) Qp[e] = ld(pb.Qs, j, NQ, e);
-#pragma unroll UNR
-        for (int e = 0; e < NR; ++e) Rp[e] = ld(pb.Rs, j, NR, e);
-#pragma unroll UNR
-        for (int e = 0; e < NX; ++e) xr[e] = ld(pb.xref, j, NX, e);
-#pragma unroll UNR
-        for (int e = 0; e < NU; ++e) ur[e] = ld(pb.uref, j, NU, e);
+        for (int r = 0; r < NX; ++r) xviol = fmax(xviol, fmax(xn[r] - ld(pb.ux, j, NX, r), ld(pb.lx, j, NX, r) - xn[r]));
       }
+      // bookkeeping (scp_mpc.py:397-405) and the scales of the acceptance test
+      double Qp[NQ], Rp[NR], xr[NX], ur[NU], qr[NX], rr_[NU];
+      cost_field(sm.tab, j, T_QS, NQ, pb.Qs, Qp);
+      cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
+      cost_field(sm.tab, j, T_XR, NX, pb.xref, xr);
+      cost_field(sm.tab, j, T_UR, NU, pb.uref, ur);
+      cost_field(sm.tab, j, T_QR, NX, pb.qref, qr);
+      cost_field(sm.tab, j, T_RR, NU, pb.rref, rr_);
       double dx[NX], du[NU], n2 = 0.0;
 #pragma unroll UNR
       for (int r = 0; r < NX; ++r) {
@@ -696,6 +674,8 @@
         n2 += d * d;
         dx[r] = xn[r] - xr[r];
         if (!(xn[r] == xn[r])) nanf = 1.0;
+        zscale = fmax(zscale, fabs(xn[r]));
+        gscale = fmax(gscale, fabs(qr[r] + pb.reg_x * xpj[r]));
       }
       dxm = fmax(dxm, sqrt(n2));
       n2 = 0.0;
@@ -705,20 +685,22 @@
         n2 += d * d;
         du[t] = u[t] - ur[t];
         if (!(u[t] == u[t])) nanf = 1.0;
+        zscale = fmax(zscale, fabs(u[t]));
+        gscale = fmax(gscale, fabs(rr_[t] + pb.reg_u * ub[t]));
       }
       dum = fmax(dum, sqrt(n2));
 #pragma unroll UNR
       for (int r = 0; r < NX; ++r) {
         double acc = 0.0;
 #pragma unroll UNR
-        for (int t = 0; t < NX; ++t) acc += symQ(Qp, r, t) * dx[t];
+        for (int t = 0; t < NX; ++t) acc += Qp[r <= t ? pk(r, t, NX) : pk(t, r, NX)] * dx[t];
         obj += dx[r] * (acc - pb.reg_x * dx[r]);
       }
 #pragma unroll UNR
       for (int b = 0; b < NU; ++b) {
         double acc = 0.0;
 #pragma unroll UNR
-        for (int t = 0; t < NU; ++t) acc += symR(Rp, b, t) * du[t];
+        for (int t = 0; t < NU; ++t) acc += Rp[b <= t ? pk(b, t, NU) : pk(t, b, NU)] * du[t];
         obj += du[b] * (acc - (pb.reg_u + (j == 0 ? rdiag : 0.0)) * du[b]);
       }
 #pragma unroll UNR
@@ -726,47 +708,115 @@
 #pragma unroll UNR
       for (int a = 0; a < NU; ++a) up[a] = u[a];
     }
-    if (use_ring) fence_proxy_async();  // X, U written above are bulk-copied by the next sweep
+    if (use_ring) fence_proxy_async();  // X, U, act written above are bulk-copied by the next sweep
     st[ST_DX] = valid ? dxm : 0.0;
     st[ST_DU] = valid ? dum : 0.0;
     st[ST_OBJ] = valid ? obj : 0.0;
     st[ST_NAN] = nanf;
+    st[ST_KKT] = kkt_v; st[ST_UVIOL] = uviol; st[ST_XVIOL] = xviol; st[ST_CHANGED] = valid ? changed : 0.0;
+    st[ST_GSCALE] = gscale; st[ST_ZSCALE] = zscale;
   }
 
-  // One convex sub-problem on the fused path.  Returns status bits (as solve_qp), or -1 when the
-  // active-set iteration has to be globalised by ADMM (caller falls back to the unfused path).
-  __device__ __forceinline__ int fused_qp(double* st, long long* cnt) {
+  // Shared block: multipliers of the fixed shared controls from the assembled system,
+  // mu = -(Hc uc + gc), and the primal-dual update of its active set.  Returns the number of changes
+  // (identical in every thread); adds the block's KKT / bound violation into kk, uv.
+  __device__ __forceinline__ double shared_active_update(double* kk, double* uv) {
+    if (!GROUPED || Nc < 1) return 0.0;
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    const double* Hc = F.Hc + (size_t)prob * D * D;
+    const double* gc = pb.gc + (size_t)prob * D;
+    const double* uc = pb.uc + (size_t)prob * D;
+    signed char* actc = pb.actc + (size_t)prob * D;
+    signed char* actcn = pb.actcn + (size_t)prob * D;
+    const size_t g0 = (size_t)prob * pb.Mpad;
+    double ch = 0.0;
+    for (int k = 0; k < D; ++k) {  // every thread evaluates the (small) shared block identically
+      const int jj = k / NU, b = k % NU;
+      const double ubv = uc[k];
+      double lo = -INFINITY, hi = INFINITY;
+      if (pb.has_ubox) {
+        lo = pb.lu[ixg(jj, NU, b, g0)];
+        hi = pb.uu[ixg(jj, NU, b, g0)];
+      }
+      signed char na = 0;
+      if (actc[k] != 0) {
+        double acc = gc[k];
+        for (int l = 0; l < D; ++l) acc += Hc[(size_t)k * D + l] * uc[l];
+        if (actc[k] > 0) {
+          *kk = fmax(*kk, fmax(acc, 0.0));
+          if (-acc > 0.0) na = 1;
+        } else {
+          *kk = fmax(*kk, fmax(-acc, 0.0));
+          if (-acc < 0.0) na = -1;
+        }
+      } else {
+        *uv = fmax(*uv, fmax(ubv - hi, lo - ubv));
+        if (ubv - hi > 0.0 && hi < INFINITY) na = 1;
+        else if (ubv - lo < 0.0 && lo > -INFINITY) na = -1;
+      }
+      if (na != actc[k]) ch += 1.0;
+      if (tid == 0) actcn[k] = na;
+    }
+    __syncthreads();  // every thread has read actc
+    for (int k = tid; k < D; k += T) actc[k] = actcn[k];
+    __syncthreads();
+    return ch;
+  }
+
+  template <bool SLEW, bool UBOX, bool DUB>
+  __device__ __forceinline__ int fused_qp_impl(const DevProb& pb, unsigned char* smem, double* st, long long* cnt) {
     double pc[NX], zc[NU];
     const bool constrained = pb.has_ubox || pb.has_xbox;
     for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
     st[ST_GSCALE] = st[ST_ZSCALE] = 1.0;
-    bool kkt = false;
     for (int tries = 0;; ++tries) {
-      // backward: (verify the iterate, move the active set,) factor and solve
-      bsweep(kkt, !kkt, st, pc, zc);
+      bsweep<SLEW, UBOX, DUB>(pb, smem, tries == 0, pc, zc);
       cnt[2] += 1;
       cnt[7] += 1;
-      if (kkt) {
-        reduce_stats(st);
-        if (st[ST_NAN] > 0.0) return 1;
-        const double tol_g = pb.kkt_tol * st[ST_GSCALE], tol_z = pb.kkt_tol * st[ST_ZSCALE];
-        if (st[ST_KKT] <= tol_g && st[ST_UVIOL] <= tol_z && st[ST_XVIOL] <= tol_z) {
-          cnt[5] += 1;
-          return 0;
+      double kk_c = 0.0, uv_c = 0.0, ch_c = 0.0;
+      if (GROUPED && Nc >= 1) {
+        assemble_shared(MODE_POLISH, 0.0, 0.0);
+        grad_shared(MODE_POLISH, 0.0, 0.0, pc, zc);
+        // the shared block is a D-dimensional box QP once the particles' value functions are fixed:
+        // iterate its active set here, without sweeping the horizon again
+        for (int t = 0; t <= 2 * D; ++t) {
+          factor_shared(MODE_POLISH);
+          apply_shared(MODE_POLISH, 0.0);
+          if (!UBOX) break;
+          kk_c = uv_c = 0.0;
+          ch_c = shared_active_update(&kk_c, &uv_c);
+          if (ch_c == 0.0) break;
         }
-        if (st[ST_XVIOL] > tol_z || st[ST_CHANGED] <= 0.0 || tries >= pb.polish_iters) return -1;
       }
-      build_shared_system(MODE_POLISH, 0.0, 0.0);
-      solve_shared(MODE_POLISH, 0.0, 0.0, pc, zc);
-      fsweep(st);
+      fsweep<SLEW, UBOX, DUB>(pb, smem, st);
       cnt[3] += 1;
       cnt[7] += 1;
+      reduce_stats(st);
+      st[ST_KKT] = fmax(st[ST_KKT], kk_c);
+      st[ST_UVIOL] = fmax(st[ST_UVIOL], uv_c);
+      st[ST_CHANGED] += ch_c;
+      if (st[ST_NAN] > 0.0) return 1;
       if (!constrained) {
-        reduce_stats(st);
         cnt[5] += 1;
-        return (st[ST_NAN] > 0.0) ? 1 : 0;
+        return 0;
       }
-      kkt = true;
+      const double tol_g = pb.kkt_tol * st[ST_GSCALE], tol_z = pb.kkt_tol * st[ST_ZSCALE];
+      if (st[ST_KKT] <= tol_g && st[ST_UVIOL] <= tol_z && st[ST_XVIOL] <= tol_z) {
+        cnt[5] += 1;
+        return 0;
+      }
+      if (st[ST_XVIOL] > tol_z || st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) return -1;
     }
+  }
+
+  // One convex sub-problem on the fused path.  Returns status bits (as solve_qp), or -1 when the
+  // active-set iteration has to be globalised by ADMM (caller falls back to the unfused path).
+  // VAR (kernel template parameter, chosen by the host from the problem's flags): bit 0 = built-in
+  // Dubins linearisation on the fly, bit 1 = lean (no slew penalty: W, Z, z and E vanish at compile time).
+  template <int VAR>
+  __device__ __forceinline__ int fused_qp(const DevProb& pb, unsigned char* smem, double* st, long long* cnt) {
+    constexpr bool DUB = (VAR & 1) && NX == 4 && NU == 2;
+    constexpr bool LEAN = (VAR & 2) != 0;
+    return fused_qp_impl<!LEAN, true, DUB>(pb, smem, st, cnt);
   }
 

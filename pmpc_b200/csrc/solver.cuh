@@ -48,6 +48,7 @@ struct DevProb {
   double *Xp, *Up, *A, *Bm, *c, *q, *r;
   FactorSet fs[2];            // [MODE_POLISH], [MODE_ADMM]
   double *kff, *X, *U;
+  double *Hs;                 // fused path: stage Hessian H of the Q-function (packed), for the multipliers
   double *wu, *yu, *wx, *yx;
   signed char *act, *actn;    // per (particle, stage, control): -1 lower, +1 upper, 0 free
   // per problem
@@ -159,6 +160,8 @@ struct Solver {
   uint64_t* bars;
   uint32_t rcount;
   const double* tab;
+  bool has_tab;
+  bool flip;  // fused path: (Xc, Uc) / (Xpv, Upv) currently are (pb.Xp, pb.Up) / (pb.X, pb.U)
   bool dead;  // whole warp beyond the last problem (thread-per-problem launch tail)
 
   __device__ Solver(const DevProb& pb_, double* red_)
@@ -633,12 +636,17 @@ struct Solver {
   }
 
   // ---- K3: assemble and invert the shared-block system (cooperative, in global scratch) -------
-  __device__ __noinline__ void build_shared_system(int mode, double rho_u, double rho_x) {
+  __device__ __forceinline__ void build_shared_system(int mode, double rho_u, double rho_x) {
+    assemble_shared(mode, rho_u, rho_x);
+    factor_shared(mode);
+  }
+
+  // Hc = sum_i H_i (+ rho on the diagonal in ADMM mode), symmetrised
+  __device__ __noinline__ void assemble_shared(int mode, double rho_u, double rho_x) {
     if (!GROUPED || Nc < 1) return;
     const FactorSet& F = pb.fs[mode];
     double* Hc = F.Hc + (size_t)prob * D * D;
     double* Hi = F.Hci + (size_t)prob * D * D;
-    double* hb = F.hb + (size_t)prob * D;
     // columns of sum_i H_i; scratch holds D rows per column -> process in column chunks that fit
     const int rows_cap = (int)(pb.scratch_stride / T);
     const int cols_per_pass = max(1, rows_cap / D);
@@ -657,8 +665,7 @@ struct Solver {
       }
       __syncthreads();
     }
-    // symmetrise, add the ADMM penalty of the shared block, mask fixed components (polish)
-    const signed char* actc = pb.actc + (size_t)prob * D;
+    // symmetrise, add the ADMM penalty of the shared block
     for (int idx = tid; idx < D * D; idx += T) {
       const int a = idx / D, b = idx % D;
       if (a <= b) {
@@ -673,6 +680,16 @@ struct Solver {
       Hc[idx] = (a <= b) ? Hi[(size_t)a * D + b] : Hi[(size_t)b * D + a];
     }
     __syncthreads();
+  }
+
+  // masked inverse of Hc for the current shared active set (polish) and hb = Hc * beta
+  __device__ __noinline__ void factor_shared(int mode) {
+    if (!GROUPED || Nc < 1) return;
+    const FactorSet& F = pb.fs[mode];
+    double* Hc = F.Hc + (size_t)prob * D * D;
+    double* Hi = F.Hci + (size_t)prob * D * D;
+    double* hb = F.hb + (size_t)prob * D;
+    const signed char* actc = pb.actc + (size_t)prob * D;
     // hb = Hc * beta (beta = bound value on fixed comps) ; then masked matrix into Hi
     const bool masked = (mode == MODE_POLISH && pb.has_ubox);
     for (int a = tid; a < D; a += T) {
@@ -735,13 +752,23 @@ struct Solver {
   }
 
   // solve for the shared controls: uc = beta - Hi (gc + hb [+ admm terms])
-  __device__ __noinline__ void solve_shared(int mode, double rho_u, double rho_x, const double* pc, const double* zc) {
+  __device__ __forceinline__ void solve_shared(int mode, double rho_u, double rho_x, const double* pc, const double* zc) {
+    grad_shared(mode, rho_u, rho_x, pc, zc);
+    apply_shared(mode, rho_u);
+  }
+
+  // gc = sum_i gradient of particle i's cost w.r.t. the shared controls at uc = 0
+  __device__ __noinline__ void grad_shared(int mode, double rho_u, double rho_x, const double* pc, const double* zc) {
+    if (!GROUPED || Nc < 1) return;
+    shared_grad(mode, false, -1, nullptr, rho_u, rho_x, pc, zc, 0);
+    reduce(D, pb.gc + (size_t)prob * D);
+  }
+
+  __device__ __noinline__ void apply_shared(int mode, double rho_u) {
     if (!GROUPED || Nc < 1) return;
     const FactorSet& F = pb.fs[mode];
-    shared_grad(mode, false, -1, nullptr, rho_u, rho_x, pc, zc, 0);
-    double* gc = pb.gc + (size_t)prob * D;
+    const double* gc = pb.gc + (size_t)prob * D;
     double* uc = pb.uc + (size_t)prob * D;
-    reduce(D, gc);
     const double* Hi = F.Hci + (size_t)prob * D * D;
     const double* hb = F.hb + (size_t)prob * D;
     const signed char* actc = pb.actc + (size_t)prob * D;
@@ -1252,15 +1279,20 @@ struct Solver {
   }
 
   // ---- the SCP loop (scp_mpc.py:337-428) ----------------------------------------------------
-  __device__ void run(unsigned char* smem) {
+  // kp: the kernel's own __grid_constant__ parameter.  The fused path reads it directly (constant bank
+  // operands) instead of through the `pb` member, which the noinline helpers force into memory.
+  template <int VAR>
+  __device__ __forceinline__ void run(const DevProb& kp, unsigned char* smem) {
     fused_init(smem);
+    flip = false;
     if (dead) return;
     double st[ST_COUNT];
     for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
     long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bool writer = valid && (GROUPED ? tid == 0 : true);
-    const bool fused_ok = pb.fused && pb.polish &&
-                          (pb.dyn_kind == DYN_AFFINE || (NX == 4 && NU == 2 && pb.dyn_kind == DYN_DUBINS));
+    // the host launches the kernel variant that matches (dyn_kind, has_slew): see launch_scp_impl
+    const bool fused_ok = pb.fused && pb.polish && ((VAR & 1) != 0) == (pb.dyn_kind == DYN_DUBINS) &&
+                          !((VAR & 2) && pb.has_slew);
     double *solX = Xc, *solU = Uc;
     int it = 0;
     for (; it < pb.max_it; ++it) {
@@ -1268,7 +1300,7 @@ struct Solver {
       int status = -1;
       bool fused_done = false;
       if (fused_ok) {
-        status = fused_qp(st, cnt);
+        status = fused_qp<VAR>(kp, smem, st, cnt);
         fused_done = status >= 0;
       }
       if (!fused_done) {
@@ -1299,6 +1331,7 @@ struct Solver {
         if (!pb.keep_prev) {
           double* t0 = Xc; Xc = Xpv; Xpv = t0;
           double* t1 = Uc; Uc = Upv; Upv = t1;
+          flip = !flip;
         }
       } else {
         scp_bookkeeping(st);

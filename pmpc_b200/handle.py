@@ -153,6 +153,12 @@ class DeviceSolver:
         check(self.lib.pmpc_get_hist(self._h, dptr(buf), int(max_it)), "get_hist")
         return dict(obj=buf[0], resid=buf[1], admm_iters=buf[2], kkt=buf[3])
 
+    def occupancy(self):
+        """(resident CTAs per SM, SM count) of the solve kernel this handle launches."""
+        a, b = C.c_int(), C.c_int()
+        check(self.lib.pmpc_get_occupancy(self._h, C.byref(a), C.byref(b)), "get_occupancy")
+        return int(a.value), int(b.value)
+
     def timer_start(self):
         """CUDA event on the handle's stream (the stream every kernel of this handle runs on)."""
         check(self.lib.pmpc_timer_start(self._h), "timer_start")

@@ -14,6 +14,7 @@ st = dict((k, int(v)) for k, v in (kv.split('=') for kv in os.environ.get('PMPC_
 s = DeviceSolver(M, N, n, m, 1, B=B, settings=st or None)
 s.set_problem(x0, Q, R, None, None, None, None, -np.ones((B, M, N, m)), np.ones((B, M, N, m)), 1.0, 1e-2)
 s.set_dubins(np.tile(p, (B, 1, 1)))
+occ = s.occupancy(); print("occupancy: %d CTAs/SM x %d SMs" % occ, flush=True)
 for rep in range(reps):
     s.set_warm_start(None, None)
     t = time.time(); s.scp_solve(100, 1e-5); wall = time.time() - t
