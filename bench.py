@@ -205,7 +205,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=592, help="independent C2 problems per GPU per step")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="independent C2 problems per GPU per step (0 = --waves full waves: SMs x resident CTAs per SM x waves)")
+    ap.add_argument("--waves", type=int, default=8)
     ap.add_argument("--latency-solves", type=int, default=20)
     ap.add_argument("--cpu-sample-its", type=int, default=8)
     ap.add_argument("--ref-sample-its", type=int, default=2)
@@ -240,8 +242,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    K, W = args.steps, max(args.warmup, 0)
+    B = args.batch
+    if B <= 0:
+        # one CTA per problem: size the batch in whole waves of the solve kernel (148 SMs x resident CTAs)
+        a1, p1, d1 = make_batch(1, 0)
+        with DeviceSolver(M, N, NX, NU, NC, B=1, device=local) as probe:
+            probe.set_problem(a1["x0"], a1["Q"], a1["R"], a1["X_ref"], a1["U_ref"], None, None, a1["u_l"], a1["u_u"],
+                              d1["reg_x"], d1["reg_u"], np.zeros(M))
+            probe.set_dubins(p1)
+            ctas, sms = probe.occupancy()
+        B = ctas * sms * args.waves
     arrs, p, d0 = make_batch(B, rank)
+    # the e2e leg copies from page-locked host memory (the driver contract's "pinned host memory")
+    arrs = {k: pmpc_b200.pinned_copy(v) for k, v in arrs.items()}
+    p = pmpc_b200.pinned_copy(p)
     ds = DeviceSolver(M, N, NX, NU, NC, B=B, device=local)
     ds.set_problem(arrs["x0"], arrs["Q"], arrs["R"], arrs["X_ref"], arrs["U_ref"], None, None, arrs["u_l"], arrs["u_u"],
                    d0["reg_x"], d0["reg_u"], np.zeros(B * M))
@@ -271,11 +286,13 @@ def main():
     launches = int(parallel.reduce_sum(launches, dist, dev_t))
     info = ds.info()
     X, U = ds.solution()
+    X, U = X.copy(), U.copy()
     hist = ds.hist(int(info["scp_iters"].max()))
     last_res = np.array([hist["resid"][info["scp_iters"][b] - 1, b] for b in range(B)])
     ok = bool((info["status"] == 0).all() and (last_res < RES_TOL).all() and np.isfinite(X).all()
               and np.abs(U).max() <= 1 + 1e-9 and np.all(U[:, :, 0] == U[:, :1, 0]))
     kernel_ms = ds.last_kernel_ms()  # the last step's SCP kernel alone
+    occ = ds.occupancy()
     value = world * B * K / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (the SCP kernel) -----------------------------------------
@@ -289,8 +306,9 @@ def main():
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
             tr = json.load(fh)
-        if tr.get("batch") == B:
-            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        # ncu (--set full) DRAM read + write bytes of the same kernel, per problem, scaled to this launch
+        roofline["traffic"] = tr["dram_bytes_per_problem"] * B
+        roofline["traffic_source"] = tr.get("source")
     if rank == 0:
         for kind, key in ((0, "hbm_copy_gbs_here"), (1, "fp64_fma_tflops_here")):
             r = C.c_double()
@@ -301,7 +319,8 @@ def main():
     def e2e_step(solver):
         return pmpc_b200.solve_batch(p, arrs["Q"], arrs["R"], arrs["x0"], arrs["X_ref"], arrs["U_ref"], arrs["X_prev"],
                                      arrs["U_prev"], None, None, arrs["u_l"], arrs["u_u"], max_it=MAX_IT, res_tol=RES_TOL,
-                                     reg_x=d0["reg_x"], reg_u=d0["reg_u"], slew_rate=0.0, Nc=NC, device=local, solver=solver)
+                                     reg_x=d0["reg_x"], reg_u=d0["reg_u"], slew_rate=0.0, Nc=NC, device=local, solver=solver,
+                                     reuse_buffers=True)
 
     for _ in range(min(W, 2)):
         Xe, Ue, infoe, ds = e2e_step(ds)
@@ -313,9 +332,9 @@ def main():
     barrier()
     e2e_s = parallel.reduce_max(e2e_s, dist, dev_t)
     h2d = sum(a.nbytes for a in arrs.values()) + p.nbytes + 8 * B * M  # inputs + params + slew vector
-    d2h = Xe[:, :, 1:].nbytes + Ue.nbytes + 8 * 8 * B
+    d2h = Xe.nbytes + Ue.nbytes + 8 * 8 * B
     e2e = {"value": world * B * K / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": 1e3 * e2e_s / K, "api": "pmpc_b200.solve_batch (host numpy arrays in, host arrays out)"}
+           "ms_per_step": 1e3 * e2e_s / K, "api": "pmpc_b200.solve_batch (page-locked host numpy arrays in, page-locked host arrays out)"}
     ok = ok and np.array_equal(Xe[:, :, 1:], X.reshape(Xe[:, :, 1:].shape)) and bool((infoe["status"] == 0).all())
 
     # ---- single-solve latency through pmpc_b200.solve (the call a reference user makes) -----------
@@ -348,6 +367,7 @@ def main():
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "C2 Dubins N=50 M=128 Nc=1 particle consensus", "problems_per_gpu_per_step": B,
+                           "ctas_per_sm": occ[0], "sms": occ[1],
                            "max_it": MAX_IT, "res_tol": RES_TOL, "l2": "working set %.1f GB per GPU > 126 MB L2" % (
                                B * M * N * 135 * 8 / 1e9), "parallelism": "problem batch sharded, no collective"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,

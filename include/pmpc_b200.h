@@ -81,7 +81,7 @@ typedef struct {
   int max_admm_iter;   /* per QP                                        (4000)         */
   int check_every;     /* ADMM iterations between residual checks       (10)           */
   int polish;          /* active-set (masked Riccati) polish on/off     (1)            */
-  int polish_iters;    /* primal-dual active-set refinements / attempt  (8)            */
+  int polish_iters;    /* active-set passes per QP before the interior-point fallback (16) */
   int adapt_rho;       /*                                               (1)            */
   int warm_start;      /* carry (w,y,active set) across SCP iterations  (1)            */
   int fused;           /* fused 2-sweep polish passes with on-the-fly linearisation (1) */
@@ -106,6 +106,14 @@ int pmpc_set_problem(pmpc_handle_t h, const double *x0, const double *Q, const d
                      const double *X_ref, const double *U_ref, const double *lx, const double *ux,
                      const double *lu, const double *uu, double reg_x, double reg_u,
                      const double *slew_reg, const double *slew_reg0, const double *slew_um1);
+/* Matrix block order of the handle API's inputs (Q, R, fx, fu, A, B) and of pmpc_get_linearization:
+ * 0 (default) = column-major blocks, the reference C ABI; 1 = row-major blocks, i.e. NumPy C-order
+ * (M,N,rows,cols) arrays as `pmpc.solve` receives them, so that no host-side transpose is needed. */
+int pmpc_set_layout(pmpc_handle_t h, int row_major_matrices);
+/* Page-locked host buffers (cudaHostAlloc) for inputs / outputs of the handle API: H2D / D2H copies from
+ * them run at full PCIe / C2C speed and asynchronously. */
+int pmpc_host_alloc(void **p, size_t bytes);
+int pmpc_host_free(void *p);
 /* Warm start X_prev (n,N,B*M), U_prev (m,N,B*M); NULL = zeros.  Also resets the ADMM state. */
 int pmpc_set_warm_start(pmpc_handle_t h, const double *X_prev, const double *U_prev);
 
@@ -134,6 +142,8 @@ int pmpc_sync(pmpc_handle_t h);
 
 /* Results.  X (n,N,B*M) without x0, U (m,N,B*M). */
 int pmpc_get_solution(pmpc_handle_t h, double *X, double *U);
+/* Same with X in trajectory form (n,N+1,B*M): stage 0 is x0, what `solve` returns (static_backend.py:311). */
+int pmpc_get_trajectory(pmpc_handle_t h, double *X, double *U);
 /* Per problem b: info[b*8 + k], k = 0 scp_iters, 1 total ADMM iterations, 2 factorisations,
  * 3 polish passes, 4 status (0 ok, 1 NaN failure, 2 ADMM hit max_iter in some QP),
  * 5 QPs finished by polish, 6 QPs finished by ADMM tolerance, 7 sweeps over the horizon. */

@@ -11,6 +11,7 @@ from .static_backend import aff_solve, is_precompiled_backend_available, lqp_sol
 from .dynamics import BuiltinDynamics, DubinsCar, LTV  # noqa: F401
 from .handle import DeviceSolver  # noqa: F401
 from .batch import solve_batch  # noqa: F401
+from ._lib import pinned_copy, pinned_empty  # noqa: F401
 from .problem_struct import Problem  # noqa: F401
 
 """Keyword-compatible arguments in the solver scp solve call (reference pmpc/__init__.py:4-33)."""

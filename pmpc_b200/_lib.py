@@ -58,6 +58,9 @@ _SIG = {
     "pmpc_set_settings": (C.c_int, [C.c_void_p, C.POINTER(Settings)]),
     "pmpc_set_problem": (C.c_int, [C.c_void_p] + [_DP] * 9 + [C.c_double, C.c_double] + [_DP] * 3),
     "pmpc_set_warm_start": (C.c_int, [C.c_void_p, _DP, _DP]),
+    "pmpc_set_layout": (C.c_int, [C.c_void_p, C.c_int]),
+    "pmpc_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "pmpc_host_free": (C.c_int, [C.c_void_p]),
     "pmpc_set_dynamics": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_size_t, C.c_double]),
     "pmpc_set_linearization": (C.c_int, [C.c_void_p, _DP, _DP, _DP]),
     "pmpc_set_ltv": (C.c_int, [C.c_void_p, _DP, _DP, _DP]),
@@ -68,6 +71,7 @@ _SIG = {
     "pmpc_scp_solve_async": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "pmpc_sync": (C.c_int, [C.c_void_p]),
     "pmpc_get_solution": (C.c_int, [C.c_void_p, _DP, _DP]),
+    "pmpc_get_trajectory": (C.c_int, [C.c_void_p, _DP, _DP]),
     "pmpc_get_info": (C.c_int, [C.c_void_p, c_ll_p]),
     "pmpc_get_hist": (C.c_int, [C.c_void_p, _DP, C.c_int]),
     "pmpc_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -139,3 +143,38 @@ def default_settings(**overrides) -> Settings:
 
 def device_count() -> int:
     return int(load().pmpc_device_count())
+
+
+class _Pinned:
+    """Owner of one cudaHostAlloc block; freed when the last array view on it dies."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        check(load().pmpc_host_alloc(C.byref(self.ptr), max(int(nbytes), 8)), "host_alloc")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().pmpc_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """NumPy array in page-locked host memory (``pmpc_host_alloc``): H2D / D2H copies of the handle API
+    from such arrays run at full PCIe speed.  The memory lives as long as the array (or any view of it)."""
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    owner = _Pinned(n)
+    buf = (C.c_char * max(n, 8)).from_address(owner.ptr.value)
+    buf._owner = owner  # keep-alive chain: array -> ctypes buffer -> owner
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.asarray(a, dtype=np.float64)
+    out = pinned_empty(a.shape)
+    out[...] = a
+    return out

@@ -97,13 +97,15 @@ def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: O
 def solve_batch(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_prev=None, x_l=None, x_u=None, u_l=None,
                 u_u=None, max_it: int = 100, res_tol: float = 1e-5, reg_x: float = 1.0, reg_u: float = 1e-2,
                 slew_rate: Optional[float] = 0.0, Nc: int = -1, dyn_eps: float = 1e-6, device: int = -1,
-                solver: Optional[DeviceSolver] = None, settings: Optional[dict] = None):
+                solver: Optional[DeviceSolver] = None, settings: Optional[dict] = None, reuse_buffers: bool = False):
     """Array form of the batched solve: B independent Dubins-car particle problems given as stacked
     HOST arrays with a leading problem axis — ``dyn_params (B,M,3)``, ``Q (B,M,N,n,n)``, ``R (B,M,N,m,m)``,
     ``x0 (B,M,n)``, vectors ``(B,M,N,d)`` — solved by ONE device launch (one CTA per problem).  Argument
     meaning and defaults are those of ``solve`` (reference ``scp_mpc.py:205-238``; warm-start default
     ``X_prev = X_ref``, ``:313-314``).  Returns ``X (B,M,N+1,n)`` including x0, ``U (B,M,N,m)``, ``info``
-    (per-problem counters of ``pmpc_get_info``), and the :class:`DeviceSolver` for reuse via ``solver=``."""
+    (per-problem counters of ``pmpc_get_info``), and the :class:`DeviceSolver` for reuse via ``solver=``.
+    Inputs in page-locked memory (``pmpc_b200.pinned_empty`` / ``pinned_copy``) are copied at full PCIe
+    speed; ``reuse_buffers=True`` returns X, U in page-locked buffers owned by the solver."""
     Q = np.asarray(Q)
     B, M, N, n = Q.shape[:4]
     m = np.asarray(R).shape[-1]
@@ -114,10 +116,9 @@ def solve_batch(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_pre
                    None if slew_rate is None else np.full(B * M, float(slew_rate)))
     ds.set_warm_start(X_ref if X_prev is None else X_prev, U_ref if U_prev is None else U_prev)
     ds.set_dubins(dyn_params, dyn_eps)
-    ds.scp_solve(max_it, res_tol)
-    X, U = ds.solution()
-    X = np.concatenate([np.asarray(x0, np.float64).reshape(B, M, 1, n), X.reshape(B, M, N, n)], -2)
-    return X, U.reshape(B, M, N, m), ds.info(), ds
+    ds.scp_solve_async(max_it, res_tol)
+    X, U = ds.trajectory(reuse_buffers)  # stream-ordered after the solve; synchronises
+    return X, U, ds.info(), ds
 
 
 def solve_batched(problems: List[Dict[str, Any]], verbose: bool = False, device: int = -1, **kw):

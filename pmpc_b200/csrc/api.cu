@@ -71,6 +71,10 @@ struct pmpc_handle_s {
   size_t slab_bytes = 0;
   double* stage = nullptr;    // device staging for raw (reference-layout) inputs / outputs
   size_t stage_doubles = 0;
+  double* raw = nullptr;      // device copy of all raw pmpc_set_problem inputs (grown on demand)
+  size_t raw_doubles = 0;
+  int* flags = nullptr;       // device-side NaN-sentinel analysis of the optional arguments (FL_*)
+  int row_major = 0;          // matrices given as C-order (rows, cols) blocks instead of column-major
   double *lin_f = nullptr, *lin_fx = nullptr, *lin_fu = nullptr;  // reference-layout linearisation
   int* uniform = nullptr;     // per problem: cost / reference / bound data identical for all particles
   bool have_problem = false, have_dyn = false, solved = false;
@@ -88,11 +92,29 @@ __device__ __forceinline__ size_t tix(size_t slot, Lay L, int j, int E, int e) {
   return (((slot >> 5) * (size_t)L.N + (size_t)j) * (size_t)E + (size_t)e) * 32 + (slot & 31);
 }
 
+enum { FL_XBOX_ABSENT = 0, FL_UBOX_ABSENT, FL_SLEW_ABSENT, FL_SLEW0_ABSENT, FL_SLEW_NONZERO, FL_COUNT = 8 };
+
+// flag = 1 when any element is NaN (the reference's "option absent" sentinel, c_interface.jl:56-70)
+__global__ void nan_flag_kernel(const double* __restrict__ a, size_t n, int* flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= (a[i] != a[i]);
+  if (bad) *flag = 1;
+}
+__global__ void nonzero_flag_kernel(const double* __restrict__ a, size_t n, int* flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool nz = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) nz |= (a[i] != 0.0);
+  if (nz) *flag = 1;
+}
+
+// absent: optional device flag; when set the whole array counts as absent -> `fill`
 __global__ void pack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, Lay L, int Ei, int Eo,
-                                double fill) {
+                                double fill, const int* __restrict__ absent) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = L.N;
   if (idx >= (size_t)Ptot * N) return;
+  if (absent != nullptr && *absent) in = nullptr;
   const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
   const size_t sl = slot_of(gf, L);
   for (int e = 0; e < Eo; ++e) {
@@ -102,14 +124,17 @@ __global__ void pack_vec_kernel(const double* __restrict__ in, double* __restric
   }
 }
 
+// lead = 1 writes the trajectory form (N+1 stages per particle, stage 0 = x0: what `solve` returns)
 __global__ void unpack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, Lay L, int Ei,
-                                  int Eo) {
+                                  int Eo, int lead, const double* __restrict__ x0, size_t P) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = L.N;
   if (idx >= (size_t)Ptot * N) return;
   const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
   const size_t sl = slot_of(gf, L);
-  for (int e = 0; e < Eo; ++e) out[((size_t)gf * N + j) * Eo + e] = in[tix(sl, L, j, Ei, e)];
+  for (int e = 0; e < Eo; ++e) out[((size_t)gf * (N + lead) + j + lead) * Eo + e] = in[tix(sl, L, j, Ei, e)];
+  if (lead && j == 0)
+    for (int e = 0; e < Eo; ++e) out[(size_t)gf * (N + 1) * Eo + e] = x0[(size_t)e * P + sl];
 }
 
 __global__ void pack_particle_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, size_t P, Lay L,
@@ -124,7 +149,8 @@ __global__ void pack_particle_kernel(const double* __restrict__ in, double* __re
 __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __restrict__ Q, const double* __restrict__ R,
                                  const double* __restrict__ Xref, const double* __restrict__ Uref,
                                  const double* __restrict__ s, const double* __restrict__ s0,
-                                 const double* __restrict__ um1, int Ptot, int quirk_keep_um1) {
+                                 const double* __restrict__ um1, int Ptot, int quirk_keep_um1, int row_major,
+                                 const int* __restrict__ flags) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
@@ -134,18 +160,22 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
   const size_t P = pb.P;
   const double* Qb = Q + ((size_t)g * N + j) * n * n;  // column-major: Q[r,t] = Qb[t*n + r]
   const double* Rb = R + ((size_t)g * N + j) * m * m;
+  // element (r, t) of an (a x a) block: column-major (reference C ABI) or row-major (NumPy C order)
+  const int qr = row_major ? n : 1, qt = row_major ? 1 : n, rr_ = row_major ? m : 1, rt = row_major ? 1 : m;
+  if (flags[FL_SLEW_ABSENT]) s = nullptr;
+  if (flags[FL_SLEW0_ABSENT]) { s0 = nullptr; um1 = nullptr; }
   const double* xr = Xref ? Xref + ((size_t)g * N + j) * n : nullptr;
   const double* ur = Uref ? Uref + ((size_t)g * N + j) * m : nullptr;
   const int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2;
   for (int r = 0; r < NX; ++r) {
     for (int t = r; t < NX; ++t) {
-      double v = (r < n && t < n) ? Qb[(size_t)t * n + r] : 0.0;
+      double v = (r < n && t < n) ? Qb[(size_t)t * qt + (size_t)r * qr] : 0.0;
       if (r == t) v += (r < n) ? pb.reg_x : 1.0;
       pb.Qs[tix(sl, L, j, NQ, pk(r, t, NX))] = v;
     }
     double acc = 0.0;
     if (r < n && xr)
-      for (int t = 0; t < n; ++t) acc += Qb[(size_t)t * n + r] * xr[t];
+      for (int t = 0; t < n; ++t) acc += Qb[(size_t)t * qt + (size_t)r * qr] * xr[t];
     pb.qref[tix(sl, L, j, NX, r)] = acc;
     pb.xref[tix(sl, L, j, NX, r)] = (r < n && xr) ? xr[r] : 0.0;
   }
@@ -153,13 +183,13 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
   const double extra = (j == 0 ? s0v : 0.0) + ((N == 1 && j == 0) ? sv : 0.0);  // lqp_utils.jl:31-37
   for (int a = 0; a < NU; ++a) {
     for (int b = a; b < NU; ++b) {
-      double v = (a < m && b < m) ? Rb[(size_t)b * m + a] : 0.0;
+      double v = (a < m && b < m) ? Rb[(size_t)b * rt + (size_t)a * rr_] : 0.0;
       if (a == b) v += (a < m) ? (pb.reg_u + extra) : 1.0;
       pb.Rs[tix(sl, L, j, NR, pk(a, b, NU))] = v;
     }
     double acc = 0.0;
     if (a < m && ur)
-      for (int t = 0; t < m; ++t) acc += Rb[(size_t)t * m + a] * ur[t];
+      for (int t = 0; t < m; ++t) acc += Rb[(size_t)t * rt + (size_t)a * rr_] * ur[t];
     if (a < m && j == 0 && quirk_keep_um1 && um1) acc += s0v * um1[(size_t)g * m + a];  // lqp_utils.jl:165
     pb.rref[tix(sl, L, j, NU, a)] = acc;
     pb.uref[tix(sl, L, j, NU, a)] = (a < m && ur) ? ur[a] : 0.0;
@@ -173,7 +203,7 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
 
 // caller-supplied linearisation -> A, B, c   (lqp_utils.jl:231-300: c_j = f_j - fu_j ubar_j - fx_j xbar_{j-1})
 __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __restrict__ f, const double* __restrict__ fx,
-                                const double* __restrict__ fu, int Ptot, int c_is_f) {
+                                const double* __restrict__ fu, int Ptot, int c_is_f, int row_major) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
@@ -184,17 +214,18 @@ __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __rest
   const double* fxb = fx + ((size_t)g * N + j) * n * n;  // fx[r,t] = fxb[t*n + r]
   const double* fub = fu + ((size_t)g * N + j) * n * m;  // fu[r,t] = fub[t*n + r]
   const double* fb = f ? f + ((size_t)g * N + j) * n : nullptr;
+  const int xr_ = row_major ? n : 1, xt = row_major ? 1 : n, ur_ = row_major ? m : 1, ut = row_major ? 1 : n;
   for (int r = 0; r < NX; ++r) {
     double cv = (r < n && fb) ? fb[r] : 0.0;
     for (int t = 0; t < NX; ++t) {
-      const double a0 = (r < n && t < n) ? fxb[(size_t)t * n + r] : 0.0;
+      const double a0 = (r < n && t < n) ? fxb[(size_t)t * xt + (size_t)r * xr_] : 0.0;
       const double a = (j >= 1) ? a0 : 0.0;  // stage 1 is linearised at x0 itself: no fx term (lqp_utils.jl:288-296)
       pb.A[tix(sl, L, j, NX * NX, r * NX + t)] = a;
       if (!c_is_f && j >= 1) cv -= a * pb.Xp[tix(sl, L, j - 1, NX, t)];
       if (c_is_f && j == 0) cv += a0 * pb.x0[(size_t)t * P + sl];  // LTV: f_1 = A_1 x0 + B_1 u + c_1
     }
     for (int t = 0; t < NU; ++t) {
-      const double b = (r < n && t < m) ? fub[(size_t)t * n + r] : 0.0;
+      const double b = (r < n && t < m) ? fub[(size_t)t * ut + (size_t)r * ur_] : 0.0;
       pb.Bm[tix(sl, L, j, NX * NU, r * NU + t)] = b;
       if (!c_is_f) cv -= b * pb.Up[tix(sl, L, j, NU, t)];
     }
@@ -204,7 +235,7 @@ __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __rest
 
 // K1 stand-alone: Dubins f, fx, fu at (X_ = [x0, X_prev[:-1]], U_prev) in reference layout
 __global__ void linearize_dubins_kernel(DevProb pb, double* __restrict__ f, double* __restrict__ fx,
-                                        double* __restrict__ fu, int Ptot) {
+                                        double* __restrict__ fu, int Ptot, int row_major) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = pb.N;
   if (idx >= (size_t)Ptot * N) return;
@@ -218,8 +249,8 @@ __global__ void linearize_dubins_kernel(DevProb pb, double* __restrict__ f, doub
   dubins_f_fx_fu(x, u, pb.dynp[sl], pb.dynp[P + sl], pb.dynp[2 * P + sl], pb.dyn_eps, fo, fxo, fuo);
   for (int r = 0; r < 4; ++r) {
     f[((size_t)g * N + j) * 4 + r] = fo[r];
-    for (int t = 0; t < 4; ++t) fx[((size_t)g * N + j) * 16 + t * 4 + r] = fxo[r * 4 + t];
-    for (int t = 0; t < 2; ++t) fu[((size_t)g * N + j) * 8 + t * 4 + r] = fuo[r * 2 + t];
+    for (int t = 0; t < 4; ++t) fx[((size_t)g * N + j) * 16 + (row_major ? r * 4 + t : t * 4 + r)] = fxo[r * 4 + t];
+    for (int t = 0; t < 2; ++t) fu[((size_t)g * N + j) * 8 + (row_major ? r * 2 + t : t * 4 + r)] = fuo[r * 2 + t];
   }
 }
 
@@ -263,13 +294,6 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
 // ---------------------------------------------------------------------------------------------
 static inline int nblk(size_t n, int t = 256) { return (int)((n + t - 1) / t); }
 
-static bool has_nan(const double* p, size_t n) {
-  if (!p) return true;
-  for (size_t i = 0; i < n; ++i)
-    if (p[i] != p[i]) return true;
-  return false;
-}
-
 extern "C" {
 
 void pmpc_default_settings(pmpc_settings* s) {
@@ -282,7 +306,7 @@ void pmpc_default_settings(pmpc_settings* s) {
   s->max_admm_iter = 4000;
   s->check_every = 10;
   s->polish = 1;
-  s->polish_iters = 8;
+  s->polish_iters = 16;
   s->adapt_rho = 1;
   s->warm_start = 1;
   s->fused = 1;
@@ -395,11 +419,12 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   pb.actc = ac; ac += B * D + 32;
   pb.actcn = ac;
   // staging: the largest raw input is Q or fx: Ptot*N*n*n doubles (+ room for X/U outputs)
-  h->stage_doubles = h->Ptot * N * std::max<size_t>(xdim * xdim, xdim * udim + xdim + 16);
+  h->stage_doubles = h->Ptot * (N + 1) * std::max<size_t>(xdim * xdim, xdim * udim + xdim + udim + 16);
   CU(cudaMalloc(&h->stage, h->stage_doubles * sizeof(double)));
   CU(cudaMalloc(&h->lin_f, h->Ptot * N * xdim * sizeof(double)));
   CU(cudaMalloc(&h->lin_fx, h->Ptot * N * xdim * xdim * sizeof(double)));
   CU(cudaMalloc(&h->lin_fu, h->Ptot * N * xdim * udim * sizeof(double)));
+  CU(cudaMalloc(&h->flags, FL_COUNT * sizeof(int)));
   CU(cudaMalloc(&h->uniform, B * sizeof(int)));
   CU(cudaMemsetAsync(h->uniform, 0, B * sizeof(int), h->stream));
   pb.uniform = h->uniform;
@@ -415,7 +440,7 @@ int pmpc_destroy(pmpc_handle_t h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
-  cudaFree(h->uniform);
+  cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->tev0); cudaEventDestroy(h->tev1);
   cudaStreamDestroy(h->stream);
@@ -442,20 +467,41 @@ static int upload(pmpc_handle_t h, const double* src, size_t cnt, size_t off, do
   return PMPC_OK;
 }
 
-static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, int Eo, double fill) {
+// stream-ordered: no synchronisation here; `off` keeps concurrent uploads apart in the staging buffer
+static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, int Eo, double fill, size_t off = 0) {
   const DevProb& pb = h->pb;
   double* dev = nullptr;
   if (host) {
-    int rc = upload(h, host, h->Ptot * pb.N * Ei, 0, &dev);
+    int rc = upload(h, host, h->Ptot * pb.N * Ei, off, &dev);
     if (rc) return rc;
   }
-  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, Lay{pb.M, pb.Mpad, pb.N}, Ei, Eo, fill);
+  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, Lay{pb.M, pb.Mpad, pb.N}, Ei, Eo, fill,
+                                                              nullptr);
   ++g_launches;
   CU(cudaGetLastError());
-  if (host) CU(cudaStreamSynchronize(h->stream));  // staging buffer is reused by the next upload
   return PMPC_OK;
 }
 
+int pmpc_set_layout(pmpc_handle_t h, int row_major_matrices) {
+  if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
+  h->row_major = row_major_matrices ? 1 : 0;
+  return PMPC_OK;
+}
+
+int pmpc_host_alloc(void** p, size_t bytes) {
+  if (!p) return fail(PMPC_ERR_BAD_ARG, "null");
+  if (pmpc_device_count() < 1) return fail(PMPC_ERR_NO_DEVICE, "no CUDA device");
+  CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+  return PMPC_OK;
+}
+
+int pmpc_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return PMPC_OK;
+}
+
+// All raw inputs go to one device buffer with back-to-back async copies; the NaN-sentinel analysis
+// (c_interface.jl:56-70) and the re-layout run on the device; ONE synchronisation at the end reads the flags.
 int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const double* R, const double* X_ref,
                      const double* U_ref, const double* lx, const double* ux, const double* lu, const double* uu,
                      double reg_x, double reg_u, const double* slew_reg, const double* slew_reg0,
@@ -465,67 +511,72 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   DevProb& pb = h->pb;
   const int n = pb.n, m = pb.m, N = pb.N, NX = h->shape.NX, NU = h->shape.NU;
   const size_t Pt = h->Ptot;
-  // NaN sentinels (c_interface.jl:56-70)
-  const bool xbox = !(has_nan(lx, Pt * N * n) || has_nan(ux, Pt * N * n));
-  const bool ubox = !(has_nan(lu, Pt * N * m) || has_nan(uu, Pt * N * m));
-  const bool slew = !has_nan(slew_reg, Pt);
-  const bool slew0 = !(has_nan(slew_reg0, Pt) || has_nan(slew_um1, Pt * m));
-  pb.has_xbox = xbox; pb.has_ubox = ubox;
   pb.reg_x = reg_x; pb.reg_u = reg_u;
-  bool any_slew = false;
-  if (slew) for (size_t i = 0; i < Pt; ++i) any_slew |= (slew_reg[i] != 0.0);
-  pb.has_slew = any_slew;
-  // stage raw inputs: [Q | R | Xref | Uref | s | s0 | um1]
-  size_t off = 0;
-  double *dQ, *dR, *dXr = nullptr, *dUr = nullptr, *ds = nullptr, *ds0 = nullptr, *dum1 = nullptr;
-  int rc;
-  if ((rc = upload(h, Q, Pt * N * n * n, off, &dQ))) return rc;
-  off += Pt * N * n * n;
-  // R, refs and slew vectors are small next to Q; they go to a second allocation-free region only
-  // if they fit, otherwise they are packed in separate rounds.
-  const size_t rest = Pt * N * (m * m + n + m) + Pt * (2 + m);
-  std::vector<double> dummy;
-  double* extra = nullptr;
-  CU(cudaMallocAsync((void**)&extra, rest * sizeof(double), h->stream));
-  size_t eo = 0;
-  auto up2 = [&](const double* src, size_t cnt, double** dst) -> int {
-    *dst = extra + eo;
-    eo += cnt;
+  const size_t nQ = Pt * N * n * n, nR = Pt * N * m * m, nX = Pt * N * n, nU = Pt * N * m;
+  const size_t total = nQ + nR + 3 * nX + 3 * nU + Pt * (2 + m) + Pt * n + 64;
+  if (total > h->raw_doubles) {
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->raw);
+    h->raw = nullptr;
+    h->raw_doubles = 0;
+    CU(cudaMalloc(&h->raw, total * sizeof(double)));
+    h->raw_doubles = total;
+  }
+  double* cur = h->raw;
+  auto up = [&](const double* src, size_t cnt, double** dst) -> int {
+    *dst = nullptr;
+    if (!src) return 0;
+    *dst = cur;
+    cur += (cnt + 1) / 2 * 2;  // keep 16-byte alignment
     cudaError_t e = cudaMemcpyAsync(*dst, src, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     return e == cudaSuccess ? 0 : fail(PMPC_ERR_CUDA, cudaGetErrorString(e));
   };
-  if ((rc = up2(R, Pt * N * m * m, &dR))) return rc;
-  if (X_ref && (rc = up2(X_ref, Pt * N * n, &dXr))) return rc;
-  if (U_ref && (rc = up2(U_ref, Pt * N * m, &dUr))) return rc;
-  if (slew && (rc = up2(slew_reg, Pt, &ds))) return rc;
-  if (slew0 && (rc = up2(slew_reg0, Pt, &ds0))) return rc;
-  if (slew0 && (rc = up2(slew_um1, Pt * m, &dum1))) return rc;
+  double *dQ, *dR, *dXr, *dUr, *dlx, *dux, *dlu, *duu, *ds, *ds0, *dum1, *dx0;
+  int rc;
+  // absent-by-NULL is decided here, absent-by-NaN on the device
+  int init[FL_COUNT] = {0};
+  init[FL_XBOX_ABSENT] = (!lx || !ux);
+  init[FL_UBOX_ABSENT] = (!lu || !uu);
+  init[FL_SLEW_ABSENT] = !slew_reg;
+  init[FL_SLEW0_ABSENT] = (!slew_reg0 || !slew_um1);
+  CU(cudaMemcpyAsync(h->flags, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = up(lx, nX, &dlx)) || (rc = up(ux, nX, &dux)) || (rc = up(lu, nU, &dlu)) || (rc = up(uu, nU, &duu)) ||
+      (rc = up(slew_reg, Pt, &ds)) || (rc = up(slew_reg0, Pt, &ds0)) || (rc = up(slew_um1, Pt * m, &dum1)) ||
+      (rc = up(x0, Pt * n, &dx0)) || (rc = up(X_ref, nX, &dXr)) || (rc = up(U_ref, nU, &dUr)) || (rc = up(R, nR, &dR)) ||
+      (rc = up(Q, nQ, &dQ)))
+    return rc;
+  auto nanflag = [&](const double* d, size_t cnt, int k) {
+    if (d) { nan_flag_kernel<<<std::min(nblk(cnt), 1184), 256, 0, h->stream>>>(d, cnt, h->flags + k); ++g_launches; }
+  };
+  nanflag(dlx, nX, FL_XBOX_ABSENT); nanflag(dux, nX, FL_XBOX_ABSENT);
+  nanflag(dlu, nU, FL_UBOX_ABSENT); nanflag(duu, nU, FL_UBOX_ABSENT);
+  nanflag(ds, Pt, FL_SLEW_ABSENT);
+  nanflag(ds0, Pt, FL_SLEW0_ABSENT); nanflag(dum1, Pt * m, FL_SLEW0_ABSENT);
+  if (ds) { nonzero_flag_kernel<<<std::min(nblk(Pt), 1184), 256, 0, h->stream>>>(ds, Pt, h->flags + FL_SLEW_NONZERO); ++g_launches; }
   pack_cost_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, dQ, dR, dXr, dUr, ds, ds0, dum1, (int)Pt,
-                                                         h->Nc_orig >= 1 ? 1 : 0);
+                                                         h->Nc_orig >= 1 ? 1 : 0, h->row_major, h->flags);
   ++g_launches;
-  CU(cudaGetLastError());
-  CU(cudaFreeAsync(extra, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(nullptr, pb.x0, (int)Pt, pb.P, Lay{pb.M, pb.Mpad, pb.N}, 0, NX, 0.0);
+  const Lay L{pb.M, pb.Mpad, pb.N};
+  pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(dx0, pb.x0, (int)Pt, pb.P, L, n, NX, 0.0);
   ++g_launches;
-  {
-    double* d;
-    if ((rc = upload(h, x0, Pt * n, 0, &d))) return rc;
-    pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(d, pb.x0, (int)Pt, pb.P, Lay{pb.M, pb.Mpad, pb.N}, n, NX, 0.0);
-    ++g_launches;
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
-  }
   const double inf = INFINITY;
-  if ((rc = pack_vec(h, ubox ? lu : nullptr, pb.lu, m, NU, -inf))) return rc;
-  if ((rc = pack_vec(h, ubox ? uu : nullptr, pb.uu, m, NU, inf))) return rc;
-  if ((rc = pack_vec(h, xbox ? lx : nullptr, pb.lx, n, NX, -inf))) return rc;
-  if ((rc = pack_vec(h, xbox ? ux : nullptr, pb.ux, n, NX, inf))) return rc;
+  const int nb = nblk(Pt * N);
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dlu, pb.lu, (int)Pt, L, m, NU, -inf, h->flags + FL_UBOX_ABSENT);
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(duu, pb.uu, (int)Pt, L, m, NU, inf, h->flags + FL_UBOX_ABSENT);
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dlx, pb.lx, (int)Pt, L, n, NX, -inf, h->flags + FL_XBOX_ABSENT);
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dux, pb.ux, (int)Pt, L, n, NX, inf, h->flags + FL_XBOX_ABSENT);
+  g_launches += 4;
   fill_int_kernel<<<nblk(pb.B), 256, 0, h->stream>>>(h->uniform, pb.B, 1);
   ++g_launches;
   uniform_check_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, h->uniform, (int)Pt);
   ++g_launches;
   CU(cudaGetLastError());
+  int fl[FL_COUNT];
+  CU(cudaMemcpyAsync(fl, h->flags, sizeof(fl), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  pb.has_xbox = !fl[FL_XBOX_ABSENT];
+  pb.has_ubox = !fl[FL_UBOX_ABSENT];
+  pb.has_slew = (!fl[FL_SLEW_ABSENT] && fl[FL_SLEW_NONZERO]) ? 1 : 0;
   h->have_problem = true;
   return pmpc_set_warm_start(h, nullptr, nullptr);
 }
@@ -535,8 +586,8 @@ int pmpc_set_warm_start(pmpc_handle_t h, const double* X_prev, const double* U_p
   CU(cudaSetDevice(h->device));
   DevProb& pb = h->pb;
   int rc;
-  if ((rc = pack_vec(h, X_prev, pb.Xp, pb.n, h->shape.NX, 0.0))) return rc;
-  if ((rc = pack_vec(h, U_prev, pb.Up, pb.m, h->shape.NU, 0.0))) return rc;
+  if ((rc = pack_vec(h, X_prev, pb.Xp, pb.n, h->shape.NX, 0.0, 0))) return rc;
+  if ((rc = pack_vec(h, U_prev, pb.Up, pb.m, h->shape.NU, 0.0, h->Ptot * pb.N * pb.n))) return rc;
   // reset ADMM / active-set state
   const size_t P = pb.P, N = pb.N, NX = h->shape.NX, NU = h->shape.NU;
   CU(cudaMemsetAsync(pb.wu, 0, N * NU * P * sizeof(double), h->stream));
@@ -550,6 +601,7 @@ int pmpc_set_warm_start(pmpc_handle_t h, const double* X_prev, const double* U_p
   fill_kernel<<<nblk(pb.B), 256, 0, h->stream>>>(pb.rho, pb.B, pb.rho0);
   ++g_launches;
   CU(cudaGetLastError());
+  if (X_prev || U_prev) CU(cudaStreamSynchronize(h->stream));  // the caller's buffers are not retained
   return PMPC_OK;
 }
 
@@ -591,7 +643,8 @@ static int set_affine(pmpc_handle_t h, const double* f, const double* fx, const 
     CU(cudaMemcpyAsync(h->lin_f, f, Pt * N * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     df = h->lin_f;
   }
-  pack_lin_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, h->shape.NX, h->shape.NU, df, dfx, dfu, (int)Pt, c_is_f);
+  pack_lin_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, h->shape.NX, h->shape.NU, df, dfx, dfu, (int)Pt, c_is_f,
+                                                        h->row_major);
   ++g_launches;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
@@ -614,7 +667,7 @@ int pmpc_linearize(pmpc_handle_t h) {
   if (h->pb.dyn_kind != DYN_DUBINS) return fail(PMPC_ERR_STATE, "pmpc_linearize needs built-in dynamics");
   CU(cudaSetDevice(h->device));
   linearize_dubins_kernel<<<nblk(h->Ptot * h->pb.N), 256, 0, h->stream>>>(h->pb, h->lin_f, h->lin_fx, h->lin_fu,
-                                                                           (int)h->Ptot);
+                                                                           (int)h->Ptot, h->row_major);
   ++g_launches;
   CU(cudaGetLastError());
   return PMPC_OK;
@@ -701,23 +754,33 @@ int pmpc_qp_solve(pmpc_handle_t h, int keep_prev) {
   return pmpc_sync(h);
 }
 
-int pmpc_get_solution(pmpc_handle_t h, double* X, double* U) {
+static int get_solution_impl(pmpc_handle_t h, double* X, double* U, int lead) {
   if (!h || !h->solved) return fail(PMPC_ERR_STATE, "no solution yet");
   CU(cudaSetDevice(h->device));
   const DevProb& pb = h->pb;
   const size_t Pt = h->Ptot, N = pb.N;
+  const size_t nXo = Pt * (N + lead) * pb.n, nUo = Pt * N * pb.m;
+  if (nXo + nUo > h->stage_doubles) return fail(PMPC_ERR_STATE, "staging too small");
   double* dX = h->stage;
-  double* dU = h->stage + Pt * N * pb.n;
-  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, Lay{pb.M, pb.Mpad, pb.N}, h->shape.NX, pb.n);
-  ++g_launches;
-  unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.U, dU, (int)Pt, Lay{pb.M, pb.Mpad, pb.N}, h->shape.NU, pb.m);
-  ++g_launches;
+  double* dU = h->stage + nXo;
+  const Lay L{pb.M, pb.Mpad, pb.N};
+  if (X) {
+    unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, L, h->shape.NX, pb.n, lead, pb.x0, pb.P);
+    ++g_launches;
+    CU(cudaMemcpyAsync(X, dX, nXo * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (U) {
+    unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.U, dU, (int)Pt, L, h->shape.NU, pb.m, 0, nullptr, pb.P);
+    ++g_launches;
+    CU(cudaMemcpyAsync(U, dU, nUo * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(cudaGetLastError());
-  if (X) CU(cudaMemcpyAsync(X, dX, Pt * N * pb.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (U) CU(cudaMemcpyAsync(U, dU, Pt * N * pb.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return PMPC_OK;
 }
+
+int pmpc_get_solution(pmpc_handle_t h, double* X, double* U) { return get_solution_impl(h, X, U, 0); }
+int pmpc_get_trajectory(pmpc_handle_t h, double* X, double* U) { return get_solution_impl(h, X, U, 1); }
 
 int pmpc_get_info(pmpc_handle_t h, long long* info) {
   if (!h || !info) return fail(PMPC_ERR_BAD_ARG, "null");
@@ -747,6 +810,7 @@ int pmpc_get_hist(pmpc_handle_t h, double* hist, int max_it) {
 
 int pmpc_last_kernel_ms(pmpc_handle_t h, float* ms) {
   if (!h || !ms) return fail(PMPC_ERR_BAD_ARG, "null");
+  if (h->solved && cudaEventQuery(h->ev1) == cudaSuccess) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   *ms = h->last_ms;
   return PMPC_OK;
 }

@@ -9,37 +9,37 @@
 //     xp2 = y + v T (s P1 + c P2) + b T^2 (s P4 - c P3)
 //     P1 = A, P2 = D B, P3 = D (C - B), P4 = A - B,
 //     A = sin D/D, B = (1-cos D)/D^2, C = (D-sin D)/D^3, Dd = (D^2/2-1+cos D)/D^4, E = (D^3/6-D+sin D)/D^5
-// (entire functions, power series for |D| <= 2).  oracle/dubins.py evaluates the identical form.
+// (entire functions, power series for |D| <= 2).  oracle/dubins.py evaluates the same form (all five
+// series summed directly); the two agree to ~1e-16.
 #pragma once
 #include <math.h>
 
 namespace pmpc {
 
-// sum_k (-1)^k D2^k / (2k+j)!  for j = 1..5, 12 terms (|D| <= 2  ->  truncation < 1e-17)
+// A..E for j = 1..5:  sum_k (-1)^k x^k / (2k+j)!,  x = D^2.  Only the two highest-order series (Dd, E) are
+// summed (Horner, 11 terms: |D| <= 2 -> truncation < 1e-19); the others follow from the exact relations
+//     B = 1/2 - x Dd,   C = 1/6 - x E,   A = 1 - x C
+// evaluated upwards, which is free of cancellation (x Dd <= 0.17 next to 1/2 for |D| <= 2).
 __device__ __forceinline__ void dubins_entire(double D, double* A, double* B, double* C, double* Dd, double* E) {
   if (fabs(D) <= 2.0) {
     const double x = D * D;
-    // reciprocal factorials 1/n!
-    const double rf[29] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
-                           1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
-                           1.0 / 87178291200.0, 1.0 / 1307674368000.0, 1.0 / 20922789888000.0,
-                           1.0 / 355687428096000.0, 1.0 / 6402373705728000.0, 1.0 / 121645100408832000.0,
-                           1.0 / 2432902008176640000.0, 1.0 / 51090942171709440000.0,
-                           1.0 / 1124000727777607680000.0, 1.0 / 25852016738884976640000.0,
-                           1.0 / 620448401733239439360000.0, 1.0 / 15511210043330985984000000.0,
-                           1.0 / 403291461126605635584000000.0, 1.0 / 10888869450418352160768000000.0,
-                           1.0 / 304888344611713860501504000000.0};
-    double a = 0, b = 0, c = 0, d = 0, e = 0;
+    // reciprocal factorials 1/(2k+4)! and 1/(2k+5)!, k = 0..10, alternating sign folded in
+    const double rd[11] = {1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600, -1.0 / 87178291200.0,
+                           1.0 / 20922789888000.0, -1.0 / 6402373705728000.0, 1.0 / 2432902008176640000.0,
+                           -1.0 / 1124000727777607680000.0, 1.0 / 620448401733239439360000.0};
+    const double re[11] = {1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800.0,
+                           -1.0 / 1307674368000.0, 1.0 / 355687428096000.0, -1.0 / 121645100408832000.0,
+                           1.0 / 51090942171709440000.0, -1.0 / 25852016738884976640000.0,
+                           1.0 / 15511210043330985984000000.0};
+    double d = rd[10], e = re[10];
 #pragma unroll
-    for (int k = 11; k >= 0; --k) {
-      const double sg = (k & 1) ? -1.0 : 1.0;
-      a = a * x + sg * rf[2 * k + 1];
-      b = b * x + sg * rf[2 * k + 2];
-      c = c * x + sg * rf[2 * k + 3];
-      d = d * x + sg * rf[2 * k + 4];
-      e = e * x + sg * rf[2 * k + 5];
+    for (int k = 9; k >= 0; --k) {
+      d = fma(d, x, rd[k]);
+      e = fma(e, x, re[k]);
     }
-    *A = a; *B = b; *C = c; *Dd = d; *E = e;
+    const double b = fma(-x, d, 0.5);
+    const double c = fma(-x, e, 1.0 / 6.0);
+    *A = fma(-x, c, 1.0); *B = b; *C = c; *Dd = d; *E = e;
   } else {
     double sD, cD;
     sincos(D, &sD, &cD);

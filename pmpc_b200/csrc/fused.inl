@@ -142,6 +142,58 @@
     }
   }
 
+  // ---- interior-point fallback (ALG = 1) -------------------------------------------------------
+  // The primal-dual active-set iteration can cycle on a strictly convex box QP.  When it does, the same
+  // two sweeps run a primal-dual interior-point method instead: with slacks sh = hi - u, sl = u - lo and
+  // multipliers lh, ll the Newton step for target mu is the LQ problem with
+  //     R~ = Rs + diag(lh/sh + ll/sl),   r~ = r - diag(.) u + mu/sh - mu/sl
+  // (bsweep), its solution u+ comes out of the rollout (fsweep) together with the fraction-to-boundary
+  // ratios and the sums that predict the complementarity after the step; the damped update
+  //     u += ap (u+ - u),  lam += ad dlam
+  // is applied lazily at the start of the next bsweep.  State: u -> pb.wu, lh -> pb.yu, ll -> pb.wx
+  // (the ADMM arrays, indexed with E = NU), shared-block entries in particle 0's slots.
+  struct Ipm {
+    double mu, mu_prev;  // barrier parameter of the system being built / of the previous one
+    double ap, ad;       // step lengths of the previous step (applied lazily)
+    int init;            // first iteration: initialise (u, lh, ll) strictly inside the box
+  };
+  // updated (u, lh, ll) of one bounded scalar: lazy step of the previous iteration, or the initial point
+  __device__ __forceinline__ void ipm_point(const Ipm& ip, double u0, double unew, double lo, double hi, double uprev,
+                                            double& u, double& lh, double& ll) const {
+    if (ip.init) {
+      const double w = hi - lo;  // inf when one-sided or free
+      const double dl = (w < INFINITY) ? 0.01 * w : 0.01 * fmax(1.0, fabs(lo));
+      const double dh = (w < INFINITY) ? 0.01 * w : 0.01 * fmax(1.0, fabs(hi));
+      u = fmin(fmax(uprev, lo + dl), hi - dh);
+      lh = ip.mu_prev / (hi - u);
+      ll = ip.mu_prev / (u - lo);
+    } else {
+      const double sh = hi - u0, sl = u0 - lo, du = unew - u0;
+      const double dlh = ip.mu_prev / sh - lh + (lh / sh) * du;
+      const double dll = ip.mu_prev / sl - ll - (ll / sl) * du;
+      u = u0 + ip.ap * du;
+      lh += ip.ad * dlh;
+      ll += ip.ad * dll;
+    }
+  }
+  // fraction-to-boundary ratios and complementarity-prediction sums of one bounded scalar
+  __device__ __forceinline__ void ipm_ratios(const Ipm& ip, double u0, double unew, double lo, double hi, double lh,
+                                             double ll, double* acc) const {
+    const double sh = hi - u0, sl = u0 - lo, du = unew - u0;
+    const double dlh = ip.mu / sh - lh + (lh / sh) * du;
+    const double dll = ip.mu / sl - ll - (ll / sl) * du;
+    if (du > 0.0 && hi < INFINITY) acc[0] = fmin(acc[0], sh / du);
+    if (du < 0.0 && lo > -INFINITY) acc[0] = fmin(acc[0], sl / -du);
+    if (dlh < 0.0) acc[1] = fmin(acc[1], lh / -dlh);
+    if (dll < 0.0) acc[1] = fmin(acc[1], ll / -dll);
+    if (hi < INFINITY) {
+      acc[2] += lh * sh; acc[3] += dlh * sh; acc[4] += -lh * du; acc[5] += -dlh * du; acc[6] += 1.0;
+    }
+    if (lo > -INFINITY) {
+      acc[2] += ll * sl; acc[3] += dll * sl; acc[4] += ll * du; acc[5] += dll * du; acc[6] += 1.0;
+    }
+  }
+
   // lane 0: stream the backward-sweep inputs of stage jj into ring slot `sl`
   template <bool UBOX>
   __device__ __forceinline__ void issue_b(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl) {
@@ -178,8 +230,9 @@
   // Backward sweep over the stages j = N-1 .. (first ? 0 : Nc).  Free stages (j >= Nc): masked
   // Riccati matrix + vector step; shared stages (j < Nc, only when the linearisation point changed
   // since the last sweep): store the stage data the consensus Schur step (K3) reads.
-  template <bool SLEW, bool UBOX, bool DUB>
-  __device__ __forceinline__ void bsweep(const DevProb& pb, unsigned char* smem, bool first, double* pc, double* zc) {
+  template <bool SLEW, bool UBOX, bool DUB, int ALG = 0>
+  __device__ __forceinline__ void bsweep(const DevProb& pb, unsigned char* smem, bool first, double* pc, double* zc,
+                                         const Ipm ip = Ipm()) {
     const FactorSet& F = pb.fs[MODE_POLISH];
     const Sm sm = smem_view(pb, smem);
     const bool use_ring = RING_SHAPE && sm.ring != nullptr;
@@ -240,7 +293,7 @@
         if (UBOX) {
           const signed char* ab = reinterpret_cast<const signed char*>(sm.ring + sl * SLOT + R_ACTB) + col;
 #pragma unroll UNR
-          for (int t = 0; t < NU; ++t) act[t] = (j >= Nc) ? ab[t * 32] : 0;
+          for (int t = 0; t < NU; ++t) act[t] = (j >= Nc && ALG == 0) ? ab[t * 32] : 0;
         }
         __syncwarp();
         if (lane == 0 && j - DEPTH >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, j - DEPTH, sl);
@@ -252,7 +305,7 @@
         for (int e = 0; e < NU; ++e) ub[e] = ld(Upv, j, NU, e);
         if (UBOX) {
 #pragma unroll UNR
-          for (int t = 0; t < NU; ++t) act[t] = (j >= Nc) ? pb.act[ix(j, NU, t)] : 0;
+          for (int t = 0; t < NU; ++t) act[t] = (j >= Nc && ALG == 0) ? pb.act[ix(j, NU, t)] : 0;
         }
       }
       double A[NX * NX], Bm[NX * NU], cv[NX];
@@ -265,6 +318,31 @@
       for (int e = 0; e < NX; ++e) q[e] = -q[e] - pb.reg_x * xq[e];
 #pragma unroll UNR
       for (int e = 0; e < NU; ++e) r[e] = -r[e] - pb.reg_u * ub[e];
+      double sig[NU];
+#pragma unroll UNR
+      for (int a = 0; a < NU; ++a) sig[a] = 0.0;
+      if (ALG == 1 && j >= Nc) {
+        // interior point: (lazily) updated iterate, barrier diagonal and linear term of this stage
+        double lo[NU], hi[NU];
+        cost_field(sm.tab, j, T_LU, NU, pb.lu, lo);
+        cost_field(sm.tab, j, T_UU, NU, pb.uu, hi);
+        const double* Unew = flip ? pb.Up : pb.U;  // u+ of the previous interior-point iteration (fsweep's Uc)
+#pragma unroll UNR
+        for (int a = 0; a < NU; ++a) {
+          const size_t o = ix(j, NU, a);
+          double u = 0.0, lh = 0.0, ll = 0.0, u0 = 0.0, un = 0.0;
+          if (!ip.init) {
+            u0 = pb.wu[o]; lh = pb.yu[o]; ll = pb.wx[o]; un = Unew[o];
+          }
+          ipm_point(ip, u0, un, lo[a], hi[a], ub[a], u, lh, ll);
+          if (valid) {
+            pb.wu[o] = u; pb.yu[o] = lh; pb.wx[o] = ll;
+          }
+          const double sh = hi[a] - u, sl = u - lo[a];
+          sig[a] = lh / sh + ll / sl;
+          r[a] += -sig[a] * u + ip.mu / sh - ip.mu / sl;
+        }
+      }
       if (j >= Nc) {
         // ---- Riccati step with the stage's active set.  S = Qs + P (symmetric, packed)
         double S[NQ];
@@ -301,6 +379,7 @@
 #pragma unroll UNR
             for (int b = a; b < NU; ++b) {
               double acc = Rp[pk(a, b, NU)];
+              if (ALG == 1 && a == b) acc += sig[a];
               if (SLEW) {
                 acc += Z[a * NU + b];
                 if (a == b && j >= 1) acc += s;
@@ -499,8 +578,9 @@
 
   // Forward sweep: rollout of the feedback policy, multipliers + primal-dual active-set update of the
   // free-stage controls, SCP bookkeeping against (Xpv, Upv).  Fills the per-thread statistics.
-  template <bool SLEW, bool UBOX, bool DUB>
-  __device__ __forceinline__ void fsweep(const DevProb& pb, unsigned char* smem, double* st) {
+  template <bool SLEW, bool UBOX, bool DUB, int ALG = 0>
+  __device__ __forceinline__ void fsweep(const DevProb& pb, unsigned char* smem, double* st, const Ipm ip = Ipm(),
+                                         double* ipacc = nullptr) {
     const FactorSet& F = pb.fs[MODE_POLISH];
     const Sm sm = smem_view(pb, smem);
     const bool use_ring = RING_SHAPE && sm.ring != nullptr;
@@ -551,7 +631,7 @@
             for (int e = 0; e < NR; ++e) Hj[e] = b[R_H + e * 32];
             const signed char* ab = reinterpret_cast<const signed char*>(sm.ring + sl * SLOT + R_ACTF) + col;
 #pragma unroll UNR
-            for (int t = 0; t < NU; ++t) act[t] = ab[t * 32];
+            for (int t = 0; t < NU; ++t) act[t] = (ALG == 0) ? ab[t * 32] : 0;
           }
         }
         __syncwarp();
@@ -571,7 +651,7 @@
 #pragma unroll UNR
             for (int e = 0; e < NR; ++e) Hj[e] = ld(pb.Hs, j, NR, e);
 #pragma unroll UNR
-            for (int t = 0; t < NU; ++t) act[t] = pb.act[ix(j, NU, t)];
+            for (int t = 0; t < NU; ++t) act[t] = (ALG == 0) ? pb.act[ix(j, NU, t)] : 0;
           }
         }
       }
@@ -605,7 +685,14 @@
           u[a] = acc;
           if (UBOX && act[a] != 0) u[a] = (act[a] > 0) ? hi[a] : lo[a];
         }
-        if (UBOX) {
+        if (ALG == 1) {
+#pragma unroll UNR
+          for (int a = 0; a < NU; ++a) {
+            const size_t o = ix(j, NU, a);
+            ipm_ratios(ip, pb.wu[o], u[a], lo[a], hi[a], pb.yu[o], pb.wx[o], ipacc);
+          }
+        }
+        if (UBOX && ALG == 0) {
 #pragma unroll UNR
           for (int a = 0; a < NU; ++a) {
             const double ua = u[a];
@@ -763,14 +850,141 @@
     return ch;
   }
 
+  // ---- interior-point fallback: shared block and driver ----------------------------------------
+  // before the shared solve: lazy step / initial point of the shared controls, barrier terms into Hc, gc
+  __device__ __forceinline__ void ipm_shared_pre(const DevProb& pb, const Ipm& ip) {
+    if (!GROUPED || Nc < 1) return;
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    double* Hc = F.Hc + (size_t)prob * D * D;
+    double* gc = pb.gc + (size_t)prob * D;
+    const double* ucn = pb.uc + (size_t)prob * D;  // u+ of the previous iteration
+    const double* Up0 = flip ? pb.U : pb.Up;
+    const size_t g0 = (size_t)prob * pb.Mpad;
+    for (int k = tid; k < D; k += T) {
+      const size_t o = ixg(k / NU, NU, k % NU, g0);
+      const double lo = pb.lu[o], hi = pb.uu[o];
+      double u = 0.0, lh = 0.0, ll = 0.0, u0 = 0.0;
+      if (!ip.init) {
+        u0 = pb.wu[o]; lh = pb.yu[o]; ll = pb.wx[o];
+      }
+      ipm_point(ip, u0, ucn[k], lo, hi, Up0[o], u, lh, ll);
+      pb.wu[o] = u; pb.yu[o] = lh; pb.wx[o] = ll;
+      const double sh = hi - u, sl = u - lo, sg = lh / sh + ll / sl;
+      Hc[(size_t)k * D + k] += sg;
+      gc[k] += -sg * u + ip.mu / sh - ip.mu / sl;
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void ipm_shared_post(const DevProb& pb, const Ipm& ip, double* acc) {
+    if (!GROUPED || Nc < 1) return;
+    const double* ucn = pb.uc + (size_t)prob * D;
+    const size_t g0 = (size_t)prob * pb.Mpad;
+    for (int k = tid; k < D; k += T) {
+      const size_t o = ixg(k / NU, NU, k % NU, g0);
+      ipm_ratios(ip, pb.wu[o], ucn[k], pb.lu[o], pb.uu[o], pb.yu[o], pb.wx[o], acc);
+    }
+  }
+  // last step applied, active set read off the complementarity pairs (bound active iff slack < multiplier)
+  __device__ __noinline__ void ipm_finish(const DevProb& pb, const Ipm ip) {
+    const double* Unew = flip ? pb.Up : pb.U;
+    for (int j = Nc; j < N; ++j) {
+#pragma unroll UNR
+      for (int a = 0; a < NU; ++a) {
+        const size_t o = ix(j, NU, a);
+        const double lo = pb.lu[o], hi = pb.uu[o];
+        double u = 0.0, lh = pb.yu[o], ll = pb.wx[o];
+        ipm_point(ip, pb.wu[o], Unew[o], lo, hi, 0.0, u, lh, ll);
+        const signed char na = (hi - u < lh) ? 1 : ((u - lo < ll) ? -1 : 0);
+        if (valid) pb.act[o] = na;
+      }
+    }
+    if (GROUPED && Nc >= 1) {
+      const double* ucn = pb.uc + (size_t)prob * D;
+      const size_t g0 = (size_t)prob * pb.Mpad;
+      __syncthreads();
+      for (int k = tid; k < D; k += T) {
+        const size_t o = ixg(k / NU, NU, k % NU, g0);
+        const double lo = pb.lu[o], hi = pb.uu[o];
+        double u = 0.0, lh = pb.yu[o], ll = pb.wx[o];
+        ipm_point(ip, pb.wu[o], ucn[k], lo, hi, 0.0, u, lh, ll);
+        pb.actc[(size_t)prob * D + k] = (hi - u < lh) ? 1 : ((u - lo < ll) ? -1 : 0);
+      }
+      __syncthreads();
+    }
+  }
+
+  // Interior-point solve of the current QP down to complementarity tol_c; leaves its active-set estimate in
+  // act / actc for the polish pass that follows.  Returns 0, 1 (NaN) or -1 (no convergence).
+  template <bool SLEW, bool UBOX, bool DUB>
+  __device__ __noinline__ int ipm_solve(const DevProb& pb, unsigned char* smem, double* st, long long* cnt, double scale) {
+    double pc[NX], zc[NU];
+    Ipm ip;
+    ip.mu_prev = scale;
+    ip.mu = 0.2 * scale;
+    ip.ap = ip.ad = 0.0;
+    ip.init = 1;
+    const double tol_c = 1e-9 * scale;
+    int rc = -1;
+    for (int it = 0; it < 80; ++it) {
+      bsweep<SLEW, UBOX, DUB, 1>(pb, smem, false, pc, zc, ip);
+      if (GROUPED && Nc >= 1) {
+        assemble_shared(MODE_POLISH, 0.0, 0.0);
+        grad_shared(MODE_POLISH, 0.0, 0.0, pc, zc);
+        ipm_shared_pre(pb, ip);
+        factor_shared(MODE_POLISH, false);
+        apply_shared(MODE_POLISH, 0.0, false);
+      }
+      double acc[7] = {INFINITY, INFINITY, 0.0, 0.0, 0.0, 0.0, 0.0};
+      fsweep<SLEW, UBOX, DUB, 1>(pb, smem, st, ip, acc);
+      const double nanf = st[ST_NAN];
+      if (!valid) {
+        acc[0] = acc[1] = INFINITY;
+        acc[2] = acc[3] = acc[4] = acc[5] = acc[6] = 0.0;
+      }
+      ipm_shared_post(pb, ip, acc);
+      cnt[1] += 1; cnt[2] += 1; cnt[3] += 1; cnt[7] += 2;
+      if (GROUPED) {
+        double* sc = scr();
+        sc[(size_t)0 * T + tid] = -acc[0];
+        sc[(size_t)1 * T + tid] = -acc[1];
+        for (int k = 2; k < 7; ++k) sc[(size_t)k * T + tid] = acc[k];
+        sc[(size_t)7 * T + tid] = nanf;
+        reduce(8, red, 1000, 0x7cu);
+        acc[0] = -red[0]; acc[1] = -red[1];
+        for (int k = 2; k < 7; ++k) acc[k] = red[k];
+        const double nf = red[7];
+        __syncthreads();
+        if (nf > 0.0) return 1;
+      } else if (nanf > 0.0) {
+        return 1;
+      }
+      const double ap = fmin(1.0, 0.995 * acc[0]), ad = fmin(1.0, 0.995 * acc[1]);
+      const double comp = (acc[2] + ad * acc[3] + ap * acc[4] + ap * ad * acc[5]) / fmax(acc[6], 1.0);
+      if (!(comp == comp)) return 1;
+      ip.mu_prev = ip.mu;
+      ip.ap = ap;
+      ip.ad = ad;
+      ip.init = 0;
+      if (comp <= tol_c && ap >= 0.9) {
+        rc = 0;
+        break;
+      }
+      ip.mu = fmax(0.2 * comp, 1e-3 * tol_c);
+    }
+    ipm_finish(pb, ip);
+    return rc;
+  }
+
   template <bool SLEW, bool UBOX, bool DUB>
   __device__ __forceinline__ int fused_qp_impl(const DevProb& pb, unsigned char* smem, double* st, long long* cnt) {
     double pc[NX], zc[NU];
     const bool constrained = pb.has_ubox || pb.has_xbox;
     for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
     st[ST_GSCALE] = st[ST_ZSCALE] = 1.0;
+    bool ipm_used = false, first = true;
     for (int tries = 0;; ++tries) {
-      bsweep<SLEW, UBOX, DUB>(pb, smem, tries == 0, pc, zc);
+      bsweep<SLEW, UBOX, DUB>(pb, smem, first, pc, zc);
+      first = false;
       cnt[2] += 1;
       cnt[7] += 1;
       double kk_c = 0.0, uv_c = 0.0, ch_c = 0.0;
@@ -805,7 +1019,15 @@
         cnt[5] += 1;
         return 0;
       }
-      if (st[ST_XVIOL] > tol_z || st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) return -1;
+      if (st[ST_XVIOL] > tol_z) return -1;  // a state bound wants to be active: ADMM's job (unfused path)
+      if (st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) {
+        // the active-set iteration stalls or cycles: one interior-point solve, then polish from its estimate
+        if (ipm_used || !pb.has_ubox) return -1;
+        ipm_used = true;
+        const int rc = ipm_solve<SLEW, UBOX, DUB>(pb, smem, st, cnt, fmax(st[ST_GSCALE], 1.0));
+        if (rc == 1) return 1;
+        tries = 0;  // (the loop increment makes the next pass a "not first" one: same linearisation point)
+      }
     }
   }
 

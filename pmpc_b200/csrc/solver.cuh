@@ -195,14 +195,16 @@ struct Solver {
 
   // ---- reductions over the particles of the problem (deterministic order) -------------------
   // every thread wrote scr()[k*T + tid], k < cnt.  out[k] = sum (or max) over threads.
-  __device__ __noinline__ void reduce(int cnt, double* out, int max_mask_from = -1) {
+  // max_mask_from < 0: every row is summed; otherwise rows are max-reduced except row `max_mask_from` and the
+  // rows whose bit is set in sum_mask (summed).
+  __device__ __noinline__ void reduce(int cnt, double* out, int max_mask_from = -1, unsigned sum_mask = 0u) {
     if (!GROUPED) return;
     __syncthreads();
     const int lane = tid & 31, w = tid >> 5, nw = T >> 5;
     const double* sc = scr();
     for (int k = w; k < cnt; k += nw) {
       double acc = 0.0;
-      const bool is_sum = (max_mask_from < 0) || (k == max_mask_from);
+      const bool is_sum = (max_mask_from < 0) || (k == max_mask_from) || (k < 32 && ((sum_mask >> k) & 1u));
       if (is_sum) {
         for (int t = lane; t < T; t += 32) acc += sc[(size_t)k * T + t];
         acc = warp_sum(acc);
@@ -683,7 +685,8 @@ struct Solver {
   }
 
   // masked inverse of Hc for the current shared active set (polish) and hb = Hc * beta
-  __device__ __noinline__ void factor_shared(int mode) {
+  // use_mask = false: plain inverse of Hc (interior-point fallback: no component is fixed)
+  __device__ __noinline__ void factor_shared(int mode, bool use_mask = true) {
     if (!GROUPED || Nc < 1) return;
     const FactorSet& F = pb.fs[mode];
     double* Hc = F.Hc + (size_t)prob * D * D;
@@ -691,7 +694,7 @@ struct Solver {
     double* hb = F.hb + (size_t)prob * D;
     const signed char* actc = pb.actc + (size_t)prob * D;
     // hb = Hc * beta (beta = bound value on fixed comps) ; then masked matrix into Hi
-    const bool masked = (mode == MODE_POLISH && pb.has_ubox);
+    const bool masked = (mode == MODE_POLISH && pb.has_ubox && use_mask);
     for (int a = tid; a < D; a += T) {
       double acc = 0.0;
       if (masked) {
@@ -764,7 +767,7 @@ struct Solver {
     reduce(D, pb.gc + (size_t)prob * D);
   }
 
-  __device__ __noinline__ void apply_shared(int mode, double rho_u) {
+  __device__ __noinline__ void apply_shared(int mode, double rho_u, bool use_mask = true) {
     if (!GROUPED || Nc < 1) return;
     const FactorSet& F = pb.fs[mode];
     const double* gc = pb.gc + (size_t)prob * D;
@@ -776,7 +779,7 @@ struct Solver {
     for (int a = tid; a < D; a += T) {
       double acc = 0.0;
       const int ja = a / NU, ta = a % NU;
-      if (mode == MODE_POLISH && pb.has_ubox && actc[a] != 0)
+      if (mode == MODE_POLISH && pb.has_ubox && use_mask && actc[a] != 0)
         acc = (actc[a] > 0) ? pb.uu[ixg(ja, NU, ta, g0)] : pb.lu[ixg(ja, NU, ta, g0)];
       for (int b = 0; b < D; ++b) {
         double gb = gc[b] + hb[b];

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import check, dptr, f64c, mat_cm
+from ._lib import check, dptr, f64c, pinned_empty
 
 INFO_FIELDS = ("scp_iters", "admm_iters", "factorizations", "polish_passes", "status", "qp_by_polish", "qp_by_admm",
                "sweeps")
@@ -27,6 +27,10 @@ class DeviceSolver:
         self.Nc = int(Nc)
         self._h = C.c_void_p()
         check(self.lib.pmpc_create(C.byref(self._h), device, self.B, self.M, self.N, self.n, self.m, self.Nc), "create")
+        # NumPy C-order (..., rows, cols) matrix blocks are consumed as they are: the re-layout of
+        # static_backend.py:71-74 (py2jl + asfortranarray) happens in the device packing kernels
+        check(self.lib.pmpc_set_layout(self._h, 1), "set_layout")
+        self._out = None  # page-locked result buffers, allocated on first use
         if settings:
             self.set_settings(**settings)
 
@@ -61,7 +65,7 @@ class DeviceSolver:
             return None
         a = np.asarray(a, dtype=np.float64)
         assert a.size == self.B * self.M * self.N * r * c, (a.shape, (self.B, self.M, self.N, r, c))
-        return mat_cm(a.reshape(self.B * self.M, self.N, r, c))
+        return f64c(a).reshape(self.B * self.M, self.N, r, c)
 
     def _per_particle(self, a, d=None):
         if a is None:
@@ -118,10 +122,10 @@ class DeviceSolver:
         """Device linearisation (kernel K1) about the handle's (X_prev, U_prev): f, fx, fu."""
         check(self.lib.pmpc_linearize(self._h), "linearize")
         P, N, n, m = self.B * self.M, self.N, self.n, self.m
-        f, fx, fu = np.empty((P, N, n)), np.empty((P, N, n, n)), np.empty((P, N, m, n))
+        f, fx, fu = np.empty((P, N, n)), np.empty((P, N, n, n)), np.empty((P, N, n, m))
         check(self.lib.pmpc_get_linearization(self._h, dptr(f), dptr(fx), dptr(fu)), "get_linearization")
         shp = (self.B, self.M, N) if self.B > 1 else (self.M, N)
-        return f.reshape(shp + (n,)), np.swapaxes(fx, -1, -2).reshape(shp + (n, n)), np.swapaxes(fu, -1, -2).reshape(shp + (n, m))
+        return f.reshape(shp + (n,)), fx.reshape(shp + (n, n)), fu.reshape(shp + (n, m))
 
     def qp_solve(self, keep_prev=False):
         check(self.lib.pmpc_qp_solve(self._h, int(keep_prev)), "qp_solve")
@@ -142,6 +146,20 @@ class DeviceSolver:
         check(self.lib.pmpc_get_solution(self._h, dptr(X), dptr(U)), "get_solution")
         shp = (self.B, self.M, N) if self.B > 1 else (self.M, N)
         return X.reshape(shp + (self.n,)), U.reshape(shp + (self.m,))
+
+    def trajectory(self, reuse_buffers: bool = False):
+        """``X (B, M, N+1, n)`` including x0 and ``U (B, M, N, m)`` — the arrays ``solve`` returns
+        (``static_backend.py:311``), assembled on the device.  With ``reuse_buffers`` the results land in
+        page-locked buffers owned by this solver (overwritten by the next call) instead of fresh arrays."""
+        P, N = self.B * self.M, self.N
+        if reuse_buffers:
+            if self._out is None:
+                self._out = (pinned_empty((P, N + 1, self.n)), pinned_empty((P, N, self.m)))
+            X, U = self._out
+        else:
+            X, U = np.empty((P, N + 1, self.n)), np.empty((P, N, self.m))
+        check(self.lib.pmpc_get_trajectory(self._h, dptr(X), dptr(U)), "get_trajectory")
+        return X.reshape(self.B, self.M, N + 1, self.n), U.reshape(self.B, self.M, N, self.m)
 
     def info(self):
         buf = np.zeros((self.B, 8), dtype=np.int64)
