@@ -168,6 +168,20 @@ int pmpc_get_occupancy(pmpc_handle_t h, int *ctas_per_sm, int *num_sms);
 int pmpc_microbench(int device, int kind, double *result);
 
 /* ------------------------------------------------------------------------------------------
+ * 2b. Particle sharding of ONE consensus problem over the GPUs of a node (one process per GPU).
+ *     Rank r creates its handle with its own slice of the particles (M = local count, same B, N, Nc) and
+ *     gives every rank the shared-block bounds of global particle 0 in its local particle 0
+ *     (`lqp_utils.jl:329-330`).  Each rank exports its exchange buffer as a 64-byte CUDA IPC handle, the
+ *     host plumbing (torch.distributed / MPI / files) all-gathers the handles, pmpc_comm_connect maps the
+ *     peers' buffers.  From then on every solve on the handle exchanges the Nc*m consensus terms
+ *     (sum_i H_i once per factorisation, sum_i g_i once per pass) and the pass statistics INSIDE the
+ *     kernel by loads from peer memory over NVLink, combined in rank order (bit-identical on all ranks).
+ *     All ranks must issue the same sequence of solves.  world <= 8, B <= resident CTAs of the kernel.
+ * ------------------------------------------------------------------------------------------ */
+int pmpc_comm_export(pmpc_handle_t h, void *ipc_handle_64);
+int pmpc_comm_connect(pmpc_handle_t h, int rank, int world, const void *ipc_handles, size_t M_total);
+
+/* ------------------------------------------------------------------------------------------
  * 3. int-returning variant of the compat entry with explicit settings and statistics.
  * ------------------------------------------------------------------------------------------ */
 int pmpc_lqp_solve(double *X_out, double *U_out, size_t xdim, size_t udim, size_t N, size_t M,

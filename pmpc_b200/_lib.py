@@ -77,6 +77,8 @@ _SIG = {
     "pmpc_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pmpc_timer_start": (C.c_int, [C.c_void_p]),
     "pmpc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pmpc_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pmpc_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "pmpc_launch_count": (C.c_longlong, []),
     "pmpc_get_occupancy": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pmpc_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

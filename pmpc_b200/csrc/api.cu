@@ -75,6 +75,10 @@ struct pmpc_handle_s {
   size_t raw_doubles = 0;
   int* flags = nullptr;       // device-side NaN-sentinel analysis of the optional arguments (FL_*)
   int row_major = 0;          // matrices given as C-order (rows, cols) blocks instead of column-major
+  double* comm = nullptr;     // particle sharding: this rank's exchange buffer (IPC-exported to the peers)
+  size_t comm_bytes = 0;
+  void* peer_open[8] = {nullptr};  // peers' buffers opened with cudaIpcOpenMemHandle (to close on destroy)
+  unsigned long long seq = 0;  // exchange sequence base, advanced identically on every rank per launch
   double *lin_f = nullptr, *lin_fx = nullptr, *lin_fu = nullptr;  // reference-layout linearisation
   int* uniform = nullptr;     // per problem: cost / reference / bound data identical for all particles
   bool have_problem = false, have_dyn = false, solved = false;
@@ -369,6 +373,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   pb.Mpad = (M == 1) ? 1 : (int)(((M + 31) / 32) * 32);
   pb.P = (int)((((size_t)B * pb.Mpad + 31) / 32) * 32);
   pb.hist_len = 128;
+  pb.rank = 0; pb.world = 1; pb.M_total = (int)M; pb.comm_cap = 0; pb.seq0 = 0;
   pmpc_default_settings(&h->settings);
   apply_settings(h);
   // ---- carve one slab
@@ -441,6 +446,9 @@ int pmpc_destroy(pmpc_handle_t h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
   cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw);
+  for (int r = 0; r < 8; ++r)
+    if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_open[r]);
+  cudaFree(h->comm);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->tev0); cudaEventDestroy(h->tev1);
   cudaStreamDestroy(h->stream);
@@ -703,6 +711,12 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
     cudaError_t e = fn(pb, blocks, threads, h->stream, occ_out);
     return e == cudaSuccess ? PMPC_OK : fail(PMPC_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
   }
+  if (pb.world > 1) {
+    if (kind == 0) return fail(PMPC_ERR_UNSUPPORTED, "particle sharding needs at least 2 particles per rank");
+    // every launch gets its own window of exchange sequence numbers (flags only ever grow)
+    h->seq += (1ull << 32);
+    h->pb.seq0 = h->seq;
+  }
   CU(cudaEventRecord(h->ev0, h->stream));
   cudaError_t e = fn(pb, blocks, threads, h->stream, nullptr);
   if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -812,6 +826,49 @@ int pmpc_last_kernel_ms(pmpc_handle_t h, float* ms) {
   if (!h || !ms) return fail(PMPC_ERR_BAD_ARG, "null");
   if (h->solved && cudaEventQuery(h->ev1) == cudaSuccess) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   *ms = h->last_ms;
+  return PMPC_OK;
+}
+
+// ---- particle sharding over the GPUs of one node -------------------------------------------------
+int pmpc_comm_export(pmpc_handle_t h, void* ipc_handle_64) {
+  if (!h || !ipc_handle_64) return fail(PMPC_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!h->comm) {
+    const DevProb& pb = h->pb;
+    const size_t D = (size_t)pb.D;
+    const size_t cap = std::max<size_t>(D * D, (size_t)ST_COUNT) + 32;
+    h->comm_bytes = (size_t)pb.B * 2 * (cap + 1) * sizeof(double);
+    CU(cudaMalloc(&h->comm, h->comm_bytes));
+    CU(cudaMemset(h->comm, 0, h->comm_bytes));
+    h->pb.comm_cap = (int)cap;
+  }
+  cudaIpcMemHandle_t ih;
+  CU(cudaIpcGetMemHandle(&ih, h->comm));
+  memcpy(ipc_handle_64, &ih, 64);
+  return PMPC_OK;
+}
+
+int pmpc_comm_connect(pmpc_handle_t h, int rank, int world, const void* ipc_handles, size_t M_total) {
+  if (!h || !ipc_handles || world < 1 || world > 8 || rank < 0 || rank >= world)
+    return fail(PMPC_ERR_BAD_ARG, "rank/world (world <= 8) or handles");
+  if (!h->comm) return fail(PMPC_ERR_STATE, "pmpc_comm_export first");
+  CU(cudaSetDevice(h->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->pb.peer[r] = h->comm;
+      continue;
+    }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, (const char*)ipc_handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_open[r] = p;
+    h->pb.peer[r] = (double*)p;
+  }
+  h->pb.rank = rank;
+  h->pb.world = world;
+  h->pb.M_total = (int)M_total;
   return PMPC_OK;
 }
 

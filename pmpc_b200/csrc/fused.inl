@@ -950,6 +950,7 @@
         for (int k = 2; k < 7; ++k) sc[(size_t)k * T + tid] = acc[k];
         sc[(size_t)7 * T + tid] = nanf;
         reduce(8, red, 1000, 0x7cu);
+        xreduce(red, 8, false, 0x7cu);
         acc[0] = -red[0]; acc[1] = -red[1];
         for (int k = 2; k < 7; ++k) acc[k] = red[k];
         const double nf = red[7];

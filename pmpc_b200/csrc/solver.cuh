@@ -69,6 +69,12 @@ struct DevProb {
   // run parameters
   int max_it, keep_prev;
   double res_tol;
+  // particle sharding of ONE consensus problem over the GPUs of a node (SURVEY.md 8e case 2): this rank
+  // holds M of the M_total particles; the Nc*m consensus terms and the pass statistics are exchanged
+  // INSIDE the kernel through peer-mapped buffers (NVLink loads), see Solver::xreduce
+  int rank, world, M_total, comm_cap;   // comm_cap: doubles per exchange slot
+  unsigned long long seq0;              // exchange sequence number before this launch (same on every rank)
+  double* peer[8];                      // exchange buffer of every rank (peer[rank] is this GPU's own)
 };
 
 __host__ __device__ constexpr int pk(int r, int t, int n) { return r * n - (r * (r - 1)) / 2 + (t - r); }
@@ -163,10 +169,11 @@ struct Solver {
   bool has_tab;
   bool flip;  // fused path: (Xc, Uc) / (Xpv, Upv) currently are (pb.Xp, pb.Up) / (pb.X, pb.U)
   bool dead;  // whole warp beyond the last problem (thread-per-problem launch tail)
+  unsigned long long xseq;  // cross-GPU exchange counter (uniform over the CTA, identical on every rank)
 
   __device__ Solver(const DevProb& pb_, double* red_)
       : pb(pb_), P(pb_.P), N(pb_.N), Nc(GROUPED ? pb_.Nc : 0), D(GROUPED ? pb_.D : 0), T(blockDim.x),
-        tid(threadIdx.x), red(red_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up) {
+        tid(threadIdx.x), red(red_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0) {
     // lanes without a particle mirror the last valid lane of their own warp (same warp tile)
     dead = false;
     if (GROUPED) {
@@ -214,6 +221,49 @@ struct Solver {
         acc = warp_max(acc);
       }
       if (lane == 0) out[k] = acc;
+    }
+    __syncthreads();
+  }
+
+
+  // ---- cross-GPU all-reduce of a short vector (particle sharding) -------------------------------
+  // Every rank publishes its partial vector in its own exchange slot (double-buffered by sequence
+  // parity), raises the slot's flag to the sequence number with system-scope release, then reads the
+  // slots of ALL ranks over NVLink and combines them in rank order — the same order on every GPU, so
+  // the result is bit-identical everywhere and no broadcast is needed.  Payloads are D, D*D or a
+  // handful of scalars: latency-bound, hence inside the kernel instead of a host-launched collective.
+  // sum_mask: bit k set -> element k is summed, otherwise max-reduced; all_sum overrides.
+  __device__ __noinline__ void xreduce(double* vec, int len, bool all_sum, unsigned sum_mask = 0u) {
+    if (!GROUPED || pb.world <= 1) return;
+    __syncthreads();
+    ++xseq;
+    const size_t slot = (size_t)pb.comm_cap + 1;  // data + flag
+    const size_t off = ((size_t)prob * 2 + (size_t)(xseq & 1ull)) * slot;
+    volatile double* mine = pb.peer[pb.rank] + off;
+    for (int k = tid; k < len; k += T) mine[k] = vec[k];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long* flag = reinterpret_cast<unsigned long long*>(pb.peer[pb.rank] + off + pb.comm_cap);
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(xseq) : "memory");
+      for (int r = 0; r < pb.world; ++r) {
+        const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(pb.peer[r] + off + pb.comm_cap);
+        unsigned long long v;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(pf) : "memory");
+        } while (v < xseq);
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < len; k += T) {
+      const bool is_sum = all_sum || (k < 32 && ((sum_mask >> k) & 1u));
+      double acc = is_sum ? 0.0 : -INFINITY;
+      for (int r = 0; r < pb.world; ++r) {
+        const volatile double* p = pb.peer[r] + off;
+        const double v = p[k];
+        acc = is_sum ? acc + v : fmax(acc, v);
+      }
+      vec[k] = acc;
     }
     __syncthreads();
   }
@@ -667,6 +717,7 @@ struct Solver {
       }
       __syncthreads();
     }
+    xreduce(Hc, D * D, true);  // particle sharding: sum over the ranks
     // symmetrise, add the ADMM penalty of the shared block
     for (int idx = tid; idx < D * D; idx += T) {
       const int a = idx / D, b = idx % D;
@@ -765,6 +816,7 @@ struct Solver {
     if (!GROUPED || Nc < 1) return;
     shared_grad(mode, false, -1, nullptr, rho_u, rho_x, pc, zc, 0);
     reduce(D, pb.gc + (size_t)prob * D);
+    xreduce(pb.gc + (size_t)prob * D, D, true);
   }
 
   __device__ __noinline__ void apply_shared(int mode, double rho_u, bool use_mask = true) {
@@ -994,6 +1046,7 @@ struct Solver {
     if (GROUPED && Nc >= 1) {
       double* muc = pb.muc + (size_t)prob * D;
       reduce(D, muc);  // muc = sum_i reduced gradient on the shared block
+      xreduce(muc, D, true);
       const size_t g0 = (size_t)prob * pb.Mpad;
       const double* uc = pb.uc + (size_t)prob * D;
       const signed char* actc = pb.actc + (size_t)prob * D;
@@ -1103,6 +1156,7 @@ struct Solver {
     double* sc = scr();
     for (int k = 0; k < ST_COUNT; ++k) sc[(size_t)k * T + tid] = st[k];
     reduce(ST_COUNT, red, ST_OBJ);
+    xreduce(red, ST_COUNT, false, 1u << ST_OBJ);
     for (int k = 0; k < ST_COUNT; ++k) st[k] = red[k];
     __syncthreads();
   }
@@ -1341,7 +1395,7 @@ struct Solver {
         reduce_stats(st);
       }
       const double max_res = fmax(st[ST_DX], st[ST_DU]);
-      const double obj = st[ST_OBJ] / ((double)N * (double)pb.M);
+      const double obj = st[ST_OBJ] / ((double)N * (double)(pb.world > 1 ? pb.M_total : pb.M));
       if (writer && it < pb.hist_len) {
         double* h = pb.hist;
         const size_t Bn = (size_t)pb.B;

@@ -177,6 +177,19 @@ class DeviceSolver:
         check(self.lib.pmpc_get_occupancy(self._h, C.byref(a), C.byref(b)), "get_occupancy")
         return int(a.value), int(b.value)
 
+    # -- particle sharding over the GPUs of one node ----------------------------------------------
+    def comm_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange buffer (``pmpc_comm_export``)."""
+        buf = C.create_string_buffer(64)
+        check(self.lib.pmpc_comm_export(self._h, buf), "comm_export")
+        return buf.raw
+
+    def comm_connect(self, rank: int, world: int, handles, M_total: int):
+        """Map the peers' exchange buffers; ``handles`` = the ``world`` IPC handles in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * world
+        check(self.lib.pmpc_comm_connect(self._h, int(rank), int(world), C.c_char_p(blob), int(M_total)), "comm_connect")
+
     def timer_start(self):
         """CUDA event on the handle's stream (the stream every kernel of this handle runs on)."""
         check(self.lib.pmpc_timer_start(self._h), "timer_start")

@@ -4,8 +4,11 @@ collective (SURVEY.md 8e case 1: independent problems shard naturally).
 The reference's counterpart is the ZeroMQ task farm ``pmpc/remote.py:391-452`` (one problem per CPU
 worker process over TCP).  Here rank r owns the contiguous slice ``shard_bounds(B, r, world)`` of the
 problem batch and runs it on its own B200; only the per-rank wall/device time is reduced (max) for
-reporting.  Particle sharding of ONE consensus problem (8e case 2) needs a per-ADMM-iteration
-all-reduce of the Nc*m consensus terms and is not in this round (DESIGN.md "next").
+reporting.  
+Particle sharding of ONE consensus problem (8e case 2, BASELINE config 5): rank r holds the particles
+``shard_bounds(M, r, world)``; the Nc*m consensus terms and the pass statistics are all-reduced INSIDE
+the solve kernel through peer-mapped exchange buffers (``Solver::xreduce`` in csrc/solver.cuh), so
+the host only has to all-gather the 64-byte CUDA IPC handles once (``solve_consensus_sharded``).
 """
 from __future__ import annotations
 
@@ -78,3 +81,67 @@ def solve_problems_sharded(problems: Sequence[dict], dist=None, device: int = -1
     local = solve_batched(list(problems[lo:hi]), device=device)
     parts = gather_objects(local, dist)
     return [r for part in parts for r in part]
+
+
+def shard_particles(arrs: dict, lo: int, hi: int, Nc: int) -> dict:
+    """Rank-local slice ``[lo, hi)`` of the particle axis (axis 0) of every array of a consensus problem.
+    The shared block's bounds belong to global particle 0 (``lqp_utils.jl:329-330``): they are copied
+    into the local particle 0 so that every rank projects the shared controls identically."""
+    import numpy as np
+
+    out = {}
+    for k, v in arrs.items():
+        if v is None:
+            out[k] = None
+            continue
+        a = np.array(np.asarray(v, dtype=np.float64)[lo:hi])
+        if k in ("u_l", "u_u") and Nc > 0:
+            a[0, :Nc] = np.asarray(v, dtype=np.float64)[0, :Nc]
+        out[k] = a
+    return out
+
+
+def solve_consensus_sharded(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_prev=None, u_l=None, u_u=None,
+                            max_it: int = 100, res_tol: float = 1e-5, reg_x: float = 1.0, reg_u: float = 1e-2,
+                            slew_rate=0.0, Nc: int = 1, dyn_eps: float = 1e-6, dist=None, device: int = -1,
+                            ltv=None, settings=None):
+    """ONE consensus problem (arrays with leading particle axis M, as ``pmpc.solve`` takes them) with its
+    particles sharded over the ranks of ``dist`` (one process per GPU of one node).  Dynamics: Dubins car
+    with per-particle parameters ``dyn_params (M, 3)``, or ``ltv=(A, B, c)`` with ``A (M,N,n,n)``.
+    Every rank passes the same full arrays and gets the same full result ``X (M,N+1,n), U (M,N,m), info``.
+    Control box only (a state box needs the unsharded solver)."""
+    import numpy as np
+
+    from .handle import DeviceSolver
+
+    rank, world = (0, 1) if dist is None else (dist.get_rank(), dist.get_world_size())
+    Q = np.asarray(Q, dtype=np.float64)
+    M, N, n = Q.shape[:3]
+    m = np.asarray(R).shape[-1]
+    Nc_eff = N if Nc < 0 else int(Nc)
+    lo, hi = shard_bounds(M, rank, world)
+    assert hi - lo >= 2, "particle sharding needs at least 2 particles per rank"
+    full = dict(Q=Q, R=R, x0=x0, X_ref=X_ref, U_ref=U_ref, X_prev=X_prev, U_prev=U_prev, u_l=u_l, u_u=u_u)
+    loc = shard_particles(full, lo, hi, Nc_eff)
+    ds = DeviceSolver(hi - lo, N, n, m, Nc, B=1, device=device, settings=settings)
+    ds.set_problem(loc["x0"], loc["Q"], loc["R"], loc["X_ref"], loc["U_ref"], None, None, loc["u_l"], loc["u_u"], reg_x,
+                   reg_u, None if slew_rate is None else np.full(hi - lo, float(slew_rate)))
+    ds.set_warm_start(loc["X_ref"] if loc["X_prev"] is None else loc["X_prev"],
+                      loc["U_ref"] if loc["U_prev"] is None else loc["U_prev"])
+    if ltv is not None:
+        A, Bm, c = ltv
+        ds.set_ltv(np.asarray(A)[lo:hi], np.asarray(Bm)[lo:hi], None if c is None else np.asarray(c)[lo:hi])
+    else:
+        ds.set_dubins(np.asarray(dyn_params, dtype=np.float64)[lo:hi], dyn_eps)
+    if world > 1:
+        handles = gather_objects(ds.comm_export(), dist)
+        ds.comm_connect(rank, world, handles, M)
+        dist.barrier()  # every peer buffer is mapped before any kernel spins on it
+    ds.scp_solve(max_it, res_tol)
+    X, U = ds.trajectory()
+    info = {k: int(v[0]) for k, v in ds.info().items()}
+    info["kernel_ms"] = ds.last_kernel_ms()
+    parts = gather_objects((X[0], U[0]), dist)
+    if world > 1:
+        dist.barrier()  # nobody unmaps while a peer may still read
+    return np.concatenate([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts], 0), info

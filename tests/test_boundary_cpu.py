@@ -166,3 +166,20 @@ def test_two_process_gloo_sharding(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_shard_particles_copies_shared_block_bounds():
+    """Particle sharding (SURVEY 8e case 2): every rank must project the shared controls with global
+    particle 0's bounds (lqp_utils.jl:329-330) whatever its own slice says."""
+    from pmpc_b200 import parallel
+
+    rng = np.random.default_rng(0)
+    M, N, m, Nc = 6, 5, 2, 2
+    full = dict(u_l=-rng.uniform(0.5, 1.0, (M, N, m)), u_u=rng.uniform(0.5, 1.0, (M, N, m)), x0=rng.standard_normal((M, 3)),
+                X_ref=None)
+    parts = [parallel.shard_particles(full, *parallel.shard_bounds(M, r, 3), Nc) for r in range(3)]
+    assert np.array_equal(np.concatenate([p["x0"] for p in parts]), full["x0"]) and parts[1]["X_ref"] is None
+    for r, p in enumerate(parts):
+        lo, hi = parallel.shard_bounds(M, r, 3)
+        assert np.array_equal(p["u_l"][0, :Nc], full["u_l"][0, :Nc]) and np.array_equal(p["u_u"][0, :Nc], full["u_u"][0, :Nc])
+        assert np.array_equal(p["u_l"][0, Nc:], full["u_l"][lo, Nc:]) and np.array_equal(p["u_l"][1:], full["u_l"][lo + 1:hi])

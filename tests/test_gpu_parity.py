@@ -254,3 +254,29 @@ def test_ltv_c4_reduced_matches_oracle(gpu):
                                 x_u=d["x_u"], reg_x=d["reg_x"], reg_u=d["reg_u"], slew_rate=d["slew_rate"],
                                 max_it=d["max_it"], res_tol=d["res_tol"], solver_settings=d["solver_settings"])
     assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+
+
+def _gpu_count():
+    from pmpc_b200 import _lib
+    return _lib.device_count()
+
+
+def test_particle_sharded_consensus_two_gpus(gpu, tmp_path):
+    """SURVEY 8e case 2: ONE consensus problem, particles sharded over 2 GPUs, consensus terms exchanged
+    inside the kernel over peer memory == the same problem on one GPU."""
+    import json
+    import subprocess
+    import sys
+
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = tmp_path / "sharded.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(os.path.dirname(__file__), "sharded_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(out.read_text())
+    for name, v in res.items():
+        assert v["status"] == 0 and v["consensus"], (name, v)
+        assert v["scp_iters"] == v["scp_iters_single"], (name, v)
+        assert v["err_X"] < 1e-8 and v["err_U"] < 1e-8, (name, v)
