@@ -22,9 +22,10 @@
   // =============================================================================================
   static constexpr bool RING_SHAPE = (NX <= 4);
   static constexpr int DEPTH = 3;
-  // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | act]
+  // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | (L) | act]
   static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_K = R_UP + NU * 32, R_KF = R_K + NU * NX * 32,
-                       R_H = R_KF + NU * 32, R_ACTF = R_H + NR * 32, R_ACTB = R_UP + NU * 32;
+                       R_H = R_KF + NU * 32, R_LIN = R_H + NR * 32, R_ACTF = R_LIN + ((NX == 4 && NU == 2) ? 14 * 32 : 0),
+                       R_ACTB = R_UP + NU * 32;
   static constexpr int SLOT = R_ACTF + NU * 4;
   // uniform cost table row: [Qs | Rs | qref | rref | xref | uref | lu | uu]
   static constexpr int T_QS = 0, T_RS = T_QS + NQ, T_QR = T_RS + NR, T_RR = T_QR + NX, T_XR = T_RR + NU,
@@ -142,6 +143,47 @@
     }
   }
 
+  // ---- structure of the Dubins linearisation (lean Dubins variant) ----------------------------------
+  // fx = I + N with N non-zero only in rows 0,1 x columns 2,3; fu non-zero at (0,0) (0,1) (1,0) (1,1) (2,0) (3,1)
+  // (tests/dubins_car.py:48-90 differentiated).  The stage is carried as 14 doubles
+  //     L = [n02 n03 n12 n13 | b00 b01 b10 b11 b20 b31 | c0 c1 c2 c3]
+  // which (a) cuts the Riccati algebra from ~330 to ~135 FMAs per stage and (b) is small enough to hand
+  // from the backward to the forward sweep through HBM + the TMA ring, so the forward sweep does not
+  // evaluate the dynamics again.  Stage 0 has A = 0 (lqp_utils.jl:288-296): its n-entries are unused.
+  static constexpr int NLIN = 14;
+  static constexpr bool CAN_SPARSE = (NX == 4 && NU == 2);
+  __device__ __forceinline__ void lin_sparse(const DevProb& pb, int j, const double* xm1, const double* ub,
+                                             const double* dp, double* L) const {
+    if constexpr (CAN_SPARSE) {
+      double f[4], fx[16], fu[8];
+      dubins_f_fx_fu(xm1, ub, dp[0], dp[1], dp[2], pb.dyn_eps, f, fx, fu);
+      L[0] = fx[2]; L[1] = fx[3]; L[2] = fx[6]; L[3] = fx[7];
+      L[4] = fu[0]; L[5] = fu[1]; L[6] = fu[2]; L[7] = fu[3]; L[8] = fu[4]; L[9] = fu[7];
+      double c0 = f[0] - L[4] * ub[0] - L[5] * ub[1], c1 = f[1] - L[6] * ub[0] - L[7] * ub[1];
+      double c2 = f[2] - L[8] * ub[0], c3 = f[3] - L[9] * ub[1];
+      if (j >= 1) {
+        c0 -= xm1[0] + L[0] * xm1[2] + L[1] * xm1[3];
+        c1 -= xm1[1] + L[2] * xm1[2] + L[3] * xm1[3];
+        c2 -= xm1[2];
+        c3 -= xm1[3];
+      }
+      L[10] = c0; L[11] = c1; L[12] = c2; L[13] = c3;
+    }
+  }
+  // dense (A, B, c) of a sparse stage, for the shared stages the consensus step reads
+  __device__ __forceinline__ void lin_expand(int j, const double* L, double* A, double* Bm, double* c) const {
+    if constexpr (CAN_SPARSE) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) A[e] = 0.0;
+      if (j >= 1) {
+        A[0] = A[5] = A[10] = A[15] = 1.0;
+        A[2] = L[0]; A[3] = L[1]; A[6] = L[2]; A[7] = L[3];
+      }
+      Bm[0] = L[4]; Bm[1] = L[5]; Bm[2] = L[6]; Bm[3] = L[7]; Bm[4] = L[8]; Bm[5] = 0.0; Bm[6] = 0.0; Bm[7] = L[9];
+      c[0] = L[10]; c[1] = L[11]; c[2] = L[12]; c[3] = L[13];
+    }
+  }
+
   // ---- interior-point fallback (ALG = 1) -------------------------------------------------------
   // The primal-dual active-set iteration can cycle on a strictly convex box QP.  When it does, the same
   // two sweeps run a primal-dual interior-point method instead: with slacks sh = hi - u, sl = u - lo and
@@ -207,16 +249,17 @@
     bulk_g2s(dst + R_UP, blk(Upv, jj, NU), NU * 256, bar);
     if (UBOX) bulk_g2s(dst + R_ACTB, blk(pb.act, jj, NU), NU * 32, bar);
   }
-  template <bool UBOX>
+  template <bool UBOX, bool SPD = false>
   __device__ __forceinline__ void issue_f(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl) {
     double* dst = sm.ring + sl * SLOT;
     uint64_t* bar = sm.bars + sl;
     const FactorSet& F = pb.fs[MODE_POLISH];
-    uint32_t bytes = (NX + NU) * 256;
+    uint32_t bytes = (NX + NU) * 256 + (SPD ? NLIN * 256 : 0);
     if (jj >= Nc) bytes += (NU * NX + NU) * 256 + (UBOX ? NR * 256 + NU * 32 : 0);
     mbar_expect_tx(bar, bytes);
     bulk_g2s(dst + R_XP, blk(Xpv, jj, NX), NX * 256, bar);
     bulk_g2s(dst + R_UP, blk(Upv, jj, NU), NU * 256, bar);
+    if (SPD) bulk_g2s(dst + R_LIN, blk(pb.lin, jj, NLIN), NLIN * 256, bar);
     if (jj >= Nc) {
       bulk_g2s(dst + R_K, blk(F.K, jj, NU * NX), NU * NX * 256, bar);
       bulk_g2s(dst + R_KF, blk(pb.kff, jj, NU), NU * 256, bar);
@@ -308,8 +351,20 @@
           for (int t = 0; t < NU; ++t) act[t] = (j >= Nc && ALG == 0) ? pb.act[ix(j, NU, t)] : 0;
         }
       }
-      double A[NX * NX], Bm[NX * NU], cv[NX];
-      lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
+      constexpr bool SPD = DUB && !SLEW && CAN_SPARSE;  // sparse Dubins stage (lean Dubins variant)
+      double A[NX * NX], Bm[NX * NU], cv[NX], L[NLIN];
+      if constexpr (SPD) {
+        lin_sparse(pb, j, xm1, ub, dp, L);
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < NLIN; ++e) at(pb.lin, j, NLIN, e) = L[e];
+        }
+#pragma unroll
+        for (int e = 0; e < NX; ++e) cv[e] = L[10 + e];
+        if (j < Nc) lin_expand(j, L, A, Bm, cv);
+      } else {
+        lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
+      }
       // proximal / reference linear terms (lqp_utils.jl:164-214)
       double q[NX], r[NU];
       cost_field(sm.tab, j, T_QR, NX, pb.qref, q);
@@ -360,18 +415,36 @@
         }
         // SBW = S B + W
         double SBW[NX * NU];
-#pragma unroll UNR
-        for (int rr = 0; rr < NX; ++rr)
-#pragma unroll UNR
-          for (int t = 0; t < NU; ++t) {
-            double acc = SLEW ? W[rr * NU + t] : 0.0;
-#pragma unroll UNR
-            for (int k = 0; k < NX; ++k) acc += S[rr <= k ? pk(rr, k, NX) : pk(k, rr, NX)] * Bm[k * NU + t];
-            SBW[rr * NU + t] = acc;
+        if constexpr (SPD) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const double s0 = S[rr <= 0 ? pk(rr, 0, 4) : pk(0, rr, 4)], s1 = S[rr <= 1 ? pk(rr, 1, 4) : pk(1, rr, 4)];
+            const double s2 = S[rr <= 2 ? pk(rr, 2, 4) : pk(2, rr, 4)], s3 = S[rr <= 3 ? pk(rr, 3, 4) : pk(3, rr, 4)];
+            SBW[rr * 2 + 0] = s0 * L[4] + s1 * L[6] + s2 * L[8];
+            SBW[rr * 2 + 1] = s0 * L[5] + s1 * L[7] + s3 * L[9];
           }
+        } else {
+#pragma unroll UNR
+          for (int rr = 0; rr < NX; ++rr)
+#pragma unroll UNR
+            for (int t = 0; t < NU; ++t) {
+              double acc = SLEW ? W[rr * NU + t] : 0.0;
+#pragma unroll UNR
+              for (int k = 0; k < NX; ++k) acc += S[rr <= k ? pk(rr, k, NX) : pk(k, rr, NX)] * Bm[k * NU + t];
+              SBW[rr * NU + t] = acc;
+            }
+        }
         // H = Rs + [j>=1] s I + B'(SB + W) + W'B + Z ;  h0 = r + B'wv + W'c + z
         double H[NU * NU], h0[NU];
-        {
+        if constexpr (SPD) {
+          double Rp[NR];
+          cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
+          H[0] = Rp[0] + (ALG == 1 ? sig[0] : 0.0) + L[4] * SBW[0] + L[6] * SBW[2] + L[8] * SBW[4];
+          H[1] = H[2] = Rp[1] + L[4] * SBW[1] + L[6] * SBW[3] + L[8] * SBW[5];
+          H[3] = Rp[2] + (ALG == 1 ? sig[1] : 0.0) + L[5] * SBW[1] + L[7] * SBW[3] + L[9] * SBW[7];
+          h0[0] = r[0] + L[4] * wv[0] + L[6] * wv[1] + L[8] * wv[2];
+          h0[1] = r[1] + L[5] * wv[0] + L[7] * wv[1] + L[9] * wv[3];
+        } else {
           double Rp[NR];
           cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
 #pragma unroll UNR
@@ -392,16 +465,16 @@
               H[a * NU + b] = acc;
               H[b * NU + a] = acc;
             }
-        }
 #pragma unroll UNR
-        for (int a = 0; a < NU; ++a) {
-          double acc = r[a] + (SLEW ? z[a] : 0.0);
+          for (int a = 0; a < NU; ++a) {
+            double acc = r[a] + (SLEW ? z[a] : 0.0);
 #pragma unroll UNR
-          for (int k = 0; k < NX; ++k) {
-            acc += Bm[k * NU + a] * wv[k];
-            if (SLEW) acc += W[k * NU + a] * cv[k];
+            for (int k = 0; k < NX; ++k) {
+              acc += Bm[k * NU + a] * wv[k];
+              if (SLEW) acc += W[k * NU + a] * cv[k];
+            }
+            h0[a] = acc;
           }
-          h0[a] = acc;
         }
         bool fixed[NU];
         double ufix[NU], E[NU * NU];
@@ -443,15 +516,25 @@
         double K[NU * NX], G[NU * NX];
         if (j >= 1) {
           // G = (SB + W)' A ;  K = -E G
-#pragma unroll UNR
-          for (int a = 0; a < NU; ++a)
-#pragma unroll UNR
-            for (int t = 0; t < NX; ++t) {
-              double acc = 0.0;
-#pragma unroll UNR
-              for (int k = 0; k < NX; ++k) acc += SBW[k * NU + a] * A[k * NX + t];
-              G[a * NX + t] = acc;
+          if constexpr (SPD) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              G[a * 4 + 0] = SBW[0 * 2 + a];
+              G[a * 4 + 1] = SBW[1 * 2 + a];
+              G[a * 4 + 2] = SBW[2 * 2 + a] + SBW[0 * 2 + a] * L[0] + SBW[1 * 2 + a] * L[2];
+              G[a * 4 + 3] = SBW[3 * 2 + a] + SBW[0 * 2 + a] * L[1] + SBW[1 * 2 + a] * L[3];
             }
+          } else {
+#pragma unroll UNR
+            for (int a = 0; a < NU; ++a)
+#pragma unroll UNR
+              for (int t = 0; t < NX; ++t) {
+                double acc = 0.0;
+#pragma unroll UNR
+                for (int k = 0; k < NX; ++k) acc += SBW[k * NU + a] * A[k * NX + t];
+                G[a * NX + t] = acc;
+              }
+          }
 #pragma unroll UNR
           for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
@@ -463,7 +546,39 @@
             }
           // p <- A'(wv + SBW k) + G'... : with u = K x + k the cost-to-go gradient is
           //   p' = A' wv + G' k   (+ K'(h0 + H k + ...) = 0 on free comps, and fixed comps have K = 0)
-          double pn[NX];
+          double pn[NX], Pn[NQ];
+          if constexpr (SPD) {
+            pn[0] = wv[0]; pn[1] = wv[1];
+            pn[2] = wv[2] + L[0] * wv[0] + L[2] * wv[1];
+            pn[3] = wv[3] + L[1] * wv[0] + L[3] * wv[1];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) pn[t] += G[0 * 4 + t] * kv[0] + G[1 * 4 + t] * kv[1];
+            // A'SA with A = I + N:  T = S[:,0:2] N2 ; U = S[0:2,2:4] + T[0:2,:] ; lower-right += T[2:4,:] + N2'U
+            double Tm[4 * 2], Um[2 * 2];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const double s0 = S[rr <= 0 ? pk(rr, 0, 4) : pk(0, rr, 4)], s1 = S[rr <= 1 ? pk(rr, 1, 4) : pk(1, rr, 4)];
+              Tm[rr * 2 + 0] = s0 * L[0] + s1 * L[2];
+              Tm[rr * 2 + 1] = s0 * L[1] + s1 * L[3];
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) Um[rr * 2 + c] = S[pk(rr, 2 + c, 4)] + Tm[rr * 2 + c];
+            Pn[pk(0, 0, 4)] = S[pk(0, 0, 4)]; Pn[pk(0, 1, 4)] = S[pk(0, 1, 4)]; Pn[pk(1, 1, 4)] = S[pk(1, 1, 4)];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) Pn[pk(rr, 2 + c, 4)] = Um[rr * 2 + c];
+            // (2+d, 2+c), d <= c:  S + T[2+d][c] + N2[0][d] U[0][c] + N2[1][d] U[1][c]   (N2[0][.] = L0,L1 ; N2[1][.] = L2,L3)
+            Pn[pk(2, 2, 4)] = S[pk(2, 2, 4)] + Tm[2 * 2 + 0] + L[0] * Um[0] + L[2] * Um[2];
+            Pn[pk(2, 3, 4)] = S[pk(2, 3, 4)] + Tm[2 * 2 + 1] + L[0] * Um[1] + L[2] * Um[3];
+            Pn[pk(3, 3, 4)] = S[pk(3, 3, 4)] + Tm[3 * 2 + 1] + L[1] * Um[1] + L[3] * Um[3];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+              for (int rr = 0; rr <= t; ++rr) Pn[pk(rr, t, 4)] += G[0 * 4 + rr] * K[0 * 4 + t] + G[1 * 4 + rr] * K[1 * 4 + t];
+          } else {
 #pragma unroll UNR
           for (int t = 0; t < NX; ++t) {
             double acc = 0.0;
@@ -473,10 +588,7 @@
             for (int a = 0; a < NU; ++a) acc += G[a * NX + t] * kv[a];
             pn[t] = acc;
           }
-#pragma unroll UNR
-          for (int t = 0; t < NX; ++t) p[t] = pn[t];
           // P <- A' S A + G' K   (column t of S A at a time keeps the live set small)
-          double Pn[NQ];
 #pragma unroll UNR
           for (int t = 0; t < NX; ++t) {
             double sa[NX];
@@ -497,6 +609,9 @@
               Pn[pk(rr, t, NX)] = acc;
             }
           }
+          }
+#pragma unroll UNR
+          for (int t = 0; t < NX; ++t) p[t] = pn[t];
 #pragma unroll UNR
           for (int e = 0; e < NQ; ++e) Pm[e] = Pn[e];
           if (SLEW) {
@@ -584,6 +699,7 @@
     const FactorSet& F = pb.fs[MODE_POLISH];
     const Sm sm = smem_view(pb, smem);
     const bool use_ring = RING_SHAPE && sm.ring != nullptr;
+    constexpr bool SPD = DUB && !SLEW && CAN_SPARSE;  // the backward sweep left the sparse stage in pb.lin
     const double* const Xpv = flip ? pb.X : pb.Xp;
     const double* const Upv = flip ? pb.U : pb.Up;
     double* const Xc = flip ? pb.Xp : pb.X;
@@ -596,7 +712,7 @@
       __syncwarp();
       if (lane == 0) {
         for (int d = 0; d < DEPTH; ++d)
-          if (d < N) issue_f<UBOX>(pb, sm, Xpv, Upv, d, (rcount + d) % DEPTH);
+          if (d < N) issue_f<UBOX, SPD>(pb, sm, Xpv, Upv, d, (rcount + d) % DEPTH);
       }
     }
     const double* uc = (GROUPED && Nc >= 1) ? pb.uc + (size_t)prob * D : nullptr;
@@ -609,7 +725,7 @@
            gscale = 1.0, zscale = 1.0;
     const double rdiag = pb.rdiag0[g];
     for (int j = 0; j < N; ++j) {
-      double ub[NU], xpj[NX], Kj[NU * NX], kf[NU], Hj[NR], u[NU], xn[NX];
+      double ub[NU], xpj[NX], Kj[NU * NX], kf[NU], Hj[NR], u[NU], xn[NX], L[NLIN];
       signed char act[NU];
 #pragma unroll UNR
       for (int t = 0; t < NU; ++t) act[t] = 0;
@@ -621,6 +737,10 @@
         for (int e = 0; e < NX; ++e) xpj[e] = b[R_XP + e * 32];
 #pragma unroll UNR
         for (int e = 0; e < NU; ++e) ub[e] = b[R_UP + e * 32];
+        if (SPD) {
+#pragma unroll
+          for (int e = 0; e < NLIN; ++e) L[e] = b[R_LIN + e * 32];
+        }
         if (j >= Nc) {
 #pragma unroll UNR
           for (int e = 0; e < NU * NX; ++e) Kj[e] = b[R_K + e * 32];
@@ -635,13 +755,17 @@
           }
         }
         __syncwarp();
-        if (lane == 0 && j + DEPTH < N) issue_f<UBOX>(pb, sm, Xpv, Upv, j + DEPTH, sl);
+        if (lane == 0 && j + DEPTH < N) issue_f<UBOX, SPD>(pb, sm, Xpv, Upv, j + DEPTH, sl);
         ++rcount;
       } else {
 #pragma unroll UNR
         for (int e = 0; e < NX; ++e) xpj[e] = ld(Xpv, j, NX, e);
 #pragma unroll UNR
         for (int e = 0; e < NU; ++e) ub[e] = ld(Upv, j, NU, e);
+        if (SPD) {
+#pragma unroll
+          for (int e = 0; e < NLIN; ++e) L[e] = ld(pb.lin, j, NLIN, e);
+        }
         if (j >= Nc) {
 #pragma unroll UNR
           for (int e = 0; e < NU * NX; ++e) Kj[e] = ld(F.K, j, NU * NX, e);
@@ -723,18 +847,32 @@
           }
         }
       }
-      double A[NX * NX], Bm[NX * NU], cv[NX];
-      lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
-#pragma unroll UNR
-      for (int r = 0; r < NX; ++r) {
-        double acc = cv[r];
+      if constexpr (SPD) {
+        // x+ = (I + N) x + B u + c with the sparse stage (stage 0: A = 0)
+        xn[0] = L[10] + L[4] * u[0] + L[5] * u[1];
+        xn[1] = L[11] + L[6] * u[0] + L[7] * u[1];
+        xn[2] = L[12] + L[8] * u[0];
+        xn[3] = L[13] + L[9] * u[1];
         if (j >= 1) {
-#pragma unroll UNR
-          for (int t = 0; t < NX; ++t) acc += A[r * NX + t] * x[t];
+          xn[0] += x[0] + L[0] * x[2] + L[1] * x[3];
+          xn[1] += x[1] + L[2] * x[2] + L[3] * x[3];
+          xn[2] += x[2];
+          xn[3] += x[3];
         }
+      } else {
+        double A[NX * NX], Bm[NX * NU], cv[NX];
+        lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
 #pragma unroll UNR
-        for (int t = 0; t < NU; ++t) acc += Bm[r * NU + t] * u[t];
-        xn[r] = acc;
+        for (int r = 0; r < NX; ++r) {
+          double acc = cv[r];
+          if (j >= 1) {
+#pragma unroll UNR
+            for (int t = 0; t < NX; ++t) acc += A[r * NX + t] * x[t];
+          }
+#pragma unroll UNR
+          for (int t = 0; t < NU; ++t) acc += Bm[r * NU + t] * u[t];
+          xn[r] = acc;
+        }
       }
       if (valid) {
 #pragma unroll UNR

@@ -49,6 +49,7 @@ struct DevProb {
   FactorSet fs[2];            // [MODE_POLISH], [MODE_ADMM]
   double *kff, *X, *U;
   double *Hs;                 // fused path: stage Hessian H of the Q-function (packed), for the multipliers
+  double *lin;                // lean Dubins variant: sparse stage [N2 | B | c] (14 doubles) handed from bsweep to fsweep
   double *wu, *yu, *wx, *yx;
   signed char *act, *actn;    // per (particle, stage, control): -1 lower, +1 upper, 0 free
   // per problem

@@ -26,8 +26,11 @@ def main():
     rank, world, local = parallel.env_rank_world()
     dist = parallel.init_process_group("gloo")
     res = {}
-    for name, (M, N, Nc) in dict(c2_small=(64, 20, 1), c2_full=(128, 50, 1), nc3=(32, 16, 3)).items():
+    # "wide": control box +-5, so the shared controls are interior and the exchanged sums decide them
+    for name, (M, N, Nc, box) in dict(c2_small=(64, 20, 1, 1.0), c2_full=(128, 50, 1, 1.0), nc3=(32, 16, 3, 1.0),
+                                      wide=(64, 20, 2, 5.0)).items():
         d, p = config_c2(M, N)
+        d["u_l"], d["u_u"] = box * d["u_l"], box * d["u_u"]
         kw = dict(X_ref=d["X_ref"], U_ref=d["U_ref"], X_prev=d["X_prev"], U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"],
                   reg_x=d["reg_x"], reg_u=d["reg_u"], max_it=d["max_it"], res_tol=d["res_tol"], Nc=Nc)
         t = time.time()

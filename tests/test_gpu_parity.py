@@ -256,6 +256,26 @@ def test_ltv_c4_reduced_matches_oracle(gpu):
     assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
 
 
+def test_interior_point_fallback_matches_oracle(gpu):
+    """polish_iters = 1 makes every QP whose first active-set guess is wrong leave the primal-dual
+    active-set iteration immediately: the interior-point fallback (+ certifying polish pass) has to
+    deliver the same QP minimisers, i.e. the same SCP trajectory as the oracle."""
+    d, p = config_c2(M=8, N=15)
+    d.update(res_tol=1e-7, max_it=60)
+    Xo, Uo, do = _oracle_scp(d, p)
+    X, U, data = pmpc_b200.solve(DubinsCar(p), **dict(d, solver_settings=dict(d["solver_settings"], b200=dict(polish_iters=1))))
+    assert data["device"]["status"] == 0 and data["device"]["admm_iters"] > 0  # fallback iterations are counted here
+    assert len(data["hist"]) == len(do["hist"])
+    assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+    assert max(sd["kkt"] for sd in data["solver_data"]) < 1e-8
+    # single-particle problems (thread-per-problem kernel) take the same route
+    d1, p1 = config_c1()
+    Xo1, Uo1, _ = _oracle_scp(d1, p1)
+    k1 = {k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in d1.items()}
+    X1, U1, data1 = pmpc_b200.solve(DubinsCar(p1[0]), **dict(k1, solver_settings=dict(d1["solver_settings"], b200=dict(polish_iters=1))))
+    assert rel(X1, Xo1[0]) < 1e-5 and rel(U1, Uo1[0]) < 1e-5
+
+
 def _gpu_count():
     from pmpc_b200 import _lib
     return _lib.device_count()
