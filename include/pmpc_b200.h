@@ -126,8 +126,25 @@ int pmpc_set_linearization(pmpc_handle_t h, const double *f, const double *fx, c
 /* LTV system x+ = A_j x + B_j u + c_j given once (fx = A, fu = B, c may be NULL). */
 int pmpc_set_ltv(pmpc_handle_t h, const double *A, const double *Bm, const double *c);
 
-/* Linearise only (built-in dynamics) about the handle's (X_prev, U_prev); results readable with
- * pmpc_get_linearization in reference layout. */
+/* User device dynamics (north_star: "a C-ABI hook for registering user device dynamics").  Replaces the
+ * reference's host callable `f_fx_fu_fn(X_, U_prev) -> f, fx, fu` (pmpc/scp_mpc.py:338-342; e.g.
+ * tests/dubins_car.py:48-90 evaluated through torch autograd on the CPU every SCP iteration) by CUDA C++
+ * source that defines
+ *     __device__ void <fn_name>(const double *x, const double *u, const double *p,
+ *                               double *f, double *fx, double *fu);
+ * x (xdim) is the state the control u (udim) is applied to, p the particle's `nparam` parameters; the
+ * function writes f (xdim) = the next state, fx[r*xdim + t] = df_r/dx_t and fu[r*udim + t] = df_r/du_t
+ * (row-major; all three are zero on entry).  The source is compiled at run time with NVRTC for sm_100a into
+ * a linearisation kernel that writes straight into the handle's HBM layout; compile errors are returned
+ * through pmpc_last_error().  params: (nparam, B*M) column-major as for pmpc_set_dynamics, NULL if
+ * nparam == 0.  Afterwards pmpc_linearize / pmpc_qp_solve / pmpc_scp_solve use it; the SCP loop is then
+ * driven from the host (one solve-kernel launch per iteration, 4 bytes read back per iteration) and
+ * pmpc_scp_solve_async is synchronous. */
+int pmpc_register_dynamics(pmpc_handle_t h, const char *cuda_src, const char *fn_name,
+                           const double *params, size_t nparam);
+
+/* Linearise only (built-in or registered dynamics) about the handle's (X_prev, U_prev); results readable
+ * with pmpc_get_linearization in reference layout. */
 int pmpc_linearize(pmpc_handle_t h);
 int pmpc_get_linearization(pmpc_handle_t h, double *f, double *fx, double *fu);
 

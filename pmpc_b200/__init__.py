@@ -8,10 +8,10 @@ from .scp_mpc import (  # noqa: F401
     AA_method, FILTER_MAP, scp_solve, select_method, smooth_method, solve, solve_problems,
 )
 from .static_backend import aff_solve, is_precompiled_backend_available, lqp_solve  # noqa: F401
-from .dynamics import BuiltinDynamics, DubinsCar, LTV  # noqa: F401
+from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics  # noqa: F401
 from .handle import DeviceSolver  # noqa: F401
 from .batch import solve_batch  # noqa: F401
-from ._lib import pinned_copy, pinned_empty  # noqa: F401
+from ._lib import PmpcError, pinned_copy, pinned_empty  # noqa: F401
 from .problem_struct import Problem  # noqa: F401
 
 """Keyword-compatible arguments in the solver scp solve call (reference pmpc/__init__.py:4-33)."""

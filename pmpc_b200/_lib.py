@@ -64,6 +64,7 @@ _SIG = {
     "pmpc_set_dynamics": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_size_t, C.c_double]),
     "pmpc_set_linearization": (C.c_int, [C.c_void_p, _DP, _DP, _DP]),
     "pmpc_set_ltv": (C.c_int, [C.c_void_p, _DP, _DP, _DP]),
+    "pmpc_register_dynamics": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, _DP, C.c_size_t]),
     "pmpc_linearize": (C.c_int, [C.c_void_p]),
     "pmpc_get_linearization": (C.c_int, [C.c_void_p, _DP, _DP, _DP]),
     "pmpc_qp_solve": (C.c_int, [C.c_void_p, C.c_int]),

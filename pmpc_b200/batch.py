@@ -11,13 +11,13 @@ from typing import Any, Dict, List, Optional
 
 import numpy as np
 
-from .dynamics import BuiltinDynamics, DubinsCar, LTV
+from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics
 from .handle import DeviceSolver
 
 
 def _sig(p: Dict[str, Any]):
     dyn = p.get("f_fx_fu_fn")
-    if not isinstance(dyn, (DubinsCar, LTV)):
+    if not isinstance(dyn, (DubinsCar, LTV, UserDynamics)):
         return None
     if any(p.get(k) is not None and p.get(k) != "" for k in ("lin_cost_fn", "extra_cstrs_fns")) or p.get("filter_method", ""):
         return None
@@ -25,7 +25,8 @@ def _sig(p: Dict[str, Any]):
     Q, R = np.asarray(p["Q"]), np.asarray(p["R"])
     ss = p.get("solver_settings") or {}
     present = tuple(p.get(k) is not None and np.size(p.get(k)) > 0 for k in ("x_l", "x_u", "u_l", "u_u"))
-    return (type(dyn).__name__, getattr(dyn, "eps", None), x0.ndim, Q.shape, R.shape, ss.get("Nc", -1), ss.get("slew_reg"),
+    user = (dyn.src, dyn.fn_name, dyn.params is None) if isinstance(dyn, UserDynamics) else None
+    return (type(dyn).__name__, user, getattr(dyn, "eps", None), x0.ndim, Q.shape, R.shape, ss.get("Nc", -1), ss.get("slew_reg"),
             float(p.get("reg_x", 1.0)), float(p.get("reg_u", 1e-2)), p.get("slew_rate", 0.0), p.get("u0_slew") is None,
             present, int(p.get("max_it", 100)), float(p.get("res_tol", 1e-5)))
 
@@ -67,6 +68,9 @@ def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: O
     dyn0 = p0["f_fx_fu_fn"]
     if isinstance(dyn0, DubinsCar):
         ds.set_dubins(np.stack([p["f_fx_fu_fn"].params_for(M) for p in problems]), dyn0.eps)
+    elif isinstance(dyn0, UserDynamics):
+        ds.register_dynamics(dyn0.src, dyn0.fn_name,
+                             None if dyn0.params is None else np.stack([p["f_fx_fu_fn"].params_for(M) for p in problems]))
     else:
         bc = lambda a, tail: np.stack([np.broadcast_to(np.asarray(getattr(p["f_fx_fu_fn"], a)), (M, N) + tail) for p in problems])
         ds.set_ltv(bc("A", (n, n)), bc("B", (n, m)), None if dyn0.c is None else bc("c", (n,)))

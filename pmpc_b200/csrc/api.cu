@@ -1,6 +1,7 @@
 // C ABI of libpmpc_b200.so: handle management, layout packing kernels, kernel dispatch and the
 // byte-compatible `c_lqp_solve` / `c_lcone_solve` entry points (see include/pmpc_b200.h).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -58,6 +59,8 @@ static bool pick_shape(int n, int m, Shape* out) {
   return false;
 }
 
+struct pmpc_userdyn_s;  // userdyn.inl
+
 struct pmpc_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -84,6 +87,9 @@ struct pmpc_handle_s {
   bool have_problem = false, have_dyn = false, solved = false;
   pmpc_settings settings{};
   float last_ms = 0.f;
+  pmpc_userdyn_s* user = nullptr;              // registered user device dynamics (pmpc_register_dynamics)
+  cudaEvent_t uev0 = nullptr, uev1 = nullptr;  // span of the host-driven SCP loop
+  bool user_timed = false;                     // last_ms already holds that span
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -363,6 +369,8 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaEventCreate(&h->ev1));
   CU(cudaEventCreate(&h->tev0));
   CU(cudaEventCreate(&h->tev1));
+  CU(cudaEventCreate(&h->uev0));
+  CU(cudaEventCreate(&h->uev1));
   h->shape = sh;
   h->Nc_orig = Nc;
   h->Ptot = B * M;
@@ -440,10 +448,14 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   return PMPC_OK;
 }
 
+static void userdyn_free(pmpc_userdyn_s* u);
+
 int pmpc_destroy(pmpc_handle_t h) {
   if (!h) return PMPC_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  userdyn_free(h->user);
+  cudaEventDestroy(h->uev0); cudaEventDestroy(h->uev1);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
   cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw);
   for (int r = 0; r < 8; ++r)
@@ -630,6 +642,8 @@ int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double* params, size_t np
     pb.dyn_kind = DYN_DUBINS;
     pb.dyn_eps = eps;
     h->have_dyn = true;
+    userdyn_free(h->user);
+    h->user = nullptr;
     return PMPC_OK;
   }
   return fail(PMPC_ERR_BAD_ARG, "unknown dynamics kind (use pmpc_set_linearization / pmpc_set_ltv for AFFINE)");
@@ -658,6 +672,8 @@ static int set_affine(pmpc_handle_t h, const double* f, const double* fx, const 
   CU(cudaStreamSynchronize(h->stream));
   pb.dyn_kind = DYN_AFFINE;
   h->have_dyn = true;
+  userdyn_free(h->user);
+  h->user = nullptr;
   return PMPC_OK;
 }
 
@@ -670,9 +686,16 @@ int pmpc_set_ltv(pmpc_handle_t h, const double* A, const double* Bm, const doubl
   return set_affine(h, c, A, Bm, 1);
 }
 
+static int userdyn_launch_lin(pmpc_handle_t h, bool want_ref_layout, const int* done);
+static int userdyn_scp(pmpc_handle_t h, int max_it, double res_tol);
+
 int pmpc_linearize(pmpc_handle_t h) {
   if (!h || !h->have_problem || !h->have_dyn) return fail(PMPC_ERR_STATE, "set problem and dynamics first");
-  if (h->pb.dyn_kind != DYN_DUBINS) return fail(PMPC_ERR_STATE, "pmpc_linearize needs built-in dynamics");
+  if (h->user) {
+    CU(cudaSetDevice(h->device));
+    return userdyn_launch_lin(h, true, nullptr);
+  }
+  if (h->pb.dyn_kind != DYN_DUBINS) return fail(PMPC_ERR_STATE, "pmpc_linearize needs built-in or registered dynamics");
   CU(cudaSetDevice(h->device));
   linearize_dubins_kernel<<<nblk(h->Ptot * h->pb.N), 256, 0, h->stream>>>(h->pb, h->lin_f, h->lin_fx, h->lin_fu,
                                                                            (int)h->Ptot, h->row_major);
@@ -730,6 +753,8 @@ int pmpc_scp_solve_async(pmpc_handle_t h, int max_it, double res_tol) {
   if (!h || !h->have_problem || !h->have_dyn) return fail(PMPC_ERR_STATE, "set problem and dynamics first");
   if (max_it < 1) return fail(PMPC_ERR_BAD_ARG, "max_it < 1");
   CU(cudaSetDevice(h->device));
+  h->user_timed = false;
+  if (h->user) return userdyn_scp(h, max_it, res_tol);  // host-driven loop: synchronous
   h->pb.max_it = max_it;
   h->pb.res_tol = res_tol;
   h->pb.keep_prev = 0;
@@ -743,7 +768,7 @@ int pmpc_sync(pmpc_handle_t h) {
   if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
-  if (h->solved) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  if (h->solved && !h->user_timed) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   return PMPC_OK;
 }
 
@@ -762,6 +787,11 @@ int pmpc_qp_solve(pmpc_handle_t h, int keep_prev) {
   h->pb.max_it = 1;
   h->pb.res_tol = -1.0;
   h->pb.keep_prev = keep_prev;
+  h->user_timed = false;
+  if (h->user) {  // registered dynamics: the sub-problem is the one at the handle's (X_prev, U_prev)
+    int rl = userdyn_launch_lin(h, false, nullptr);
+    if (rl) return rl;
+  }
   int rc = launch(h);
   h->pb.dyn_kind = kind;
   if (rc) return rc;
@@ -873,6 +903,8 @@ int pmpc_comm_connect(pmpc_handle_t h, int rank, int world, const void* ipc_hand
 }
 
 long long pmpc_launch_count(void) { return g_launches.load(); }
+
+#include "userdyn.inl"
 
 int pmpc_get_occupancy(pmpc_handle_t h, int* ctas_per_sm, int* num_sms) {
   if (!h || !ctas_per_sm || !num_sms) return fail(PMPC_ERR_BAD_ARG, "null");

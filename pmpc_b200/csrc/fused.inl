@@ -21,7 +21,10 @@
   // ADMM (active-set iteration stalls, or a state bound active) falls back to the unfused path.
   // =============================================================================================
   static constexpr bool RING_SHAPE = (NX <= 4);
-  static constexpr int DEPTH = 3;
+#ifndef PMPC_DEPTH
+#define PMPC_DEPTH 3
+#endif
+  static constexpr int DEPTH = PMPC_DEPTH;
   // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | (L) | act]
   static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_K = R_UP + NU * 32, R_KF = R_K + NU * NX * 32,
                        R_H = R_KF + NU * 32, R_LIN = R_H + NR * 32, R_ACTF = R_LIN + ((NX == 4 && NU == 2) ? 14 * 32 : 0),
@@ -51,9 +54,17 @@
   }
 
   // element 0 of the warp's stage-j block of an E-element array (no lane offset): bulk-copy source
+  // wb = (g >> 5) * N: first stage block of this warp's particle tile
   template <typename Tp>
-  __device__ __forceinline__ const Tp* blk(const Tp* a, int j, int E) const {
-    return a + (((size_t)(g >> 5) * (size_t)N + (size_t)j) * (size_t)E) * 32;
+  __device__ __forceinline__ static const Tp* blk(const Tp* a, int j, int E, size_t wb) {
+    return a + ((wb + (size_t)j) * (size_t)E) * 32;
+  }
+  // warp-tile SoA index from sweep-local invariants (wb as above, col = g & 31).  The sweeps use these
+  // instead of ix()/ld()/at(): the Solver object lives in local memory (it escapes into the noinline
+  // helpers), and every asm volatile "memory" clobber of the ring protocol would force its members to be
+  // re-read from there (LDL + long-scoreboard stall) at each use.
+  __device__ __forceinline__ static size_t ixw(size_t wb, int col, int j, int E, int e) {
+    return ((wb + (size_t)j) * (size_t)E + (size_t)e) * 32 + (size_t)col;
   }
 
   // dynamic shared memory: [table][ring of every warp][mbarriers of every warp]
@@ -100,21 +111,22 @@
   }
 
   // one field (E doubles at table offset `off`) of the stage's cost / reference / bound data
-  __device__ __forceinline__ void cost_field(const double* tab, int j, int off, int E, const double* arr, double* out) const {
+  __device__ __forceinline__ static void cost_field(const double* tab, int j, int off, int E, const double* arr, double* out,
+                                                    size_t wb, int col) {
     if (tab != nullptr) {
       const double* t = tab + j * TW + off;
 #pragma unroll UNR
       for (int e = 0; e < E; ++e) out[e] = t[e];
     } else {
 #pragma unroll UNR
-      for (int e = 0; e < E; ++e) out[e] = ld(arr, j, E, e);
+      for (int e = 0; e < E; ++e) out[e] = arr[ixw(wb, col, j, E, e)];
     }
   }
 
   // x_j = A x_{j-1} + B u_j + c about (xm1 = X_[j], ub = U_prev[j]); A_0 = 0 (lqp_utils.jl:288-296)
   template <bool DUB>
-  __device__ __forceinline__ void lin_stage(const DevProb& pb, int j, const double* xm1, const double* ub, const double* dp, double* A,
-                                            double* Bm, double* c) const {
+  __device__ __forceinline__ static void lin_stage(const DevProb& pb, int j, const double* xm1, const double* ub, const double* dp,
+                                                   double* A, double* Bm, double* c, size_t wb, int col) {
     if constexpr (DUB && NX == 4 && NU == 2) {
       double f[4], fx[16], fu[8];
       dubins_f_fx_fu(xm1, ub, dp[0], dp[1], dp[2], pb.dyn_eps, f, fx, fu);
@@ -135,11 +147,11 @@
       for (int e = 0; e < 8; ++e) Bm[e] = fu[e];
     } else {
 #pragma unroll UNR
-      for (int e = 0; e < NX * NX; ++e) A[e] = ld(pb.A, j, NX * NX, e);
+      for (int e = 0; e < NX * NX; ++e) A[e] = pb.A[ixw(wb, col, j, NX * NX, e)];
 #pragma unroll UNR
-      for (int e = 0; e < NX * NU; ++e) Bm[e] = ld(pb.Bm, j, NX * NU, e);
+      for (int e = 0; e < NX * NU; ++e) Bm[e] = pb.Bm[ixw(wb, col, j, NX * NU, e)];
 #pragma unroll UNR
-      for (int e = 0; e < NX; ++e) c[e] = ld(pb.c, j, NX, e);
+      for (int e = 0; e < NX; ++e) c[e] = pb.c[ixw(wb, col, j, NX, e)];
     }
   }
 
@@ -152,8 +164,8 @@
   // evaluate the dynamics again.  Stage 0 has A = 0 (lqp_utils.jl:288-296): its n-entries are unused.
   static constexpr int NLIN = 14;
   static constexpr bool CAN_SPARSE = (NX == 4 && NU == 2);
-  __device__ __forceinline__ void lin_sparse(const DevProb& pb, int j, const double* xm1, const double* ub,
-                                             const double* dp, double* L) const {
+  __device__ __forceinline__ static void lin_sparse(const DevProb& pb, int j, const double* xm1, const double* ub,
+                                                    const double* dp, double* L) {
     if constexpr (CAN_SPARSE) {
       double f[4], fx[16], fu[8];
       dubins_f_fx_fu(xm1, ub, dp[0], dp[1], dp[2], pb.dyn_eps, f, fx, fu);
@@ -171,7 +183,7 @@
     }
   }
   // dense (A, B, c) of a sparse stage, for the shared stages the consensus step reads
-  __device__ __forceinline__ void lin_expand(int j, const double* L, double* A, double* Bm, double* c) const {
+  __device__ __forceinline__ static void lin_expand(int j, const double* L, double* A, double* Bm, double* c) {
     if constexpr (CAN_SPARSE) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) A[e] = 0.0;
@@ -238,34 +250,36 @@
 
   // lane 0: stream the backward-sweep inputs of stage jj into ring slot `sl`
   template <bool UBOX>
-  __device__ __forceinline__ void issue_b(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl) {
+  __device__ __forceinline__ static void issue_b(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl,
+                                                 size_t wb) {
     double* dst = sm.ring + sl * SLOT;
     uint64_t* bar = sm.bars + sl;
     uint32_t bytes = NU * 256;
     if (jj >= 1) bytes += NX * 256;
     if (UBOX) bytes += NU * 32;
     mbar_expect_tx(bar, bytes);
-    if (jj >= 1) bulk_g2s(dst + R_XP, blk(Xpv, jj - 1, NX), NX * 256, bar);
-    bulk_g2s(dst + R_UP, blk(Upv, jj, NU), NU * 256, bar);
-    if (UBOX) bulk_g2s(dst + R_ACTB, blk(pb.act, jj, NU), NU * 32, bar);
+    if (jj >= 1) bulk_g2s(dst + R_XP, blk(Xpv, jj - 1, NX, wb), NX * 256, bar);
+    bulk_g2s(dst + R_UP, blk(Upv, jj, NU, wb), NU * 256, bar);
+    if (UBOX) bulk_g2s(dst + R_ACTB, blk(pb.act, jj, NU, wb), NU * 32, bar);
   }
   template <bool UBOX, bool SPD = false>
-  __device__ __forceinline__ void issue_f(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl) {
+  __device__ __forceinline__ static void issue_f(const DevProb& pb, const Sm& sm, const double* Xpv, const double* Upv, int jj, int sl,
+                                                 size_t wb, int Nc) {
     double* dst = sm.ring + sl * SLOT;
     uint64_t* bar = sm.bars + sl;
     const FactorSet& F = pb.fs[MODE_POLISH];
     uint32_t bytes = (NX + NU) * 256 + (SPD ? NLIN * 256 : 0);
     if (jj >= Nc) bytes += (NU * NX + NU) * 256 + (UBOX ? NR * 256 + NU * 32 : 0);
     mbar_expect_tx(bar, bytes);
-    bulk_g2s(dst + R_XP, blk(Xpv, jj, NX), NX * 256, bar);
-    bulk_g2s(dst + R_UP, blk(Upv, jj, NU), NU * 256, bar);
-    if (SPD) bulk_g2s(dst + R_LIN, blk(pb.lin, jj, NLIN), NLIN * 256, bar);
+    bulk_g2s(dst + R_XP, blk(Xpv, jj, NX, wb), NX * 256, bar);
+    bulk_g2s(dst + R_UP, blk(Upv, jj, NU, wb), NU * 256, bar);
+    if (SPD) bulk_g2s(dst + R_LIN, blk(pb.lin, jj, NLIN, wb), NLIN * 256, bar);
     if (jj >= Nc) {
-      bulk_g2s(dst + R_K, blk(F.K, jj, NU * NX), NU * NX * 256, bar);
-      bulk_g2s(dst + R_KF, blk(pb.kff, jj, NU), NU * 256, bar);
+      bulk_g2s(dst + R_K, blk(F.K, jj, NU * NX, wb), NU * NX * 256, bar);
+      bulk_g2s(dst + R_KF, blk(pb.kff, jj, NU, wb), NU * 256, bar);
       if (UBOX) {
-        bulk_g2s(dst + R_H, blk(pb.Hs, jj, NR), NR * 256, bar);
-        bulk_g2s(dst + R_ACTF, blk(pb.act, jj, NU), NU * 32, bar);
+        bulk_g2s(dst + R_H, blk(pb.Hs, jj, NR, wb), NR * 256, bar);
+        bulk_g2s(dst + R_ACTF, blk(pb.act, jj, NU, wb), NU * 32, bar);
       }
     }
   }
@@ -276,6 +290,18 @@
   template <bool SLEW, bool UBOX, bool DUB, int ALG = 0>
   __device__ __forceinline__ void bsweep(const DevProb& pb, unsigned char* smem, bool first, double* pc, double* zc,
                                          const Ipm ip = Ipm()) {
+    // sweep-local copies of the per-thread invariants (see ixw): registers instead of local-memory reloads
+    const int N = this->N, Nc = this->Nc, g = this->g, lane = this->lane, col = this->col;
+    const size_t P = this->P;
+    const bool valid = this->valid, flip = this->flip;
+    const double s = this->s;
+    const size_t wb = (size_t)(g >> 5) * (size_t)N;
+    uint32_t rcount = this->rcount;
+    auto ix = [=](int j, int E, int e) -> size_t { return ixw(wb, col, j, E, e); };
+    auto ld = [=](const double* a, int j, int E, int e) -> double { return a[ixw(wb, col, j, E, e)]; };
+    auto at = [=](double* a, int j, int E, int e) -> double& { return a[ixw(wb, col, j, E, e)]; };
+    auto ldp = [=](const double* a, int e) -> double { return a[(size_t)e * P + g]; };
+    (void)ix; (void)ld; (void)at; (void)ldp; (void)s; (void)lane;
     const FactorSet& F = pb.fs[MODE_POLISH];
     const Sm sm = smem_view(pb, smem);
     const bool use_ring = RING_SHAPE && sm.ring != nullptr;
@@ -304,7 +330,7 @@
       __syncwarp();
       if (lane == 0) {
         for (int d = 0; d < DEPTH; ++d)
-          if (N - 1 - d >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, N - 1 - d, (rcount + d) % DEPTH);
+          if (N - 1 - d >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, N - 1 - d, (rcount + d) % DEPTH, wb);
       }
     }
 #pragma unroll UNR
@@ -325,8 +351,8 @@
       // ---- stage inputs
       double xm1[NX], ub[NU];
       signed char act[NU];
+      const int sl = rcount % DEPTH;  // ring slot of this stage; refilled at the END of the iteration (see below)
       if (use_ring) {
-        const int sl = rcount % DEPTH;
         mbar_wait(sm.bars + sl, (rcount / DEPTH) & 1);
         const double* b = sm.ring + sl * SLOT + col;
 #pragma unroll UNR
@@ -338,8 +364,6 @@
 #pragma unroll UNR
           for (int t = 0; t < NU; ++t) act[t] = (j >= Nc && ALG == 0) ? ab[t * 32] : 0;
         }
-        __syncwarp();
-        if (lane == 0 && j - DEPTH >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, j - DEPTH, sl);
         ++rcount;
       } else {
 #pragma unroll UNR
@@ -363,12 +387,12 @@
         for (int e = 0; e < NX; ++e) cv[e] = L[10 + e];
         if (j < Nc) lin_expand(j, L, A, Bm, cv);
       } else {
-        lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
+        lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv, wb, col);
       }
       // proximal / reference linear terms (lqp_utils.jl:164-214)
       double q[NX], r[NU];
-      cost_field(sm.tab, j, T_QR, NX, pb.qref, q);
-      cost_field(sm.tab, j, T_RR, NU, pb.rref, r);
+      cost_field(sm.tab, j, T_QR, NX, pb.qref, q, wb, col);
+      cost_field(sm.tab, j, T_RR, NU, pb.rref, r, wb, col);
 #pragma unroll UNR
       for (int e = 0; e < NX; ++e) q[e] = -q[e] - pb.reg_x * xq[e];
 #pragma unroll UNR
@@ -379,8 +403,8 @@
       if (ALG == 1 && j >= Nc) {
         // interior point: (lazily) updated iterate, barrier diagonal and linear term of this stage
         double lo[NU], hi[NU];
-        cost_field(sm.tab, j, T_LU, NU, pb.lu, lo);
-        cost_field(sm.tab, j, T_UU, NU, pb.uu, hi);
+        cost_field(sm.tab, j, T_LU, NU, pb.lu, lo, wb, col);
+        cost_field(sm.tab, j, T_UU, NU, pb.uu, hi, wb, col);
         const double* Unew = flip ? pb.Up : pb.U;  // u+ of the previous interior-point iteration (fsweep's Uc)
 #pragma unroll UNR
         for (int a = 0; a < NU; ++a) {
@@ -401,7 +425,7 @@
       if (j >= Nc) {
         // ---- Riccati step with the stage's active set.  S = Qs + P (symmetric, packed)
         double S[NQ];
-        cost_field(sm.tab, j, T_QS, NQ, pb.Qs, S);
+        cost_field(sm.tab, j, T_QS, NQ, pb.Qs, S, wb, col);
 #pragma unroll UNR
         for (int e = 0; e < NQ; ++e) S[e] += Pm[e];
         // wv = S c + q + p
@@ -438,7 +462,7 @@
         double H[NU * NU], h0[NU];
         if constexpr (SPD) {
           double Rp[NR];
-          cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
+          cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp, wb, col);
           H[0] = Rp[0] + (ALG == 1 ? sig[0] : 0.0) + L[4] * SBW[0] + L[6] * SBW[2] + L[8] * SBW[4];
           H[1] = H[2] = Rp[1] + L[4] * SBW[1] + L[6] * SBW[3] + L[8] * SBW[5];
           H[3] = Rp[2] + (ALG == 1 ? sig[1] : 0.0) + L[5] * SBW[1] + L[7] * SBW[3] + L[9] * SBW[7];
@@ -446,7 +470,7 @@
           h0[1] = r[1] + L[5] * wv[0] + L[7] * wv[1] + L[9] * wv[3];
         } else {
           double Rp[NR];
-          cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
+          cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp, wb, col);
 #pragma unroll UNR
           for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
@@ -485,8 +509,8 @@
         }
         if (UBOX) {
           double lo[NU], hi[NU];
-          cost_field(sm.tab, j, T_LU, NU, pb.lu, lo);
-          cost_field(sm.tab, j, T_UU, NU, pb.uu, hi);
+          cost_field(sm.tab, j, T_LU, NU, pb.lu, lo, wb, col);
+          cost_field(sm.tab, j, T_UU, NU, pb.uu, hi, wb, col);
 #pragma unroll UNR
           for (int t = 0; t < NU; ++t) {
             fixed[t] = act[t] != 0;
@@ -687,8 +711,18 @@
       }
 #pragma unroll UNR
       for (int e = 0; e < NX; ++e) xq[e] = xm1[e];
+      // Refill the slot only now: the bulk copy (async proxy) overwrites shared memory the lanes read with
+      // plain LDS above, and a converged __syncwarp does not wait for outstanding LDS to complete.  At
+      // this point every loaded value has been consumed, so the write-after-read hazard is closed by
+      // data dependence (issuing right after the loads raced once the LSU queue was backed up by the
+      // stage's global stores).  The prefetch distance is still DEPTH - 1 full stages.
+      if (use_ring) {
+        __syncwarp();
+        if (lane == 0 && j - DEPTH >= jmin) issue_b<UBOX>(pb, sm, Xpv, Upv, j - DEPTH, sl, wb);
+      }
     }
     if (use_ring) fence_proxy_async();  // K, k, H written above are bulk-copied by the next sweep
+    this->rcount = rcount;
   }
 
   // Forward sweep: rollout of the feedback policy, multipliers + primal-dual active-set update of the
@@ -696,6 +730,18 @@
   template <bool SLEW, bool UBOX, bool DUB, int ALG = 0>
   __device__ __forceinline__ void fsweep(const DevProb& pb, unsigned char* smem, double* st, const Ipm ip = Ipm(),
                                          double* ipacc = nullptr) {
+    // sweep-local copies of the per-thread invariants (see ixw): registers instead of local-memory reloads
+    const int N = this->N, Nc = this->Nc, g = this->g, lane = this->lane, col = this->col;
+    const size_t P = this->P;
+    const bool valid = this->valid, flip = this->flip;
+    const double s = this->s;
+    const size_t wb = (size_t)(g >> 5) * (size_t)N;
+    uint32_t rcount = this->rcount;
+    auto ix = [=](int j, int E, int e) -> size_t { return ixw(wb, col, j, E, e); };
+    auto ld = [=](const double* a, int j, int E, int e) -> double { return a[ixw(wb, col, j, E, e)]; };
+    auto at = [=](double* a, int j, int E, int e) -> double& { return a[ixw(wb, col, j, E, e)]; };
+    auto ldp = [=](const double* a, int e) -> double { return a[(size_t)e * P + g]; };
+    (void)ix; (void)ld; (void)at; (void)ldp; (void)s; (void)lane;
     const FactorSet& F = pb.fs[MODE_POLISH];
     const Sm sm = smem_view(pb, smem);
     const bool use_ring = RING_SHAPE && sm.ring != nullptr;
@@ -712,7 +758,7 @@
       __syncwarp();
       if (lane == 0) {
         for (int d = 0; d < DEPTH; ++d)
-          if (d < N) issue_f<UBOX, SPD>(pb, sm, Xpv, Upv, d, (rcount + d) % DEPTH);
+          if (d < N) issue_f<UBOX, SPD>(pb, sm, Xpv, Upv, d, (rcount + d) % DEPTH, wb, Nc);
       }
     }
     const double* uc = (GROUPED && Nc >= 1) ? pb.uc + (size_t)prob * D : nullptr;
@@ -729,8 +775,8 @@
       signed char act[NU];
 #pragma unroll UNR
       for (int t = 0; t < NU; ++t) act[t] = 0;
+      const int sl = rcount % DEPTH;  // refilled at the end of the iteration (write-after-read, see bsweep)
       if (use_ring) {
-        const int sl = rcount % DEPTH;
         mbar_wait(sm.bars + sl, (rcount / DEPTH) & 1);
         const double* b = sm.ring + sl * SLOT + col;
 #pragma unroll UNR
@@ -754,8 +800,6 @@
             for (int t = 0; t < NU; ++t) act[t] = (ALG == 0) ? ab[t * 32] : 0;
           }
         }
-        __syncwarp();
-        if (lane == 0 && j + DEPTH < N) issue_f<UBOX, SPD>(pb, sm, Xpv, Upv, j + DEPTH, sl);
         ++rcount;
       } else {
 #pragma unroll UNR
@@ -781,8 +825,8 @@
       }
       double lo[NU], hi[NU];
       if (UBOX) {
-        cost_field(sm.tab, j, T_LU, NU, pb.lu, lo);
-        cost_field(sm.tab, j, T_UU, NU, pb.uu, hi);
+        cost_field(sm.tab, j, T_LU, NU, pb.lu, lo, wb, col);
+        cost_field(sm.tab, j, T_UU, NU, pb.uu, hi, wb, col);
       }
       if (j < Nc) {
 #pragma unroll UNR
@@ -861,7 +905,7 @@
         }
       } else {
         double A[NX * NX], Bm[NX * NU], cv[NX];
-        lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv);
+        lin_stage<DUB>(pb, j, xm1, ub, dp, A, Bm, cv, wb, col);
 #pragma unroll UNR
         for (int r = 0; r < NX; ++r) {
           double acc = cv[r];
@@ -886,12 +930,12 @@
       }
       // bookkeeping (scp_mpc.py:397-405) and the scales of the acceptance test
       double Qp[NQ], Rp[NR], xr[NX], ur[NU], qr[NX], rr_[NU];
-      cost_field(sm.tab, j, T_QS, NQ, pb.Qs, Qp);
-      cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp);
-      cost_field(sm.tab, j, T_XR, NX, pb.xref, xr);
-      cost_field(sm.tab, j, T_UR, NU, pb.uref, ur);
-      cost_field(sm.tab, j, T_QR, NX, pb.qref, qr);
-      cost_field(sm.tab, j, T_RR, NU, pb.rref, rr_);
+      cost_field(sm.tab, j, T_QS, NQ, pb.Qs, Qp, wb, col);
+      cost_field(sm.tab, j, T_RS, NR, pb.Rs, Rp, wb, col);
+      cost_field(sm.tab, j, T_XR, NX, pb.xref, xr, wb, col);
+      cost_field(sm.tab, j, T_UR, NU, pb.uref, ur, wb, col);
+      cost_field(sm.tab, j, T_QR, NX, pb.qref, qr, wb, col);
+      cost_field(sm.tab, j, T_RR, NU, pb.rref, rr_, wb, col);
       double dx[NX], du[NU], n2 = 0.0;
 #pragma unroll UNR
       for (int r = 0; r < NX; ++r) {
@@ -932,8 +976,13 @@
       for (int r = 0; r < NX; ++r) { x[r] = xn[r]; xm1[r] = xpj[r]; }
 #pragma unroll UNR
       for (int a = 0; a < NU; ++a) up[a] = u[a];
+      if (use_ring) {
+        __syncwarp();
+        if (lane == 0 && j + DEPTH < N) issue_f<UBOX, SPD>(pb, sm, Xpv, Upv, j + DEPTH, sl, wb, Nc);
+      }
     }
     if (use_ring) fence_proxy_async();  // X, U, act written above are bulk-copied by the next sweep
+    this->rcount = rcount;
     st[ST_DX] = valid ? dxm : 0.0;
     st[ST_DU] = valid ? dum : 0.0;
     st[ST_OBJ] = valid ? obj : 0.0;

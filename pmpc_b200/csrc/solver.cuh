@@ -69,6 +69,7 @@ struct DevProb {
   const int* uniform;
   // run parameters
   int max_it, keep_prev;
+  int hist_off;               // first hist row of this launch (host-driven SCP loop: one iteration per launch)
   double res_tol;
   // particle sharding of ONE consensus problem over the GPUs of a node (SURVEY.md 8e case 2): this rank
   // holds M of the M_total particles; the Nc*m consensus terms and the pass statistics are exchanged
@@ -1397,13 +1398,14 @@ struct Solver {
       }
       const double max_res = fmax(st[ST_DX], st[ST_DU]);
       const double obj = st[ST_OBJ] / ((double)N * (double)(pb.world > 1 ? pb.M_total : pb.M));
-      if (writer && it < pb.hist_len) {
+      const int hrow = it + pb.hist_off;
+      if (writer && hrow < pb.hist_len) {
         double* h = pb.hist;
         const size_t Bn = (size_t)pb.B;
-        h[((size_t)0 * pb.hist_len + it) * Bn + prob] = obj;
-        h[((size_t)1 * pb.hist_len + it) * Bn + prob] = max_res;
-        h[((size_t)2 * pb.hist_len + it) * Bn + prob] = (double)(cnt[1] - admm0);
-        h[((size_t)3 * pb.hist_len + it) * Bn + prob] = kkt_rel;
+        h[((size_t)0 * pb.hist_len + hrow) * Bn + prob] = obj;
+        h[((size_t)1 * pb.hist_len + hrow) * Bn + prob] = max_res;
+        h[((size_t)2 * pb.hist_len + hrow) * Bn + prob] = (double)(cnt[1] - admm0);
+        h[((size_t)3 * pb.hist_len + hrow) * Bn + prob] = kkt_rel;
       }
       if (max_res < pb.res_tol) {
         ++it;

@@ -51,6 +51,50 @@ class DubinsCar(BuiltinDynamics):
         return (f[0], fx[0], fu[0]) if single else (f, fx, fu)
 
 
+class UserDynamics(BuiltinDynamics):
+    """User device dynamics: CUDA C++ source of one ``__device__`` function
+
+        __device__ void NAME(const double* x, const double* u, const double* p, double* f, double* fx, double* fu)
+
+    (``x`` the state ``u`` is applied to, ``p`` this particle's parameters; writes the next state ``f``, row-major
+    ``fx[r*xdim+t] = df_r/dx_t`` and ``fu[r*udim+t] = df_r/du_t``).  It replaces the Python ``f_fx_fu_fn`` callable of
+    the reference (``pmpc/scp_mpc.py:338-342``): the library compiles it with NVRTC for sm_100a
+    (``pmpc_register_dynamics``) and the whole SCP loop stays on the device.  An instance is also callable like an
+    ordinary ``f_fx_fu_fn`` (it runs the compiled linearisation kernel), so it works in the host loop too.
+    ``params``: ``(P,)`` or ``(M, P)`` per-particle parameters, or None."""
+
+    kind = "user"
+
+    def __init__(self, cuda_src: str, fn_name: str, xdim: int, udim: int, params=None):
+        self.src, self.fn_name, self.xdim, self.udim = cuda_src, fn_name, int(xdim), int(udim)
+        self.params = None if params is None else np.asarray(params, dtype=np.float64)
+        self._solver = None
+
+    def params_for(self, M: int):
+        if self.params is None:
+            return None
+        return np.ascontiguousarray(np.broadcast_to(self.params, (M, self.params.shape[-1])))
+
+    def __call__(self, X, U):
+        from .handle import DeviceSolver
+
+        X, U = np.asarray(X, np.float64), np.asarray(U, np.float64)
+        single = X.ndim == 2
+        if single:
+            X, U = X[None], U[None]
+        M, N = X.shape[:2]
+        n, m = self.xdim, self.udim
+        s = self._solver
+        if s is None or (s.M, s.N) != (M, N):
+            s = self._solver = DeviceSolver(M, N, n, m, 0)
+            s.register_dynamics(self.src, self.fn_name, self.params_for(M))
+        eye_n, eye_m = np.broadcast_to(np.eye(n), (M, N, n, n)), np.broadcast_to(np.eye(m), (M, N, m, m))
+        s.set_problem(X[:, 0], eye_n, eye_m)
+        s.set_warm_start(np.concatenate([X[:, 1:], X[:, -1:]], 1), U)
+        f, fx, fu = s.linearize()
+        return (f[0], fx[0], fu[0]) if single else (f, fx, fu)
+
+
 class LTV(BuiltinDynamics):
     """x+ = A_j x + B_j u + c_j with per-(particle, stage) matrices ``A (M,N,n,n)``, ``B (M,N,n,m)``,
     ``c (M,N,n)`` or None.  Linear, so its linearisation is itself."""

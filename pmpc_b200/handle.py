@@ -106,16 +106,35 @@ class DeviceSolver:
         p = np.asarray(p, dtype=np.float64)
         p = np.ascontiguousarray(np.broadcast_to(p, (self.B, self.M, 3)) if p.ndim < 3 else p).reshape(self.B * self.M, 3)
         check(self.lib.pmpc_set_dynamics(self._h, 1, dptr(p), 3, float(eps)), "set_dynamics")
+        self._user_key = None
+
+    def register_dynamics(self, cuda_src: str, fn_name: str, params=None):
+        """User device dynamics (`pmpc_register_dynamics`): CUDA C++ source of
+        ``__device__ void fn_name(const double* x, const double* u, const double* p, double* f, double* fx, double* fu)``
+        compiled with NVRTC; ``params``: per-particle parameters ``(P,) | (M,P) | (B,M,P)`` or None."""
+        if params is None:
+            pp, npar = None, 0
+        else:
+            pp = np.asarray(params, dtype=np.float64)
+            npar = pp.shape[-1]
+            pp = np.ascontiguousarray(np.broadcast_to(pp, (self.B, self.M, npar)) if pp.ndim < 3 else pp).reshape(self.B * self.M, npar)
+        key = (cuda_src, fn_name, None if pp is None else pp.tobytes())
+        if getattr(self, "_user_key", None) == key:
+            return  # already compiled and loaded for exactly these parameters (NVRTC costs ~0.3 s)
+        check(self.lib.pmpc_register_dynamics(self._h, cuda_src.encode(), fn_name.encode(), dptr(pp), npar), "register_dynamics")
+        self._user_key = key
 
     def set_linearization(self, f, fx, fu):
         n, m = self.n, self.m
         a, b, c = self._vec(f, n), self._mat(fx, n, n), self._mat(fu, n, m)
         check(self.lib.pmpc_set_linearization(self._h, dptr(a), dptr(b), dptr(c)), "set_linearization")
+        self._user_key = None
 
     def set_ltv(self, A, Bm, c=None):
         n, m = self.n, self.m
         a, b, cc = self._mat(A, n, n), self._mat(Bm, n, m), self._vec(c, n)
         check(self.lib.pmpc_set_ltv(self._h, dptr(a), dptr(b), dptr(cc)), "set_ltv")
+        self._user_key = None
 
     # -- compute -------------------------------------------------------------------------------
     def linearize(self):

@@ -21,7 +21,7 @@ from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .dynamics import BuiltinDynamics, DubinsCar, LTV
+from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics
 from .handle import DeviceSolver
 from .static_backend import aff_solve
 from .utils import TablePrinter, atleast_nd
@@ -143,6 +143,8 @@ def _device_scp(dyn, dims, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l
         shp = (M, N)
         ds.set_ltv(np.broadcast_to(dyn.A, shp + dyn.A.shape[-2:]), np.broadcast_to(dyn.B, shp + dyn.B.shape[-2:]),
                    None if dyn.c is None else np.broadcast_to(dyn.c, shp + (xdim,)))
+    elif isinstance(dyn, UserDynamics):
+        ds.register_dynamics(dyn.src, dyn.fn_name, dyn.params_for(M))
     else:
         raise TypeError(f"no device implementation for {type(dyn).__name__}")
     t_k = time.time()

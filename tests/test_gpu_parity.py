@@ -300,3 +300,132 @@ def test_particle_sharded_consensus_two_gpus(gpu, tmp_path):
         assert v["status"] == 0 and v["consensus"], (name, v)
         assert v["scp_iters"] == v["scp_iters_single"], (name, v)
         assert v["err_X"] < 1e-8 and v["err_U"] < 1e-8, (name, v)
+
+
+# ---- user device dynamics (pmpc_register_dynamics: CUDA source compiled with NVRTC) ---------------------
+EULER_CAR_SRC = r"""
+// Euler-discretised unicycle: state (x, y, v, th), control (acc, turn), p = (a_scale, w_scale, T)
+__device__ void euler_car(const double* x, const double* u, const double* p, double* f, double* fx, double* fu) {
+  const double T = p[2], s = sin(x[3]), c = cos(x[3]);
+  f[0] = x[0] + T * x[2] * c;  f[1] = x[1] + T * x[2] * s;  f[2] = x[2] + T * p[0] * u[0];  f[3] = x[3] + T * p[1] * u[1];
+  fx[0 * 4 + 0] = 1.0; fx[0 * 4 + 2] = T * c; fx[0 * 4 + 3] = -T * x[2] * s;
+  fx[1 * 4 + 1] = 1.0; fx[1 * 4 + 2] = T * s; fx[1 * 4 + 3] = T * x[2] * c;
+  fx[2 * 4 + 2] = 1.0; fx[3 * 4 + 3] = 1.0;
+  fu[2 * 2 + 0] = T * p[0]; fu[3 * 2 + 1] = T * p[1];
+}
+"""
+PENDULUM_SRC = r"""
+// damped pendulum, semi-implicit Euler: state (th, w), control torque, no parameters
+__device__ void pend(const double* x, const double* u, const double* p, double* f, double* fx, double* fu) {
+  const double T = 0.1, w = x[1] + T * (-9.81 * sin(x[0]) - 0.2 * x[1] + 2.0 * u[0]);
+  f[0] = x[0] + T * w;  f[1] = w;
+  fx[1 * 2 + 0] = -T * 9.81 * cos(x[0]);  fx[1 * 2 + 1] = 1.0 - 0.2 * T;
+  fx[0 * 2 + 0] = 1.0 + T * fx[1 * 2 + 0];  fx[0 * 2 + 1] = T * fx[1 * 2 + 1];
+  fu[1] = 2.0 * T;  fu[0] = T * fu[1];
+}
+"""
+
+
+def _euler_car_np(p):
+    p = np.asarray(p, float)
+
+    def fn(X, U):
+        pp = p[:, None, :] if (p.ndim == 2 and X.ndim == 3) else p
+        a, w, T = pp[..., 0], pp[..., 1], pp[..., 2]
+        s, c = np.sin(X[..., 3]), np.cos(X[..., 3])
+        f = np.stack([X[..., 0] + T * X[..., 2] * c, X[..., 1] + T * X[..., 2] * s, X[..., 2] + T * a * U[..., 0],
+                      X[..., 3] + T * w * U[..., 1]], -1)
+        fx = np.zeros(X.shape + (4,)); fu = np.zeros(X.shape + (2,))
+        for k in range(4):
+            fx[..., k, k] = 1.0
+        fx[..., 0, 2], fx[..., 0, 3] = T * c, -T * X[..., 2] * s
+        fx[..., 1, 2], fx[..., 1, 3] = T * s, T * X[..., 2] * c
+        fu[..., 2, 0], fu[..., 3, 1] = T * a, T * w
+        return f, fx, fu
+
+    return fn
+
+
+def _pend_np(X, U):
+    T = 0.1
+    w = X[..., 1] + T * (-9.81 * np.sin(X[..., 0]) - 0.2 * X[..., 1] + 2.0 * U[..., 0])
+    f = np.stack([X[..., 0] + T * w, w], -1)
+    fx = np.zeros(X.shape + (2,)); fu = np.zeros(X.shape + (1,))
+    fx[..., 1, 0], fx[..., 1, 1] = -T * 9.81 * np.cos(X[..., 0]), 1.0 - 0.2 * T
+    fx[..., 0, 0], fx[..., 0, 1] = 1.0 + T * fx[..., 1, 0], T * fx[..., 1, 1]
+    fu[..., 1, 0] = 2.0 * T
+    fu[..., 0, 0] = T * fu[..., 1, 0]
+    return f, fx, fu
+
+
+def _euler_problem(M, N, seed, Nc=1):
+    rng = np.random.default_rng(seed)
+    p = np.stack([rng.uniform(0.8, 1.2, M), rng.uniform(0.8, 1.2, M), np.full(M, 0.2)], -1)
+    d = dict(Q=np.tile(np.eye(4), (M, N, 1, 1)), R=np.tile(0.05 * np.eye(2), (M, N, 1, 1)),
+             x0=np.tile(np.array([1.0, -0.5, 0.6, 0.3]) + 0.1 * rng.standard_normal(4), (M, 1)),
+             X_ref=np.zeros((M, N, 4)), U_ref=np.zeros((M, N, 2)), X_prev=np.zeros((M, N, 4)), U_prev=np.zeros((M, N, 2)),
+             u_l=-np.ones((M, N, 2)), u_u=np.ones((M, N, 2)), reg_x=1.0, reg_u=1e-2, max_it=80, res_tol=1e-7,
+             solver_settings=dict(solver="osqp", Nc=Nc))
+    return d, p
+
+
+def test_user_dynamics_linearisation_matches_numpy(gpu):
+    """The NVRTC-compiled user kernel (K1) against the same formulas in NumPy: 1e-12 relative (north_star)."""
+    rng = np.random.default_rng(5)
+    M, N = 5, 9
+    p = np.stack([rng.uniform(0.8, 1.2, M), rng.uniform(0.8, 1.2, M), np.full(M, 0.2)], -1)
+    X, U = rng.standard_normal((M, N, 4)), rng.standard_normal((M, N, 2))
+    f, fx, fu = pmpc_b200.UserDynamics(EULER_CAR_SRC, "euler_car", 4, 2, p)(X, U)
+    fo, fxo, fuo = _euler_car_np(p)(X, U)
+    assert rel(f, fo) < 1e-12 and rel(fx, fxo) < 1e-12 and rel(fu, fuo) < 1e-12
+    Xp, Up = rng.standard_normal((3, 7, 2)), rng.standard_normal((3, 7, 1))
+    f, fx, fu = pmpc_b200.UserDynamics(PENDULUM_SRC, "pend", 2, 1)(Xp, Up)
+    fo, fxo, fuo = _pend_np(Xp, Up)
+    assert rel(f, fo) < 1e-12 and rel(fx, fxo) < 1e-12 and rel(fu, fuo) < 1e-12
+
+
+def test_user_dynamics_scp_matches_oracle(gpu):
+    """Whole SCP solve with registered device dynamics (consensus, box) == oracle with the NumPy callable, and ==
+    the reference-style host loop that calls the same compiled kernel as an ordinary f_fx_fu_fn."""
+    d, p = _euler_problem(M=6, N=12, seed=11)
+    dyn = pmpc_b200.UserDynamics(EULER_CAR_SRC, "euler_car", 4, 2, p)
+    X, U, data = pmpc_b200.solve(dyn, **d)
+    kw = {k: d[k] for k in ("X_ref", "U_ref", "X_prev", "U_prev", "u_l", "u_u", "reg_x", "reg_u", "max_it", "res_tol")}
+    Xo, Uo, do = oscp.scp_solve(_euler_car_np(p), d["Q"], d["R"], d["x0"], solver_settings=d["solver_settings"], **kw)
+    assert len(data["hist"]) == len(do["hist"]) and data["hist"][-1]["resid"] < 1e-7
+    assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+    assert abs(data["hist"][-1]["obj"] - do["hist"][-1]["obj"]) <= 1e-6 * abs(do["hist"][-1]["obj"])
+    assert np.all(U[:, :1] == U[0:1, :1])
+    Xh, Uh, dh = pmpc_b200.solve(dyn, **dict(d, solver_settings=dict(d["solver_settings"], host_loop=True)))
+    assert rel(Xh, X) < 1e-9 and rel(Uh, U) < 1e-9 and len(dh["hist"]) == len(data["hist"])
+    # single particle, other shape (2 states, 1 control, no parameters)
+    N = 25
+    dp = dict(Q=np.tile(np.diag([4.0, 0.5]), (N, 1, 1)), R=np.tile(0.1 * np.eye(1), (N, 1, 1)), x0=np.array([2.5, 0.0]),
+              X_prev=np.zeros((N, 2)), U_prev=np.zeros((N, 1)), u_l=-np.ones((N, 1)), u_u=np.ones((N, 1)), max_it=100,
+              res_tol=1e-8, reg_x=1.0, reg_u=1e-1, solver_settings=dict(solver="osqp"))
+    X, U, data = pmpc_b200.solve(pmpc_b200.UserDynamics(PENDULUM_SRC, "pend", 2, 1), **dp)
+    Xo, Uo, do = oscp.scp_solve(_pend_np, **dp)
+    assert X.shape == (N + 1, 2) and len(data["hist"]) == len(do["hist"])
+    assert rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+
+
+def test_user_dynamics_batched_equals_individual_and_errors(gpu):
+    """B problems with registered dynamics in one handle (host-driven loop, converged problems frozen) == B separate
+    solves, although they stop after different numbers of iterations; a source that does not compile raises with the
+    NVRTC log."""
+    B = 5
+    probs = []
+    for b in range(B):
+        d, p = _euler_problem(M=4, N=10, seed=20 + b)
+        d["res_tol"] = 1e-6
+        d["x0"] = d["x0"] * (0.2 + 0.4 * b)   # different distances from the origin -> different iteration counts
+        probs.append(dict(d, f_fx_fu_fn=pmpc_b200.UserDynamics(EULER_CAR_SRC, "euler_car", 4, 2, p)))
+    res = pmpc_b200.solve_problems(probs)
+    its = [len(r[2]["hist"]) for r in res]
+    assert len(set(its)) > 1, its
+    for b in range(B):
+        X, U, data = pmpc_b200.solve(**probs[b])
+        assert rel(res[b][0], X) < 1e-12 and rel(res[b][1], U) < 1e-12 and len(data["hist"]) == its[b]
+    with pytest.raises(pmpc_b200.PmpcError, match="failed to compile"):
+        pmpc_b200.UserDynamics("__device__ void broken(const double* x) { undeclared = 1; }", "broken", 2, 1)(
+            np.zeros((1, 3, 2)), np.zeros((1, 3, 1)))
