@@ -16,8 +16,9 @@ SURVEY.md 8e case 1).
 `e2e`    : the same batch through the public API `pmpc_b200.solve_batch` with HOST arrays: H2D of
            every input, the solve, D2H of X, U and the per-problem counters, wall clock, max over ranks.
 `roofline`: the SCP kernel against the measured HBM bandwidth, algorithmic bytes per DESIGN.md.
-`cpu_baseline`: the reference algorithm restated (oracle/, OSQP port at the reference's default
-           settings) on ONE host core, bounded sample — reported beside, not the target.
+`cpu_baseline`: the reference algorithm restated in plain C (oracle/c: lqp_utils.jl assembly + OSQP 0.6.2 at the
+           reference's default settings), one problem per host thread on all cores, bounded sample —
+           reported beside, not the target.
 Only the cpu_baseline / --impl reference legs touch `oracle/`; the product path has no CPU fallback.
 """
 from __future__ import annotations
@@ -124,73 +125,77 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-# algorithmic work per (particle, stage), SURVEY.md 8(d) / DESIGN.md "roofline"
-def alg_bytes_flops(info, n=NX, m=NU, nparam=3):
-    """Streaming model: every (re)factorisation streams Q, fx, fu, R in and K, P-sized factors out; every
-    vector pass (ADMM iteration or polish solve) streams fx, fu, K, E and the stage vectors; every SCP
-    iteration streams the linearisation in/out once."""
+# algorithmic work per (particle, stage), DESIGN.md section 5
+def alg_bytes_flops(info, n=NX, m=NU, nlin=14):
+    """HBM bytes the fused two-sweep pass has to move per (particle, stage): the backward sweep reads X_prev, U_prev
+    and the active set and writes the hand-off [K | k | H | sparse stage]; the forward sweep reads X_prev, U_prev, the
+    hand-off and the active set and writes X, U and the active set.  Everything else (costs, bounds, P, S, G, the
+    Dubins linearisation) stays in registers / shared memory.  582 B at n=4, m=2.  Flops: the dense Riccati count of
+    SURVEY.md 8(d) (the sparse Dubins stage needs fewer; the figure is an upper bound on useful work)."""
+    passes = info["polish_passes"].astype(np.float64)
+    I = (info["admm_iters"] + info["polish_passes"]).astype(np.float64)
+    handoff = n * m + m + m * (m + 1) // 2 + nlin
+    b_pass = 8 * (3 * (n + m) + 2 * handoff) + 3 * m
+    f_fac = 4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0
+    f_vec = 6 * n * n + 8 * n * m + 2 * m * m
+    per = M * N
+    return float(per * (passes * b_pass).sum()), float(per * (passes * f_fac + I * f_vec).sum())
+
+
+def survey_streaming_bytes(info, n=NX, m=NU, nparam=3):
+    """SURVEY.md 8(d)'s *streaming* model (every factorisation streams Q, fx, fu, R in and K, P out; every vector pass
+    streams fx, fu, K and the stage vectors; every SCP iteration streams the linearisation once) — what an unfused
+    implementation would move.  Reported beside the roofline as the traffic the fusion removed."""
     F = info["factorizations"].astype(np.float64)
     I = (info["admm_iters"] + info["polish_passes"]).astype(np.float64)
     S = info["scp_iters"].astype(np.float64)
     b_fac = 8 * (3 * n * n + 2 * n * m + m * m)
     b_vec = 8 * (n * n + 2 * n * m + m * m) + 16 * (n + m)
     b_lin = 8 * (n + m + nparam) + 8 * (n + n * n + n * m)
-    f_fac = 4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0
-    f_vec = 6 * n * n + 8 * n * m + 2 * m * m
-    per = M * N
-    return float(per * (F * b_fac + I * b_vec + S * b_lin).sum()), float(per * (F * f_fac + I * f_vec).sum())
+    return float(M * N * (F * b_fac + I * b_vec + S * b_lin).sum())
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_sample(seed_and_its):
-    """Worker of the CPU legs: the first `its` SCP iterations of one C2 problem with the reference's
-    solver restated (oracle.osqp_port at OSQP 0.6.2 defaults).  Returns seconds."""
-    seed, its = seed_and_its
-    from oracle import dubins, scp as oscp
+def cpu_sample(cores: int, its: int, seed: int = 0):
+    """CPU leg: `cores` C2 problems, one per host thread, each the first `its` SCP iterations (res_tol = -1 forces
+    exactly `its`), with the reference's algorithm restated in C (oracle/c/pmpc_oracle.c: lqp_utils.jl assembly +
+    OSQP 0.6.2 at its defaults + Dubins + the SCP loop).  Returns wall seconds."""
+    from oracle import cport
 
-    arrs, p, d0 = make_batch(1, seed)
+    arrs, p, d0 = make_batch(cores, seed)
     t = time.perf_counter()
-    X, U, data = oscp.scp_solve(dubins.make_f_fx_fu_fn(p[0]), arrs["Q"][0], arrs["R"][0], arrs["x0"][0],
-                                X_ref=arrs["X_ref"][0], U_ref=arrs["U_ref"][0], X_prev=arrs["X_prev"][0],
-                                U_prev=arrs["U_prev"][0], u_l=arrs["u_l"][0], u_u=arrs["u_u"][0], reg_x=d0["reg_x"],
-                                reg_u=d0["reg_u"], max_it=its, res_tol=RES_TOL, solver_settings=d0["solver_settings"],
-                                qp="osqp")
-    assert X is not None and len(data["hist"]) == its
-    return time.perf_counter() - t
+    X, U, iters = cport.scp_dubins_batch(cores, p, arrs["Q"], arrs["R"], arrs["x0"], arrs["X_ref"], arrs["U_ref"], arrs["X_prev"],
+                                         arrs["U_prev"], arrs["u_l"], arrs["u_u"], reg_x=d0["reg_x"], reg_u=d0["reg_u"],
+                                         max_it=its, res_tol=-1.0, Nc=NC)
+    sec = time.perf_counter() - t
+    assert np.isfinite(X).all() and (iters == its).all()
+    return sec
 
 
 def reference_arm(args):
-    """The reference's CPU algorithm for the path (oracle port; the Julia/OSQP stack itself is not
-    buildable in this image: DESIGN.md) on all host cores.  Each step: every worker process runs the
-    first `sample_its` SCP iterations of its own C2 problem; a full solve takes `full_its` iterations
+    """The reference's CPU algorithm for the path on all host cores (the Julia/OSQP stack itself is not buildable in
+    this image, DESIGN.md: the plain-C restatement under oracle/c stands in, `kind: "port"`).  Each step: every host
+    thread runs the first `sample_its` SCP iterations of its own C2 problem; a full solve takes `full_its` iterations
     (tests/golden/c2_reference_iters.json, measured with the same code), so
-    solves/s = workers * (sample_its / full_its) / step_time."""
+    solves/s = cores * (sample_its / full_its) / step_time."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
-    import multiprocessing as mp
-
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    os.environ.setdefault("MKL_NUM_THREADS", "1")
     cores = os.cpu_count() or 1
-    full_its = c2_iters_fixture()["osqp_port_scp_iters"]
+    full_its = c2_iters_fixture()["c_port_scp_iters"]
     sample_its = args.ref_sample_its
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        run = lambda: (lambda t0: (pool.map(cpu_sample, [(s, sample_its) for s in range(cores)]), time.perf_counter() - t0))(time.perf_counter())
-        for _ in range(args.warmup):
-            run()
-        times = [run()[1] for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        cpu_sample(cores, sample_its)
+    times = [cpu_sample(cores, sample_its, seed=k) for k in range(args.steps)]
     step = float(np.mean(times))
     value = cores * (sample_its / full_its) / step
-    sample = (f"{cores} worker processes, each the first {sample_its} of {full_its} SCP iterations of one C2 problem "
-              f"(OSQP restated at reference defaults eps=1e-3), scaled to full solves")
+    sample = (f"{cores} host threads, each the first {sample_its} of {full_its} SCP iterations of its own C2 problem "
+              f"(plain-C restatement: OSQP 0.6.2 at the reference's defaults eps=1e-3), scaled to full solves")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2 Dubins N=50 M=128 Nc=1 particle consensus", "host_cores": cores,
-                       "reference": "restated CPU baseline (oracle/), not PMPC.jl: Julia/OSQP absent from the image"},
+                       "reference": "restated CPU baseline (oracle/c), not PMPC.jl: Julia/OSQP absent from the image"},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -209,8 +214,8 @@ def main():
                     help="independent C2 problems per GPU per step (0 = --waves full waves: SMs x resident CTAs per SM x waves)")
     ap.add_argument("--waves", type=int, default=8)
     ap.add_argument("--latency-solves", type=int, default=20)
-    ap.add_argument("--cpu-sample-its", type=int, default=8)
-    ap.add_argument("--ref-sample-its", type=int, default=2)
+    ap.add_argument("--cpu-sample-its", type=int, default=16)
+    ap.add_argument("--ref-sample-its", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -301,7 +306,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scp_kernel<4,2,grouped>",
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,
-                "fp64_tflops_achieved": aflops / (kernel_ms * 1e-3) / 1e12}
+                "model": "fused two-sweep pass: 582 B per (particle, stage, pass) = X_prev,U_prev,act in; K,k,H,sparse stage "
+                         "out+in; X,U,act out (DESIGN.md 5)",
+                "fp64_tflops_dense_equivalent": aflops / (kernel_ms * 1e-3) / 1e12,
+                "unfused_streaming_model_bytes_per_launch": survey_streaming_bytes(info)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
@@ -356,11 +364,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fx = c2_iters_fixture()
-        its = args.cpu_sample_its
-        sec = cpu_sample((0, its))
-        cpu = {"value": 1.0 / (sec * fx["osqp_port_scp_iters"] / its), "unit": "solves/s", "cores": 1, "kind": "port",
-               "sample": f"first {its} of {fx['osqp_port_scp_iters']} SCP iterations of C2 problem 0 with the reference's "
-                         f"solver restated (oracle.osqp_port, OSQP 0.6.2 defaults), {sec:.1f} s, scaled to a full solve"}
+        its, cores = args.cpu_sample_its, os.cpu_count() or 1
+        sec = cpu_sample(cores, its)
+        cpu = {"value": cores / (sec * fx["c_port_scp_iters"] / its), "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} host threads, each the first {its} of {fx['c_port_scp_iters']} SCP iterations of its own C2 "
+                         f"problem with the reference's solver restated in C (oracle/c/pmpc_oracle.c, OSQP 0.6.2 defaults), "
+                         f"{sec:.1f} s wall, scaled to full solves"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,

@@ -1,8 +1,9 @@
 """Generates tests/golden/c2_reference_iters.json: how many SCP iterations the CPU restatement of the
 reference needs on BASELINE config C2 (Dubins N=50 M=128 Nc=1, seed 1) to reach res_tol=1e-5, with
 (a) the reference's solver restated at its default settings (oracle.osqp_port, eps=1e-3) and
-(b) the exact QP oracle (oracle.lqp).  bench.py scales its bounded CPU samples with (a).
-Takes ~2 x 110 s on one core:  python tests/golden/make_c2_iters.py"""
+(b) the exact QP oracle (oracle.lqp), (c) the plain-C restatement (oracle/c/pmpc_oracle.c, OSQP 0.6.2 defaults).
+bench.py scales its bounded CPU samples with (c).
+Takes ~2 x 110 s + 40 s on one core:  python tests/golden/make_c2_iters.py"""
 import json, os, sys, time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -21,5 +22,14 @@ for key, qp in (("osqp_port", "osqp"), ("exact", "exact")):
     out[key + "_seconds_1core"] = round(time.time() - t, 1)
     out[key + "_final_resid"] = float(data["hist"][-1]["resid"])
     out[key + "_final_obj"] = float(data["hist"][-1]["obj"])
+from oracle import cport
+
+d, p = config_c2()
+kw = {k: d[k] for k in ("X_ref", "U_ref", "X_prev", "U_prev", "u_l", "u_u", "reg_x", "reg_u", "max_it", "res_tol")}
+t = time.time()
+X, U, h = cport.scp_dubins(p, d["Q"], d["R"], d["x0"], Nc=1, **kw)
+out.update(c_port_scp_iters=len(h), c_port_seconds_1core=round(time.time() - t, 1), c_port_final_resid=float(h[-1, 1]),
+           c_port_final_obj=float(h[-1, 0]),
+           c_port_note="oracle/c/pmpc_oracle.c (OSQP 0.6.2 restated at its defaults), one core of the build container")
 json.dump(out, open(os.path.join(HERE, "c2_reference_iters.json"), "w"), indent=1)
 print(out)
