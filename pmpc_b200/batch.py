@@ -101,28 +101,86 @@ def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: O
 def solve_batch(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_prev=None, x_l=None, x_u=None, u_l=None,
                 u_u=None, max_it: int = 100, res_tol: float = 1e-5, reg_x: float = 1.0, reg_u: float = 1e-2,
                 slew_rate: Optional[float] = 0.0, Nc: int = -1, dyn_eps: float = 1e-6, device: int = -1,
-                solver: Optional[DeviceSolver] = None, settings: Optional[dict] = None, reuse_buffers: bool = False):
+                solver=None, settings: Optional[dict] = None, reuse_buffers: bool = False, chunks: int = 1):
     """Array form of the batched solve: B independent Dubins-car particle problems given as stacked
     HOST arrays with a leading problem axis — ``dyn_params (B,M,3)``, ``Q (B,M,N,n,n)``, ``R (B,M,N,m,m)``,
-    ``x0 (B,M,n)``, vectors ``(B,M,N,d)`` — solved by ONE device launch (one CTA per problem).  Argument
+    ``x0 (B,M,n)``, vectors ``(B,M,N,d)`` — solved with one CTA per problem.  Argument
     meaning and defaults are those of ``solve`` (reference ``scp_mpc.py:205-238``; warm-start default
     ``X_prev = X_ref``, ``:313-314``).  Returns ``X (B,M,N+1,n)`` including x0, ``U (B,M,N,m)``, ``info``
-    (per-problem counters of ``pmpc_get_info``), and the :class:`DeviceSolver` for reuse via ``solver=``.
+    (per-problem counters of ``pmpc_get_info``), and the solver state for reuse via ``solver=``.
     Inputs in page-locked memory (``pmpc_b200.pinned_empty`` / ``pinned_copy``) are copied at full PCIe
-    speed; ``reuse_buffers=True`` returns X, U in page-locked buffers owned by the solver."""
+    speed; ``reuse_buffers=True`` returns X, U in page-locked buffers owned by the solver.
+
+    ``chunks > 1`` pipelines the batch: it is cut into ``chunks`` contiguous sub-batches, each on its own handle
+    (own CUDA stream); the host-to-device upload and packing of sub-batch k+1 and the device-to-host read of
+    sub-batch k-1 overlap the solve kernel of sub-batch k, so PCIe time leaves the critical path except for the
+    first upload and the last download.  Results are identical to ``chunks=1`` (problems are independent)."""
     Q = np.asarray(Q)
     B, M, N, n = Q.shape[:4]
     m = np.asarray(R).shape[-1]
+    if chunks > 1 and B >= chunks:
+        return _solve_batch_pipelined(dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u, max_it, res_tol,
+                                      reg_x, reg_u, slew_rate, Nc, dyn_eps, device, solver, settings, reuse_buffers, chunks)
     ds = solver
-    if ds is None or (ds.B, ds.M, ds.N, ds.n, ds.m, ds.Nc) != (B, M, N, n, m, Nc):
+    if not isinstance(ds, DeviceSolver) or (ds.B, ds.M, ds.N, ds.n, ds.m, ds.Nc) != (B, M, N, n, m, Nc):
         ds = DeviceSolver(M, N, n, m, Nc, B=B, device=device, settings=settings)
+    _upload_and_launch(ds, dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u, max_it, res_tol, reg_x, reg_u,
+                       slew_rate, dyn_eps)
+    X, U = ds.trajectory(reuse_buffers)  # stream-ordered after the solve; synchronises
+    return X, U, ds.info(), ds
+
+
+def _upload_and_launch(ds, dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u, max_it, res_tol, reg_x, reg_u,
+                       slew_rate, dyn_eps):
+    B, M = ds.B, ds.M
     ds.set_problem(x0, Q, R, X_ref, U_ref, x_l, x_u, u_l, u_u, reg_x, reg_u,
                    None if slew_rate is None else np.full(B * M, float(slew_rate)))
     ds.set_warm_start(X_ref if X_prev is None else X_prev, U_ref if U_prev is None else U_prev)
     ds.set_dubins(dyn_params, dyn_eps)
     ds.scp_solve_async(max_it, res_tol)
-    X, U = ds.trajectory(reuse_buffers)  # stream-ordered after the solve; synchronises
-    return X, U, ds.info(), ds
+
+
+class BatchPipeline:
+    """Solver state of a pipelined ``solve_batch``: one handle per sub-batch and the page-locked output buffers."""
+
+    def __init__(self, key, bounds, solvers):
+        self.key, self.bounds, self.solvers, self.out = key, bounds, solvers, None
+
+    def last_kernel_ms(self):
+        return sum(s.last_kernel_ms() for s in self.solvers)
+
+
+def _solve_batch_pipelined(dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u, max_it, res_tol, reg_x, reg_u,
+                           slew_rate, Nc, dyn_eps, device, solver, settings, reuse_buffers, chunks):
+    from ._lib import pinned_empty
+
+    B, M, N, n = Q.shape[:4]
+    m = np.asarray(R).shape[-1]
+    key = (B, M, N, n, m, Nc, chunks, device)
+    pipe = solver if isinstance(solver, BatchPipeline) and solver.key == key else None
+    if pipe is None:
+        bounds = [(B * k // chunks, B * (k + 1) // chunks) for k in range(chunks)]
+        pipe = BatchPipeline(key, bounds, [DeviceSolver(M, N, n, m, Nc, B=hi - lo, device=device, settings=settings)
+                                           for lo, hi in bounds])
+    if reuse_buffers:
+        if pipe.out is None:
+            pipe.out = (pinned_empty((B, M, N + 1, n)), pinned_empty((B, M, N, m)))
+        X, U = pipe.out
+    else:
+        X, U = np.empty((B, M, N + 1, n)), np.empty((B, M, N, m))
+    cut = lambda a, lo, hi: None if a is None else np.asarray(a)[lo:hi]
+    # uploads run one after the other (each gets the full PCIe bandwidth); every solve is asynchronous on its own stream,
+    # so sub-batch k+1 is uploaded and packed while sub-batch k is being solved
+    for (lo, hi), ds in zip(pipe.bounds, pipe.solvers):
+        _upload_and_launch(ds, cut(dyn_params, lo, hi), Q[lo:hi], cut(R, lo, hi), cut(x0, lo, hi), cut(X_ref, lo, hi),
+                           cut(U_ref, lo, hi), cut(X_prev, lo, hi), cut(U_prev, lo, hi), cut(x_l, lo, hi), cut(x_u, lo, hi),
+                           cut(u_l, lo, hi), cut(u_u, lo, hi), max_it, res_tol, reg_x, reg_u, slew_rate, dyn_eps)
+    infos = []
+    for (lo, hi), ds in zip(pipe.bounds, pipe.solvers):
+        ds.trajectory(out=(X[lo:hi], U[lo:hi]))  # waits for this sub-batch only; later ones keep computing
+        infos.append(ds.info())
+    info = {k: np.concatenate([i[k] for i in infos]) for k in infos[0]}
+    return X, U, info, pipe
 
 
 def solve_batched(problems: List[Dict[str, Any]], verbose: bool = False, device: int = -1, **kw):

@@ -166,12 +166,16 @@ class DeviceSolver:
         shp = (self.B, self.M, N) if self.B > 1 else (self.M, N)
         return X.reshape(shp + (self.n,)), U.reshape(shp + (self.m,))
 
-    def trajectory(self, reuse_buffers: bool = False):
+    def trajectory(self, reuse_buffers: bool = False, out=None):
         """``X (B, M, N+1, n)`` including x0 and ``U (B, M, N, m)`` — the arrays ``solve`` returns
         (``static_backend.py:311``), assembled on the device.  With ``reuse_buffers`` the results land in
-        page-locked buffers owned by this solver (overwritten by the next call) instead of fresh arrays."""
+        page-locked buffers owned by this solver (overwritten by the next call) instead of fresh arrays;
+        ``out=(X, U)`` writes into caller-provided C-contiguous arrays (e.g. slices of one page-locked buffer)."""
         P, N = self.B * self.M, self.N
-        if reuse_buffers:
+        if out is not None:
+            X, U = out
+            assert X.flags.c_contiguous and U.flags.c_contiguous and X.size == P * (N + 1) * self.n and U.size == P * N * self.m
+        elif reuse_buffers:
             if self._out is None:
                 self._out = (pinned_empty((P, N + 1, self.n)), pinned_empty((P, N, self.m)))
             X, U = self._out

@@ -429,3 +429,19 @@ def test_user_dynamics_batched_equals_individual_and_errors(gpu):
     with pytest.raises(pmpc_b200.PmpcError, match="failed to compile"):
         pmpc_b200.UserDynamics("__device__ void broken(const double* x) { undeclared = 1; }", "broken", 2, 1)(
             np.zeros((1, 3, 2)), np.zeros((1, 3, 1)))
+
+
+def test_pipelined_batch_equals_single_launch(gpu):
+    """solve_batch(chunks=3): sub-batches on their own handles / streams with uploads overlapping the solve kernels
+    must return bit-identical X, U and counters (problems are independent), also with page-locked reuse."""
+    B = 7
+    d, p = config_c3(B=B, M=5, N=12)
+    args = dict(X_ref=d["X_ref"], U_ref=d["U_ref"], X_prev=d["X_prev"], U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"],
+                max_it=d["max_it"], res_tol=d["res_tol"], reg_x=d["reg_x"], reg_u=d["reg_u"], slew_rate=0.0, Nc=1)
+    Q, R = np.ascontiguousarray(d["Q"]), np.ascontiguousarray(d["R"])
+    X1, U1, info1, _ = pmpc_b200.solve_batch(p, Q, R, d["x0"], **args)
+    pipe = None
+    for rep in range(2):  # second call reuses the pipeline (handles + page-locked outputs)
+        X3, U3, info3, pipe = pmpc_b200.solve_batch(p, Q, R, d["x0"], chunks=3, solver=pipe, reuse_buffers=True, **args)
+        assert np.array_equal(X1, X3) and np.array_equal(U1, U3)
+        assert all(np.array_equal(info1[k], info3[k]) for k in info1)
