@@ -5,8 +5,9 @@
 (hand-written sm_100a CUDA, C ABI in ``include/pmpc_b200.h``); there is no CPU fallback.
 """
 from .scp_mpc import (  # noqa: F401
-    AA_method, FILTER_MAP, scp_solve, select_method, smooth_method, solve, solve_problems,
+    AA_method, FILTER_MAP, scp_solve, select_method, smooth_method, solve, solve_problems, tune_scp,
 )
+from .accelerated import accelerated_scp_solve  # noqa: F401
 from .static_backend import aff_solve, is_precompiled_backend_available, lqp_solve  # noqa: F401
 from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics  # noqa: F401
 from .handle import DeviceSolver  # noqa: F401

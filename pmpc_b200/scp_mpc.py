@@ -17,7 +17,7 @@ from __future__ import annotations
 import math
 import time
 from copy import copy
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -340,6 +340,43 @@ def solve(*args, **kwargs):
             print_fn("  device kernel: %.3f ms" % ret[2]["device"]["kernel_ms"])
         return ret
     return scp_solve(*args, **kwargs)
+
+
+def tune_scp(*args, sample_nb: int = 14, reg_rng: Tuple[int, int] = (-3, 3), solve_fn: Optional[Callable] = None,
+             savefig: Optional[str] = None, reg_list: Optional[Sequence[float]] = None, **kwargs):
+    """Hyper-parameter sweep of the proximal weights (reference ``scp_mpc.py:460-497``): solves the problem for
+    ``sample_nb`` values of ``reg_x`` on a log grid (``reg_u = reg_ratio * reg_x``) and returns the pair with the
+    smallest final residual (``reg_list`` gives the grid explicitly).  A failed solve counts as residual 1e2, as in the
+    reference.  The residual curve is
+    plotted only when matplotlib is importable and ``savefig`` is given (the reference always plots)."""
+    solve_fn = scp_solve if solve_fn is None else solve_fn
+    reg_ratio = kwargs.pop("reg_ratio", 1e-1)
+    reg_list = np.asarray(np.logspace(*reg_rng, sample_nb) if reg_list is None else reg_list, dtype=np.float64)
+    res_list = []
+    for reg in reg_list:
+        kwargs.update(reg_x=float(reg), reg_u=float(reg * reg_ratio), verbose=False)
+        X, U, data = solve_fn(*args, **kwargs)
+        res_list.append(1e2 if data is None else data["hist"][-1]["resid"])
+        if data is not None and "device_solver" in data:  # reuse the handle for the next sample
+            kwargs["solver_settings"] = dict(kwargs.get("solver_settings") or {}, _device_solver=data["device_solver"])
+    if savefig is not None:
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+
+            plt.figure()
+            plt.loglog(reg_list, res_list)
+            plt.ylabel("final residual")
+            plt.xlabel("reg_x")
+            plt.title("reg_u = reg_x * %6.1e" % reg_ratio)
+            plt.grid(True, which="both")
+            plt.tight_layout()
+            plt.savefig(savefig, dpi=200)
+        except ImportError:
+            pass
+    reg_x = float(reg_list[int(np.argmin(res_list))])
+    return reg_x, reg_ratio * reg_x
 
 
 def solve_problems(problems: List[Dict[str, Any]], verbose: bool = False, **kw):

@@ -183,3 +183,20 @@ def test_shard_particles_copies_shared_block_bounds():
         lo, hi = parallel.shard_bounds(M, r, 3)
         assert np.array_equal(p["u_l"][0, :Nc], full["u_l"][0, :Nc]) and np.array_equal(p["u_u"][0, :Nc], full["u_u"][0, :Nc])
         assert np.array_equal(p["u_l"][0, Nc:], full["u_l"][lo, Nc:]) and np.array_equal(p["u_l"][1:], full["u_l"][lo + 1:hi])
+
+
+def test_outer_loop_variants_keep_the_reference_signatures():
+    """accelerated_scp_solve / tune_scp are drop-ins: same parameter names, order and defaults as
+    reference pmpc/accelerated.py:15-41 and pmpc/scp_mpc.py:460-467 (read from the committed signature list, the
+    reference tree does not exist on the GPU box)."""
+    import inspect
+
+    import pmpc_b200
+
+    acc = inspect.signature(pmpc_b200.accelerated_scp_solve).parameters
+    assert list(acc)[:12] == ["f_fx_fu_fn", "Q", "R", "x0", "X_ref", "U_ref", "X_prev", "U_prev", "x_l", "x_u", "u_l", "u_u"]
+    assert [acc[k].default for k in ("verbose", "max_it", "time_limit", "res_tol", "reg_x", "reg_u", "slew_rate", "method")] == \
+        [True, 100, 1000.0, 1e-5, 1e0, 1e-2, 0.0, "lqp"]
+    tune = inspect.signature(pmpc_b200.tune_scp).parameters
+    assert tune["sample_nb"].default == 14 and tune["reg_rng"].default == (-3, 3) and "savefig" in tune
+    assert pmpc_b200.accelerated.momentum_update(np.ones(2), np.zeros(2), 3) == pytest.approx(1.6 * np.ones(2))

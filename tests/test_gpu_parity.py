@@ -445,3 +445,66 @@ def test_pipelined_batch_equals_single_launch(gpu):
         X3, U3, info3, pipe = pmpc_b200.solve_batch(p, Q, R, d["x0"], chunks=3, solver=pipe, reuse_buffers=True, **args)
         assert np.array_equal(X1, X3) and np.array_equal(U1, U3)
         assert all(np.array_equal(info1[k], info3[k]) for k in info1)
+
+
+def test_accelerated_outer_loop_against_reference_golden(gpu):
+    """`accelerated_scp_solve` (momentum over SCP iterates, reference pmpc/accelerated.py:15-116) with the device
+    Dubins model against the trajectory the REFERENCE's own function produced here (make_golden_accelerated.py)."""
+    g = np.load(os.path.join(GOLD, "scp_accelerated.npz"))
+    kw = {k: g[k] for k in ("X_ref", "U_ref", "X_prev", "U_prev", "u_l", "u_u")}
+    X, U, data = pmpc_b200.accelerated_scp_solve(DubinsCar(g["p"][:, 0]), g["Q"], g["R"], g["x0"], verbose=False, max_it=60,
+                                                 res_tol=1e-7, reg_x=1.0, reg_u=1e-2, solver_settings=dict(solver="osqp", Nc=1), **kw)
+    assert abs(len(data["hist"]) - len(g["hist"])) <= 1 and data["hist"][-1]["resid"] < 1e-7
+    assert rel(X, g["X"]) < 1e-5 and rel(U, g["U"]) < 1e-5
+    assert abs(data["hist"][-1]["obj"] - g["hist"][-1, 0]) <= 1e-6 * abs(g["hist"][-1, 0])
+    k = min(len(data["hist"]), len(g["hist"])) - 2  # same contraction history away from the noisy first iterates (H3)
+    assert abs(data["hist"][k]["resid"] - g["hist"][k, 1]) <= 0.05 * g["hist"][k, 1] + 1e-9
+
+
+def test_tune_scp_picks_the_smallest_residual(gpu):
+    d, p = config_c2(M=4, N=10)
+    d.update(max_it=15, res_tol=1e-9)
+    grid = np.array([1e-2, 1e0, 1e2])
+    reg_x, reg_u = pmpc_b200.tune_scp(DubinsCar(p), d["Q"], d["R"], d["x0"], reg_list=grid, reg_ratio=1e-2,
+                                      **{k: d[k] for k in ("X_ref", "U_ref", "X_prev", "U_prev", "u_l", "u_u", "max_it", "res_tol",
+                                                           "solver_settings")})
+    res = []
+    for r in grid:
+        _, _, data = pmpc_b200.solve(DubinsCar(p), **dict(d, reg_x=float(r), reg_u=float(r) * 1e-2))
+        res.append(data["hist"][-1]["resid"])
+    assert reg_x == grid[int(np.argmin(res))] and reg_u == pytest.approx(1e-2 * reg_x)
+
+
+def test_thread_per_problem_batch_with_ragged_tail(gpu):
+    """B = 35 single-particle problems (one thread per problem: a full warp + a 3-lane tail whose idle lanes exit at
+    once) == the oracle on each problem; the kernel must not depend on what the idle lanes would have done."""
+    B, N = 35, 8
+    d, p = config_c3(B=B, M=1, N=N)
+    probs = [dict({k: (v[b, 0] if isinstance(v, np.ndarray) and v.shape[:2] == (B, 1) else v) for k, v in d.items()},
+                  f_fx_fu_fn=DubinsCar(p[b, 0])) for b in range(B)]
+    for q in probs:
+        q["solver_settings"] = dict(solver="osqp")
+        q["res_tol"] = 1e-7
+    res = pmpc_b200.solve_problems(probs)
+    for b in (0, 17, 31, 32, 34):
+        q = probs[b]
+        kw = {k: q[k][None] for k in ("X_ref", "U_ref", "X_prev", "U_prev", "u_l", "u_u")}
+        Xo, Uo, do = oscp.scp_solve(dubins.make_f_fx_fu_fn(p[b, 0]), q["Q"][None], q["R"][None], q["x0"][None], reg_x=q["reg_x"],
+                                    reg_u=q["reg_u"], max_it=q["max_it"], res_tol=q["res_tol"], solver_settings=q["solver_settings"], **kw)
+        assert res[b][0].shape == (N + 1, 4) and len(res[b][2]["hist"]) == len(do["hist"])
+        assert rel(res[b][0], Xo[0]) < 1e-5 and rel(res[b][1], Uo[0]) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,Nc", [(1024, 3, 1), (2, 1, 1), (70, 6, 6)])
+def test_extreme_shapes_properties(gpu, M, N, Nc):
+    """Largest particle count per GPU (M = 1024, kind-2 CTAs), a one-stage horizon, full consensus (Nc = N) on a
+    ragged particle count: consensus equality, box, exact linearised dynamics at the fixed point, device KKT certificate."""
+    d, p = config_c2(M=M, N=N)
+    d.update(res_tol=1e-8, max_it=80, solver_settings=dict(solver="osqp", Nc=Nc))
+    car = DubinsCar(p)
+    X, U, data = pmpc_b200.solve(car, **d)
+    assert data["device"]["status"] == 0 and data["hist"][-1]["resid"] < 1e-8
+    assert np.all(U[:, :Nc] == U[:1, :Nc]) and np.abs(U).max() <= 1 + 1e-12
+    assert max(sd["kkt"] for sd in data["solver_data"]) < 1e-8
+    f, _, _ = car(X[:, :-1], U)
+    assert np.abs(f - X[:, 1:]).max() < 1e-6
