@@ -327,6 +327,9 @@
 #pragma unroll UNR
     for (int e = 0; e < NX; ++e) p[e] = 0.0;
     if (use_ring) {
+      // X_prev, U_prev and the active set may have been written with plain stores since the last sweep (the
+      // unfused ADMM path of the previous sub-problem, ipm_finish): order them before the bulk reads below
+      fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         for (int d = 0; d < DEPTH; ++d)
