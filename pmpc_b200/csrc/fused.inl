@@ -22,7 +22,7 @@
   // =============================================================================================
   static constexpr bool RING_SHAPE = (NX <= 4);
 #ifndef PMPC_DEPTH
-#define PMPC_DEPTH 3
+#define PMPC_DEPTH 2
 #endif
   static constexpr int DEPTH = PMPC_DEPTH;
   // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | (L) | act]
@@ -1040,6 +1040,158 @@
     return ch;
   }
 
+  // Shared block of D <= DSMALL controls (C2: D = 2) solved in registers.  Same mathematics as
+  // assemble_shared / grad_shared / factor_shared / apply_shared / shared_active_update — sum_i H_i and sum_i g_i by
+  // adjoint passes over the shared stages, then the primal-dual active-set iteration of the D-dimensional box QP —
+  // but with ONE small CTA reduction (cta_reduce) and the whole D x D iteration replicated in every thread, instead
+  // of ~25 barriers and as many round trips through the problem's global scratch per pass.
+  // Returns the number of active-set changes of the last iteration; kk / uv = KKT and bound violation of the block.
+  template <bool UBOX>
+  __device__ __noinline__ double shared_small(const double* pc, const double* zc, double* kk, double* uv) {
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    const int Dn = D;
+    double hv[DSMALL * DSMALL + DSMALL];
+    if (Nc == 1 && NU <= DSMALL) {
+      // One shared stage (the MPC-typical case): H_i and g_i in closed form from ONE read of the stage-0 data and of the
+      // particle's boundary value function — the generic adjoint passes below evaluate the same expressions D + 1
+      // times through scratch stages of X.  With S0 = Qs_0 + Pc (stage 0 has no A: lqp_utils.jl:288-296):
+      //   H_i = Rs_0 + Zc + B0' (S0 B0 + Wc) + Wc' B0         g_i = r_0 + zc + Wc' c0 + B0' (q_0 + S0 c0 + pc)
+      double B0[NX * NU], S0[NX * NX], Wc[NX * NU], c0[NX], an[NX];
+#pragma unroll UNR
+      for (int e = 0; e < NX * NU; ++e) { B0[e] = ld(pb.Bm, 0, NX * NU, e); Wc[e] = F.Wc[(size_t)e * P + g]; }
+#pragma unroll UNR
+      for (int r = 0; r < NX; ++r) {
+        c0[r] = ld(pb.c, 0, NX, r);
+#pragma unroll UNR
+        for (int t = 0; t < NX; ++t)
+          S0[r * NX + t] = ld(pb.Qs, 0, NQ, r <= t ? pk(r, t, NX) : pk(t, r, NX)) + F.Pc[(size_t)(r * NX + t) * P + g];
+      }
+#pragma unroll UNR
+      for (int k = 0; k < NU; ++k) {
+#pragma unroll UNR
+        for (int r = 0; r < NX; ++r) {
+          double acc = Wc[r * NU + k];
+#pragma unroll UNR
+          for (int t = 0; t < NX; ++t) acc += S0[r * NX + t] * B0[t * NU + k];
+          an[r] = acc;
+        }
+#pragma unroll UNR
+        for (int b = 0; b < NU; ++b) {
+          double acc = ld(pb.Rs, 0, NR, b <= k ? pk(b, k, NU) : pk(k, b, NU)) + F.Zc[(size_t)(b * NU + k) * P + g];
+#pragma unroll UNR
+          for (int r = 0; r < NX; ++r) acc += Wc[r * NU + b] * B0[r * NU + k] + B0[r * NU + b] * an[r];
+          hv[k * Dn + b] = valid ? acc : 0.0;
+        }
+      }
+#pragma unroll UNR
+      for (int r = 0; r < NX; ++r) {
+        double acc = ld(pb.q, 0, NX, r) + pc[r];
+#pragma unroll UNR
+        for (int t = 0; t < NX; ++t) acc += S0[r * NX + t] * c0[t];
+        an[r] = acc;
+      }
+#pragma unroll UNR
+      for (int b = 0; b < NU; ++b) {
+        double acc = ld(pb.r, 0, NU, b) + zc[b];
+#pragma unroll UNR
+        for (int r = 0; r < NX; ++r) acc += Wc[r * NU + b] * c0[r] + B0[r * NU + b] * an[r];
+        hv[Dn * Dn + b] = valid ? acc : 0.0;
+      }
+    } else {
+      for (int k = 0; k < Dn; ++k) shared_grad(MODE_POLISH, true, k, nullptr, 0.0, 0.0, nullptr, nullptr, 0, &hv[k * Dn]);
+      shared_grad(MODE_POLISH, false, -1, nullptr, 0.0, 0.0, pc, zc, 0, &hv[Dn * Dn]);
+    }
+    cta_reduce(hv, Dn * Dn + Dn, 0xffffffffu);
+    double H[DSMALL * DSMALL], gcv[DSMALL], lo[DSMALL], hi[DSMALL], ucv[DSMALL];
+    signed char act[DSMALL];
+    const size_t g0 = (size_t)prob * pb.Mpad;  // particle 0 of the problem owns the shared bounds (lqp_utils.jl:329-330)
+    for (int a = 0; a < Dn; ++a) {
+      for (int b = 0; b < Dn; ++b) H[a * DSMALL + b] = 0.5 * (hv[b * Dn + a] + hv[a * Dn + b]);  // column k of sum H_i sits in hv[k*D ..]
+      gcv[a] = hv[Dn * Dn + a];
+      lo[a] = -INFINITY; hi[a] = INFINITY;
+      if (pb.has_ubox) {
+        lo[a] = pb.lu[ixg(a / NU, NU, a % NU, g0)];
+        hi[a] = pb.uu[ixg(a / NU, NU, a % NU, g0)];
+      }
+      act[a] = (UBOX && pb.has_ubox) ? pb.actc[(size_t)prob * Dn + a] : 0;
+      ucv[a] = 0.0;
+    }
+    double ch = 0.0;
+    for (int t = 0; t <= 2 * Dn; ++t) {
+      // masked system: fixed components at their bound beta, free ones solve  H_ff u_f = -(g_f + H_fb beta)
+      double L[DSMALL * DSMALL], rhs[DSMALL];
+      for (int a = 0; a < Dn; ++a) {
+        double acc = gcv[a];
+        for (int b = 0; b < Dn; ++b)
+          if (act[b] != 0) acc += H[a * DSMALL + b] * ((act[b] > 0) ? hi[b] : lo[b]);
+        rhs[a] = -acc;
+        for (int b = 0; b < Dn; ++b) {
+          const bool fx = act[a] != 0 || act[b] != 0;
+          L[a * DSMALL + b] = fx ? (a == b ? 1.0 : 0.0) : H[a * DSMALL + b];
+        }
+      }
+      for (int k = 0; k < Dn; ++k) {  // Cholesky (lower) of the masked matrix
+        double dk = L[k * DSMALL + k];
+        for (int l = 0; l < k; ++l) dk -= L[k * DSMALL + l] * L[k * DSMALL + l];
+        dk = sqrt(dk);
+        L[k * DSMALL + k] = dk;
+        for (int i = k + 1; i < Dn; ++i) {
+          double v = L[i * DSMALL + k];
+          for (int l = 0; l < k; ++l) v -= L[i * DSMALL + l] * L[k * DSMALL + l];
+          L[i * DSMALL + k] = v / dk;
+        }
+      }
+      double y[DSMALL];
+      for (int i = 0; i < Dn; ++i) {
+        double v = (act[i] != 0) ? 0.0 : rhs[i];
+        for (int l = 0; l < i; ++l) v -= L[i * DSMALL + l] * y[l];
+        y[i] = v / L[i * DSMALL + i];
+      }
+      for (int i = Dn - 1; i >= 0; --i) {
+        double v = y[i];
+        for (int l = i + 1; l < Dn; ++l) v -= L[l * DSMALL + i] * y[l];
+        y[i] = v / L[i * DSMALL + i];
+      }
+      for (int a = 0; a < Dn; ++a) ucv[a] = (act[a] != 0) ? ((act[a] > 0) ? hi[a] : lo[a]) : y[a];
+      if (!(UBOX && pb.has_ubox)) break;
+      // multipliers of the fixed components, violations of the free ones, primal-dual update (shared_active_update)
+      *kk = 0.0; *uv = 0.0; ch = 0.0;
+      signed char nact[DSMALL];
+      for (int k = 0; k < Dn; ++k) {
+        signed char na = 0;
+        if (act[k] != 0) {
+          double acc = gcv[k];
+          for (int l = 0; l < Dn; ++l) acc += H[k * DSMALL + l] * ucv[l];
+          if (act[k] > 0) {
+            *kk = fmax(*kk, fmax(acc, 0.0));
+            if (-acc > 0.0) na = 1;
+          } else {
+            *kk = fmax(*kk, fmax(-acc, 0.0));
+            if (-acc < 0.0) na = -1;
+          }
+        } else {
+          *uv = fmax(*uv, fmax(ucv[k] - hi[k], lo[k] - ucv[k]));
+          if (ucv[k] - hi[k] > 0.0 && hi[k] < INFINITY) na = 1;
+          else if (ucv[k] - lo[k] < 0.0 && lo[k] > -INFINITY) na = -1;
+        }
+        if (na != act[k]) ch += 1.0;
+        nact[k] = na;
+      }
+      for (int k = 0; k < Dn; ++k) act[k] = nact[k];
+      if (ch == 0.0) break;
+    }
+    if (tid == 0) {  // every thread holds the same values; the forward sweep and later passes read them from HBM
+      for (int a = 0; a < Dn; ++a) {
+        pb.uc[(size_t)prob * Dn + a] = ucv[a];
+        pb.gc[(size_t)prob * Dn + a] = gcv[a];
+        pb.actc[(size_t)prob * Dn + a] = act[a];
+        for (int b = 0; b < Dn; ++b) F.Hc[(size_t)prob * Dn * Dn + (size_t)a * Dn + b] = H[a * DSMALL + b];
+      }
+    }
+    __syncthreads();
+    return ch;
+  }
+
   // ---- interior-point fallback: shared block and driver ----------------------------------------
   // before the shared solve: lazy step / initial point of the shared controls, barrier terms into Hc, gc
   __device__ __forceinline__ void ipm_shared_pre(const DevProb& pb, const Ipm& ip) {
@@ -1179,7 +1331,9 @@
       cnt[2] += 1;
       cnt[7] += 1;
       double kk_c = 0.0, uv_c = 0.0, ch_c = 0.0;
-      if (GROUPED && Nc >= 1) {
+      if (GROUPED && Nc >= 1 && D <= DSMALL && pb.world <= 1) {
+        ch_c = shared_small<UBOX>(pc, zc, &kk_c, &uv_c);
+      } else if (GROUPED && Nc >= 1) {
         assemble_shared(MODE_POLISH, 0.0, 0.0);
         grad_shared(MODE_POLISH, 0.0, 0.0, pc, zc);
         // the shared block is a D-dimensional box QP once the particles' value functions are fixed:

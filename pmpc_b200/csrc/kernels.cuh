@@ -13,7 +13,8 @@ template <int NX, int NU, bool GROUPED, int BLK, int VAR>
 __global__ void __launch_bounds__(BLK, (BLK <= 128 ? PMPC_MINB : 1)) scp_kernel(const __grid_constant__ DevProb pb) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ double red[ST_COUNT];
-  Solver<NX, NU, GROUPED> S(pb, red);
+  __shared__ double red2[(BLK / 32) * RCAP];  // per-warp partials of the small CTA reductions (Solver::cta_reduce)
+  Solver<NX, NU, GROUPED> S(pb, red, red2);
   S.template run<VAR>(pb, dyn_smem);
 }
 

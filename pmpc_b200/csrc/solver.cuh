@@ -27,6 +27,8 @@ enum { MODE_POLISH = 0, MODE_ADMM = 1 };
 enum { DYN_AFFINE = 0, DYN_DUBINS = 1 };  // == PMPC_DYN_* of include/pmpc_b200.h
 enum { ST_KKT = 0, ST_UVIOL, ST_XVIOL, ST_CHANGED, ST_RP, ST_RD, ST_SP, ST_SD, ST_DX, ST_DU, ST_OBJ, ST_NAN,
        ST_GSCALE, ST_ZSCALE, ST_XACT, ST_COUNT };
+// small CTA reductions (Solver::cta_reduce): values per call, and the largest shared block solved in registers
+enum { RCAP = 24, DSMALL = 4 };
 
 struct FactorSet {
   double *K, *E, *d, *e;      // per (particle, stage): feedback gain, masked H^-1, S c (+fix), W'c (+fix)
@@ -158,6 +160,7 @@ struct Solver {
   bool valid;
   double s;  // slew weight of this particle
   double* red;  // shared: ST_COUNT doubles (+ D handled in global)
+  double* red2; // shared: RCAP doubles per warp
   // current iterate (Xc, Uc) and linearisation point (Xpv, Upv): the fused path swaps the two buffer
   // pairs instead of copying X_prev <- X (scp_mpc.py:407)
   double *Xc, *Uc, *Xpv, *Upv;
@@ -173,9 +176,9 @@ struct Solver {
   bool dead;  // whole warp beyond the last problem (thread-per-problem launch tail)
   unsigned long long xseq;  // cross-GPU exchange counter (uniform over the CTA, identical on every rank)
 
-  __device__ Solver(const DevProb& pb_, double* red_)
+  __device__ Solver(const DevProb& pb_, double* red_, double* red2_)
       : pb(pb_), P(pb_.P), N(pb_.N), Nc(GROUPED ? pb_.Nc : 0), D(GROUPED ? pb_.D : 0), T(blockDim.x),
-        tid(threadIdx.x), red(red_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0) {
+        tid(threadIdx.x), red(red_), red2(red2_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0) {
     // lanes without a particle mirror the last valid lane of their own warp (same warp tile)
     dead = false;
     if (GROUPED) {
@@ -227,6 +230,31 @@ struct Solver {
     __syncthreads();
   }
 
+
+  // ---- small CTA reduction without global memory ------------------------------------------------
+  // v[k], k < cnt <= RCAP, of every thread -> v[k] = sum over the CTA (bit k of sum_mask set) or max, replicated in
+  // every thread.  Warp butterfly, then the per-warp partials through shared memory, combined in warp order
+  // (deterministic).  Two barriers, no global round trip — the per-pass bookkeeping used to go through the
+  // problem's global scratch with one barrier pair per reduction plus ~20 more in the shared-block solve, which
+  // cost about a quarter of the kernel time at C2 size (ncu source view: 8 % of the instructions, 33 % of the
+  // stall samples).
+  __device__ __forceinline__ void cta_reduce(double* v, int cnt, unsigned sum_mask) {
+    if (!GROUPED) return;
+    const int ln = tid & 31, w = tid >> 5, nw = T >> 5;
+    for (int k = 0; k < cnt; ++k) {
+      const bool is_sum = (sum_mask >> k) & 1u;
+      const double r = is_sum ? warp_sum(v[k]) : warp_max(v[k]);
+      if (ln == 0) red2[w * RCAP + k] = r;
+    }
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) {
+      const bool is_sum = (sum_mask >> k) & 1u;
+      double acc = red2[k];
+      for (int ww = 1; ww < nw; ++ww) acc = is_sum ? acc + red2[ww * RCAP + k] : fmax(acc, red2[ww * RCAP + k]);
+      v[k] = acc;
+    }
+    __syncthreads();
+  }
 
   // ---- cross-GPU all-reduce of a short vector (particle sharding) -------------------------------
   // Every rank publishes its partial vector in its own exchange slot (double-buffered by sequence
@@ -579,7 +607,7 @@ struct Solver {
   // hom = false: gradient at `uc` (NULL = 0) including all linear terms; hom = true: Hessian
   // action on the unit vector ek.  Result written to scratch rows [row0, row0 + D).
   __device__ __noinline__ void shared_grad(int mode, bool hom, int ek, const double* uc, double rho_u, double rho_x,
-                              const double* pc, const double* zc, int row0) {
+                              const double* pc, const double* zc, int row0, double* out = nullptr) {
     const FactorSet& F = pb.fs[mode];
     double x[NX];
 #pragma unroll UNR
@@ -684,7 +712,8 @@ struct Solver {
         double acc = gu[b];
 #pragma unroll UNR
         for (int r = 0; r < NX; ++r) acc += ld(pb.Bm, j, NX * NU, r * NU + b) * a[r];
-        sc[(size_t)(row0 + j * NU + b) * T + tid] = valid ? acc : 0.0;
+        if (out != nullptr) out[j * NU + b] = valid ? acc : 0.0;  // caller reduces with cta_reduce
+        else sc[(size_t)(row0 + j * NU + b) * T + tid] = valid ? acc : 0.0;
       }
     }
   }
@@ -1155,6 +1184,10 @@ struct Solver {
   // reduce the per-thread statistics over the problem; result replicated in st[]
   __device__ __noinline__ void reduce_stats(double* st) {
     if (!GROUPED) return;
+    if (pb.world <= 1) {  // one GPU: shuffles + shared memory (cta_reduce); ST_OBJ is summed, the rest max-reduced
+      cta_reduce(st, ST_COUNT, 1u << ST_OBJ);
+      return;
+    }
     double* sc = scr();
     for (int k = 0; k < ST_COUNT; ++k) sc[(size_t)k * T + tid] = st[k];
     reduce(ST_COUNT, red, ST_OBJ);
