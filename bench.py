@@ -126,15 +126,16 @@ def hbm_peak():
 
 
 # algorithmic work per (particle, stage), DESIGN.md section 5
-def alg_bytes_flops(info, n=NX, m=NU, nlin=14):
+def alg_bytes_flops(info, n=NX, m=NU, nlin=10):
     """HBM bytes the fused two-sweep pass has to move per (particle, stage): the backward sweep reads X_prev, U_prev
     and the active set and writes the hand-off [K | k | H | sparse stage]; the forward sweep reads X_prev, U_prev, the
     hand-off and the active set and writes X, U and the active set.  Everything else (costs, bounds, P, S, G, the
-    Dubins linearisation) stays in registers / shared memory.  582 B at n=4, m=2.  Flops: the dense Riccati count of
+    Dubins linearisation) stays in registers / shared memory.  486 B at n=4, m=2 (10 of the 14 sparse-stage entries and
+    the off-diagonal of H are handed over; the rest is rebuilt from the particle's parameters / folded into k).  Flops: the dense Riccati count of
     SURVEY.md 8(d) (the sparse Dubins stage needs fewer; the figure is an upper bound on useful work)."""
     passes = info["polish_passes"].astype(np.float64)
     I = (info["admm_iters"] + info["polish_passes"]).astype(np.float64)
-    handoff = n * m + m + m * (m + 1) // 2 + nlin
+    handoff = n * m + m + m * (m - 1) // 2 + nlin  # K, k, off-diagonals of H, sparse stage
     b_pass = 8 * (3 * (n + m) + 2 * handoff) + 3 * m
     f_fac = 4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0
     f_vec = 6 * n * n + 8 * n * m + 2 * m * m
@@ -307,7 +308,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scp_kernel<4,2,grouped>",
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,
-                "model": "fused two-sweep pass: 582 B per (particle, stage, pass) = X_prev,U_prev,act in; K,k,H,sparse stage "
+                "model": "fused two-sweep pass: 486 B per (particle, stage, pass) = X_prev,U_prev,act in; K,k,H01,sparse stage "
                          "out+in; X,U,act out (DESIGN.md 5)",
                 "fp64_tflops_dense_equivalent": aflops / (kernel_ms * 1e-3) / 1e12,
                 "unfused_streaming_model_bytes_per_launch": survey_streaming_bytes(info)}

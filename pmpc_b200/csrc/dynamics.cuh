@@ -92,4 +92,26 @@ __device__ __forceinline__ void dubins_f_fx_fu(const double* x, const double* u,
   fu[6] = 0.0;       fu[7] = -ws * T;
 }
 
+// The entries of the sparse Dubins stage (fused.inl: lin_sparse) that need neither sin/cos nor the series:
+// b20 = fu[4], b31 = fu[7], and the affine terms of the speed / heading rows  c2 = f2 - b20 u0 [- v0],
+// c3 = f3 - b31 u1 [- th]  (the bracketed part for stages j >= 1 only), evaluated exactly as dubins_f_fx_fu and
+// lin_sparse evaluate them, so that the forward sweep can rebuild them instead of reading them from HBM.
+__device__ __forceinline__ void dubins_cheap_entries(const double* x, const double* u, double vs, double ws, double T, double eps,
+                                                     bool has_a, double* b20, double* b31, double* c2, double* c3) {
+  double b = vs * u[0];
+  double a = ws * (-u[1]);
+  b += (b >= 0.0) ? eps : -eps;
+  a += (a >= 0.0) ? eps : -eps;
+  const double f2 = x[2] + T * b, f3 = T * a + x[3];
+  *b20 = vs * T;
+  *b31 = -ws * T;
+  double v2 = f2 - (*b20) * u[0], v3 = f3 - (*b31) * u[1];
+  if (has_a) {
+    v2 -= x[2];
+    v3 -= x[3];
+  }
+  *c2 = v2;
+  *c3 = v3;
+}
+
 }  // namespace pmpc

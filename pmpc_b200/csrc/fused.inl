@@ -27,9 +27,14 @@
   static constexpr int DEPTH = PMPC_DEPTH;
   // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | (L) | act]
   static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_K = R_UP + NU * 32, R_KF = R_K + NU * NX * 32,
-                       R_H = R_KF + NU * 32, R_LIN = R_H + NR * 32, R_ACTF = R_LIN + ((NX == 4 && NU == 2) ? 14 * 32 : 0),
+                       R_H = R_KF + NU * 32, R_LIN = R_H + (NR - NU) * 32, R_ACTF = R_LIN + ((NX == 4 && NU == 2) ? 10 * 32 : 0),
                        R_ACTB = R_UP + NU * 32;
   static constexpr int SLOT = R_ACTF + NU * 4;
+  // Of the stage Hessian H only the strictly-upper triangle is handed to the forward sweep: a fixed control's multiplier
+  // is h0 + G x + H u, and the part of H u that multiplies FIXED controls (its own diagonal entry included) is known in
+  // the backward sweep and folded into the k-slot there (h = h0 + H ufix); the free controls need the off-diagonals.
+  static constexpr int NHO = NR - NU;
+  __host__ __device__ static constexpr int pko(int a, int b) { return a * NU - (a * (a + 1)) / 2 + (b - a - 1); }  // a < b
   // uniform cost table row: [Qs | Rs | qref | rref | xref | uref | lu | uu]
   static constexpr int T_QS = 0, T_RS = T_QS + NQ, T_QR = T_RS + NR, T_RR = T_QR + NX, T_XR = T_RR + NU,
                        T_UR = T_XR + NX, T_LU = T_UR + NU, T_UU = T_LU + NU, TW = T_UU + NU;
@@ -163,6 +168,10 @@
   // from the backward to the forward sweep through HBM + the TMA ring, so the forward sweep does not
   // evaluate the dynamics again.  Stage 0 has A = 0 (lqp_utils.jl:288-296): its n-entries are unused.
   static constexpr int NLIN = 14;
+  // handed through HBM: 10 of the 14 — b20 = v_scale T and b31 = -w_scale T are constants of the particle, and c2, c3
+  // (the affine terms of the speed and heading rows) need no trigonometry: the forward sweep rebuilds the four from
+  // the particle's parameters and the linearisation point (hand index h -> L index h < 8 ? h : h + 2)
+  static constexpr int NLINH = 10;
   static constexpr bool CAN_SPARSE = (NX == 4 && NU == 2);
   __device__ __forceinline__ static void lin_sparse(const DevProb& pb, int j, const double* xm1, const double* ub,
                                                     const double* dp, double* L) {
@@ -268,17 +277,17 @@
     double* dst = sm.ring + sl * SLOT;
     uint64_t* bar = sm.bars + sl;
     const FactorSet& F = pb.fs[MODE_POLISH];
-    uint32_t bytes = (NX + NU) * 256 + (SPD ? NLIN * 256 : 0);
-    if (jj >= Nc) bytes += (NU * NX + NU) * 256 + (UBOX ? NR * 256 + NU * 32 : 0);
+    uint32_t bytes = (NX + NU) * 256 + (SPD ? NLINH * 256 : 0);
+    if (jj >= Nc) bytes += (NU * NX + NU) * 256 + (UBOX ? NHO * 256 + NU * 32 : 0);
     mbar_expect_tx(bar, bytes);
     bulk_g2s(dst + R_XP, blk(Xpv, jj, NX, wb), NX * 256, bar);
     bulk_g2s(dst + R_UP, blk(Upv, jj, NU, wb), NU * 256, bar);
-    if (SPD) bulk_g2s(dst + R_LIN, blk(pb.lin, jj, NLIN, wb), NLIN * 256, bar);
+    if (SPD) bulk_g2s(dst + R_LIN, blk(pb.lin, jj, NLINH, wb), NLINH * 256, bar);
     if (jj >= Nc) {
       bulk_g2s(dst + R_K, blk(F.K, jj, NU * NX, wb), NU * NX * 256, bar);
       bulk_g2s(dst + R_KF, blk(pb.kff, jj, NU, wb), NU * 256, bar);
       if (UBOX) {
-        bulk_g2s(dst + R_H, blk(pb.Hs, jj, NR, wb), NR * 256, bar);
+        if (NHO > 0) bulk_g2s(dst + R_H, blk(pb.Hs, jj, NHO, wb), NHO * 256, bar);
         bulk_g2s(dst + R_ACTF, blk(pb.act, jj, NU, wb), NU * 32, bar);
       }
     }
@@ -384,7 +393,7 @@
         lin_sparse(pb, j, xm1, ub, dp, L);
         if (valid) {
 #pragma unroll
-          for (int e = 0; e < NLIN; ++e) at(pb.lin, j, NLIN, e) = L[e];
+          for (int e = 0; e < NLINH; ++e) at(pb.lin, j, NLINH, e) = L[e < 8 ? e : e + 2];
         }
 #pragma unroll
         for (int e = 0; e < NX; ++e) cv[e] = L[10 + e];
@@ -666,13 +675,13 @@
           for (int a = 0; a < NU; ++a) {
 #pragma unroll UNR
             for (int t = 0; t < NX; ++t) at(F.K, j, NU * NX, a * NX + t) = (UBOX && fixed[a]) ? G[a * NX + t] : K[a * NX + t];
-            at(pb.kff, j, NU, a) = (UBOX && fixed[a]) ? h0[a] : kv[a];
+            at(pb.kff, j, NU, a) = (UBOX && fixed[a]) ? h[a] : kv[a];  // h = h0 + H ufix
           }
           if (UBOX) {
 #pragma unroll UNR
             for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
-              for (int b = a; b < NU; ++b) at(pb.Hs, j, NR, pk(a, b, NU)) = H[a * NU + b];
+              for (int b = a + 1; b < NU; ++b) at(pb.Hs, j, NHO, pko(a, b)) = H[a * NU + b];
           }
           if (SLEW) {
 #pragma unroll UNR
@@ -774,7 +783,7 @@
            gscale = 1.0, zscale = 1.0;
     const double rdiag = pb.rdiag0[g];
     for (int j = 0; j < N; ++j) {
-      double ub[NU], xpj[NX], Kj[NU * NX], kf[NU], Hj[NR], u[NU], xn[NX], L[NLIN];
+      double ub[NU], xpj[NX], Kj[NU * NX], kf[NU], Hj[NHO > 0 ? NHO : 1], u[NU], xn[NX], L[NLIN];
       signed char act[NU];
 #pragma unroll UNR
       for (int t = 0; t < NU; ++t) act[t] = 0;
@@ -788,7 +797,7 @@
         for (int e = 0; e < NU; ++e) ub[e] = b[R_UP + e * 32];
         if (SPD) {
 #pragma unroll
-          for (int e = 0; e < NLIN; ++e) L[e] = b[R_LIN + e * 32];
+          for (int e = 0; e < NLINH; ++e) L[e < 8 ? e : e + 2] = b[R_LIN + e * 32];
         }
         if (j >= Nc) {
 #pragma unroll UNR
@@ -797,7 +806,7 @@
           for (int e = 0; e < NU; ++e) kf[e] = b[R_KF + e * 32];
           if (UBOX) {
 #pragma unroll UNR
-            for (int e = 0; e < NR; ++e) Hj[e] = b[R_H + e * 32];
+            for (int e = 0; e < NHO; ++e) Hj[e] = b[R_H + e * 32];
             const signed char* ab = reinterpret_cast<const signed char*>(sm.ring + sl * SLOT + R_ACTF) + col;
 #pragma unroll UNR
             for (int t = 0; t < NU; ++t) act[t] = (ALG == 0) ? ab[t * 32] : 0;
@@ -811,7 +820,7 @@
         for (int e = 0; e < NU; ++e) ub[e] = ld(Upv, j, NU, e);
         if (SPD) {
 #pragma unroll
-          for (int e = 0; e < NLIN; ++e) L[e] = ld(pb.lin, j, NLIN, e);
+          for (int e = 0; e < NLINH; ++e) L[e < 8 ? e : e + 2] = ld(pb.lin, j, NLINH, e);
         }
         if (j >= Nc) {
 #pragma unroll UNR
@@ -820,11 +829,14 @@
           for (int e = 0; e < NU; ++e) kf[e] = ld(pb.kff, j, NU, e);
           if (UBOX) {
 #pragma unroll UNR
-            for (int e = 0; e < NR; ++e) Hj[e] = ld(pb.Hs, j, NR, e);
+            for (int e = 0; e < NHO; ++e) Hj[e] = ld(pb.Hs, j, NHO, e);
 #pragma unroll UNR
             for (int t = 0; t < NU; ++t) act[t] = (ALG == 0) ? pb.act[ix(j, NU, t)] : 0;
           }
         }
+      }
+      if constexpr (SPD) {  // the four entries of the sparse stage that are not handed over (dynamics.cuh)
+        dubins_cheap_entries(xm1, ub, dp[0], dp[1], dp[2], pb.dyn_eps, j >= 1, &L[8], &L[9], &L[12], &L[13]);
       }
       double lo[NU], hi[NU];
       if (UBOX) {
@@ -869,10 +881,11 @@
             const double ua = u[a];
             signed char na = 0;
             if (act[a] != 0) {
-              // dQ/du_a = H[a,:] u + G[a,:] x + h0[a] - s u_{j-1,a}
+              // dQ/du_a = H[a,:] u + G[a,:] x + h0[a] - s u_{j-1,a};  kf[a] already holds h0[a] + H[a, fixed] u_fixed
               double acc = kf[a] + gx[a];
 #pragma unroll UNR
-              for (int b = 0; b < NU; ++b) acc += Hj[a <= b ? pk(a, b, NU) : pk(b, a, NU)] * u[b];
+              for (int b = 0; b < NU; ++b)
+                if (b != a && act[b] == 0) acc += Hj[a < b ? pko(a, b) : pko(b, a)] * u[b];
               if (SLEW && j >= 1) acc -= s * up[a];
               const double mu = -acc;
               if (act[a] > 0) {
