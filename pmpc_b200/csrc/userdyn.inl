@@ -61,6 +61,12 @@ static Nvrtc* nvrtc() {
 // pack_lin_kernel: A_j = fx_j (A_0 = 0), B_j = fu_j, c_j = f_j - fu_j ubar_j - fx_j xbar_{j-1}
 // (lqp_utils.jl:231-300; no fx term at stage 0: linearised at x0 itself, lqp_utils.jl:288-296).
 static const char* kUserWrapper = R"SRC(
+// trampoline with prefixed parameter names: the user's function may be called `f`, `x`, `c`, ... without being shadowed
+// by the wrapper kernel's own identifiers
+__device__ __forceinline__ void pmpc_call_user_(const double* pmpc_a0_, const double* pmpc_a1_, const double* pmpc_a2_,
+                                                double* pmpc_a3_, double* pmpc_a4_, double* pmpc_a5_) {
+  PMPC_USER_FN(pmpc_a0_, pmpc_a1_, pmpc_a2_, pmpc_a3_, pmpc_a4_, pmpc_a5_);
+}
 extern "C" __global__ void pmpc_user_linearize(
     const double* __restrict__ x0, const double* __restrict__ Xp, const double* __restrict__ Up,
     const double* __restrict__ prm, double* __restrict__ A, double* __restrict__ Bm, double* __restrict__ c,
@@ -82,7 +88,7 @@ extern "C" __global__ void pmpc_user_linearize(
   for (int e = 0; e < PMPC_N; ++e) f[e] = 0.0;
   for (int e = 0; e < PMPC_N * PMPC_N; ++e) fx[e] = 0.0;
   for (int e = 0; e < PMPC_N * PMPC_M; ++e) fu[e] = 0.0;
-  PMPC_USER_FN(x, u, p, f, fx, fu);
+  pmpc_call_user_(x, u, p, f, fx, fu);
   for (int r = 0; r < PMPC_NX; ++r) {
     double cv = (r < PMPC_N) ? f[r] : 0.0;
     for (int t = 0; t < PMPC_NX; ++t) {

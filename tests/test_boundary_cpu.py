@@ -200,3 +200,44 @@ def test_outer_loop_variants_keep_the_reference_signatures():
     tune = inspect.signature(pmpc_b200.tune_scp).parameters
     assert tune["sample_nb"].default == 14 and tune["reg_rng"].default == (-3, 3) and "savefig" in tune
     assert pmpc_b200.accelerated.momentum_update(np.ones(2), np.zeros(2), 3) == pytest.approx(1.6 * np.ones(2))
+
+
+def test_user_dynamics_wrapper_compiles_for_sm100a_without_a_gpu():
+    """The NVRTC path of pmpc_register_dynamics, as far as it goes without a device: the wrapper kernel of
+    csrc/userdyn.inl around a user function — deliberately named `f`, like the wrapper's own output array — compiles to an
+    sm_100a cubin that exports `pmpc_user_linearize`; a broken source yields a log naming the user's file."""
+    try:
+        rt = ctypes.CDLL("libnvrtc.so.12")
+    except OSError:
+        pytest.skip("libnvrtc.so.12 not available")
+    src = open(os.path.join(ROOT, "pmpc_b200", "csrc", "userdyn.inl")).read()
+    wrapper = src[src.index('R"SRC(') + 6:src.index(')SRC";')]
+    head = "#define PMPC_N 2\n#define PMPC_M 1\n#define PMPC_NX 2\n#define PMPC_NU 1\n#define PMPC_NP 1\n#define PMPC_USER_FN f\n#line 1 \"user_dynamics.cu\"\n"
+    good = ("__device__ void f(const double* x, const double* u, const double* p, double* f, double* fx, double* fu) {"
+            " f[0] = x[0] + p[0] * x[1]; f[1] = x[1] + p[0] * (u[0] - sin(x[0])); fx[0] = 1; fx[1] = p[0];"
+            " fx[2] = -p[0] * cos(x[0]); fx[3] = 1; fu[1] = p[0]; }")
+
+    def compile_(user):
+        prog = ctypes.c_void_p()
+        full = head + user + "\n#line 1 \"pmpc_user_wrapper.cu\"\n" + wrapper
+        assert rt.nvrtcCreateProgram(ctypes.byref(prog), full.encode(), b"pmpc_user.cu", 0, None, None) == 0
+        opts = (ctypes.c_char_p * 3)(b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device")
+        rc = rt.nvrtcCompileProgram(prog, 3, opts)
+        n = ctypes.c_size_t()
+        rt.nvrtcGetProgramLogSize(prog, ctypes.byref(n))
+        log = ctypes.create_string_buffer(max(n.value, 1))
+        rt.nvrtcGetProgramLog(prog, log)
+        cubin = b""
+        if rc == 0:
+            rt.nvrtcGetCUBINSize(prog, ctypes.byref(n))
+            buf = ctypes.create_string_buffer(n.value)
+            rt.nvrtcGetCUBIN(prog, buf)
+            cubin = buf.raw
+        rt.nvrtcDestroyProgram(ctypes.byref(prog))
+        return rc, log.value.decode(), cubin
+
+    rc, log, cubin = compile_(good)
+    assert rc == 0, log
+    assert b"pmpc_user_linearize" in cubin and cubin[:4] == b"\x7fELF"
+    rc, log, _ = compile_(good.replace("sin(x[0])", "undeclared_symbol"))
+    assert rc != 0 and "user_dynamics.cu" in log and "undeclared_symbol" in log
