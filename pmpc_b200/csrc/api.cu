@@ -404,7 +404,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
     want(&F.Pc, NX * NX * P); want(&F.Wc, NX * NU * P); want(&F.Zc, NU * NU * P);
     want(&F.Hc, B * D * D + 1); want(&F.Hci, B * D * D + 1); want(&F.hb, B * D + 1);
   }
-  want(&pb.kff, Nn * NU * P); want(&pb.Hs, Nn * (NR - NU) * P + 32); want(&pb.lin, (NX == 4 && NU == 2) ? Nn * 10 * P : 32); want(&pb.X, Nn * NX * P); want(&pb.U, Nn * NU * P);
+  want(&pb.kff, Nn * NU * P); want(&pb.hand, Nn * (((NX == 4 && NU == 2) ? 10 : 0) + NU * NX + NU + (NR - NU)) * P); want(&pb.X, Nn * NX * P); want(&pb.U, Nn * NU * P);
   want(&pb.wu, Nn * NU * P); want(&pb.yu, Nn * NU * P); want(&pb.wx, Nn * NX * P); want(&pb.yx, Nn * NX * P);
   want(&pb.gc, B * D + 1); want(&pb.uc, B * D + 1); want(&pb.muc, B * D + 1);
   want(&pb.scratch, B * pb.scratch_stride);

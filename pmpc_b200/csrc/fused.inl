@@ -26,8 +26,12 @@
 #endif
   static constexpr int DEPTH = PMPC_DEPTH;
   // ring slot layout (doubles): backward sweep [Xp | Up | act], forward sweep [Xp | Up | K | k | H | (L) | act]
-  static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_K = R_UP + NU * 32, R_KF = R_K + NU * NX * 32,
-                       R_H = R_KF + NU * 32, R_LIN = R_H + (NR - NU) * 32, R_ACTF = R_LIN + ((NX == 4 && NU == 2) ? 10 * 32 : 0),
+  // hand-off block of one stage, ONE array `pb.hand` with NH rows per (warp tile, stage) so that a single bulk copy brings
+  // it in: [sparse stage (HL rows, Dubins shapes only) | K (NU*NX) | k (NU) | H01 (NR-NU)]
+  static constexpr int HL = (NX == 4 && NU == 2) ? 10 : 0;
+  static constexpr int H_LIN = 0, H_K = HL, H_KF = H_K + NU * NX, H_H = H_KF + NU, NH = H_H + (NR - NU);
+  static constexpr int R_XP = 0, R_UP = R_XP + NX * 32, R_HAND = R_UP + NU * 32, R_LIN = R_HAND + H_LIN * 32,
+                       R_K = R_HAND + H_K * 32, R_KF = R_HAND + H_KF * 32, R_H = R_HAND + H_H * 32, R_ACTF = R_HAND + NH * 32,
                        R_ACTB = R_UP + NU * 32;
   static constexpr int SLOT = R_ACTF + NU * 4;
   // Of the stage Hessian H only the strictly-upper triangle is handed to the forward sweep: a fixed control's multiplier
@@ -277,20 +281,15 @@
     double* dst = sm.ring + sl * SLOT;
     uint64_t* bar = sm.bars + sl;
     const FactorSet& F = pb.fs[MODE_POLISH];
-    uint32_t bytes = (NX + NU) * 256 + (SPD ? NLINH * 256 : 0);
-    if (jj >= Nc) bytes += (NU * NX + NU) * 256 + (UBOX ? NHO * 256 + NU * 32 : 0);
+    // rows of the hand-off block this stage needs: the sparse stage on every stage (SPD), K | k | H01 on the free ones
+    const int r0 = SPD ? 0 : H_K, r1 = (jj >= Nc) ? NH : (SPD ? H_K : 0);
+    uint32_t bytes = (NX + NU) * 256 + (r1 > r0 ? (r1 - r0) * 256 : 0);
+    if (jj >= Nc && UBOX) bytes += NU * 32;
     mbar_expect_tx(bar, bytes);
     bulk_g2s(dst + R_XP, blk(Xpv, jj, NX, wb), NX * 256, bar);
     bulk_g2s(dst + R_UP, blk(Upv, jj, NU, wb), NU * 256, bar);
-    if (SPD) bulk_g2s(dst + R_LIN, blk(pb.lin, jj, NLINH, wb), NLINH * 256, bar);
-    if (jj >= Nc) {
-      bulk_g2s(dst + R_K, blk(F.K, jj, NU * NX, wb), NU * NX * 256, bar);
-      bulk_g2s(dst + R_KF, blk(pb.kff, jj, NU, wb), NU * 256, bar);
-      if (UBOX) {
-        if (NHO > 0) bulk_g2s(dst + R_H, blk(pb.Hs, jj, NHO, wb), NHO * 256, bar);
-        bulk_g2s(dst + R_ACTF, blk(pb.act, jj, NU, wb), NU * 32, bar);
-      }
-    }
+    if (r1 > r0) bulk_g2s(dst + R_HAND + r0 * 32, blk(pb.hand, jj, NH, wb) + r0 * 32, (r1 - r0) * 256, bar);
+    if (jj >= Nc && UBOX) bulk_g2s(dst + R_ACTF, blk(pb.act, jj, NU, wb), NU * 32, bar);
   }
 
   // Backward sweep over the stages j = N-1 .. (first ? 0 : Nc).  Free stages (j >= Nc): masked
@@ -393,7 +392,7 @@
         lin_sparse(pb, j, xm1, ub, dp, L);
         if (valid) {
 #pragma unroll
-          for (int e = 0; e < NLINH; ++e) at(pb.lin, j, NLINH, e) = L[e < 8 ? e : e + 2];
+          for (int e = 0; e < NLINH; ++e) at(pb.hand, j, NH, H_LIN + e) = L[e < 8 ? e : e + 2];
         }
 #pragma unroll
         for (int e = 0; e < NX; ++e) cv[e] = L[10 + e];
@@ -674,14 +673,14 @@
 #pragma unroll UNR
           for (int a = 0; a < NU; ++a) {
 #pragma unroll UNR
-            for (int t = 0; t < NX; ++t) at(F.K, j, NU * NX, a * NX + t) = (UBOX && fixed[a]) ? G[a * NX + t] : K[a * NX + t];
-            at(pb.kff, j, NU, a) = (UBOX && fixed[a]) ? h[a] : kv[a];  // h = h0 + H ufix
+            for (int t = 0; t < NX; ++t) at(pb.hand, j, NH, H_K + a * NX + t) = (UBOX && fixed[a]) ? G[a * NX + t] : K[a * NX + t];
+            at(pb.hand, j, NH, H_KF + a) = (UBOX && fixed[a]) ? h[a] : kv[a];  // h = h0 + H ufix
           }
           if (UBOX) {
 #pragma unroll UNR
             for (int a = 0; a < NU; ++a)
 #pragma unroll UNR
-              for (int b = a + 1; b < NU; ++b) at(pb.Hs, j, NHO, pko(a, b)) = H[a * NU + b];
+              for (int b = a + 1; b < NU; ++b) at(pb.hand, j, NH, H_H + pko(a, b)) = H[a * NU + b];
           }
           if (SLEW) {
 #pragma unroll UNR
@@ -820,16 +819,16 @@
         for (int e = 0; e < NU; ++e) ub[e] = ld(Upv, j, NU, e);
         if (SPD) {
 #pragma unroll
-          for (int e = 0; e < NLINH; ++e) L[e < 8 ? e : e + 2] = ld(pb.lin, j, NLINH, e);
+          for (int e = 0; e < NLINH; ++e) L[e < 8 ? e : e + 2] = ld(pb.hand, j, NH, H_LIN + e);
         }
         if (j >= Nc) {
 #pragma unroll UNR
-          for (int e = 0; e < NU * NX; ++e) Kj[e] = ld(F.K, j, NU * NX, e);
+          for (int e = 0; e < NU * NX; ++e) Kj[e] = ld(pb.hand, j, NH, H_K + e);
 #pragma unroll UNR
-          for (int e = 0; e < NU; ++e) kf[e] = ld(pb.kff, j, NU, e);
+          for (int e = 0; e < NU; ++e) kf[e] = ld(pb.hand, j, NH, H_KF + e);
           if (UBOX) {
 #pragma unroll UNR
-            for (int e = 0; e < NHO; ++e) Hj[e] = ld(pb.Hs, j, NHO, e);
+            for (int e = 0; e < NHO; ++e) Hj[e] = ld(pb.hand, j, NH, H_H + e);
 #pragma unroll UNR
             for (int t = 0; t < NU; ++t) act[t] = (ALG == 0) ? pb.act[ix(j, NU, t)] : 0;
           }
@@ -962,7 +961,7 @@
         zscale = fmax(zscale, fabs(xn[r]));
         gscale = fmax(gscale, fabs(qr[r] + pb.reg_x * xpj[r]));
       }
-      dxm = fmax(dxm, sqrt(n2));
+      dxm = fmax(dxm, n2);  // squared per-stage norms; one sqrt after the sweep (sqrt is monotone and correctly rounded)
       n2 = 0.0;
 #pragma unroll UNR
       for (int t = 0; t < NU; ++t) {
@@ -973,7 +972,7 @@
         zscale = fmax(zscale, fabs(u[t]));
         gscale = fmax(gscale, fabs(rr_[t] + pb.reg_u * ub[t]));
       }
-      dum = fmax(dum, sqrt(n2));
+      dum = fmax(dum, n2);
 #pragma unroll UNR
       for (int r = 0; r < NX; ++r) {
         double acc = 0.0;
@@ -999,8 +998,8 @@
     }
     if (use_ring) fence_proxy_async();  // X, U, act written above are bulk-copied by the next sweep
     this->rcount = rcount;
-    st[ST_DX] = valid ? dxm : 0.0;
-    st[ST_DU] = valid ? dum : 0.0;
+    st[ST_DX] = valid ? sqrt(dxm) : 0.0;
+    st[ST_DU] = valid ? sqrt(dum) : 0.0;
     st[ST_OBJ] = valid ? obj : 0.0;
     st[ST_NAN] = nanf;
     st[ST_KKT] = kkt_v; st[ST_UVIOL] = uviol; st[ST_XVIOL] = xviol; st[ST_CHANGED] = valid ? changed : 0.0;

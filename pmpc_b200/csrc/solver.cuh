@@ -50,8 +50,7 @@ struct DevProb {
   double *Xp, *Up, *A, *Bm, *c, *q, *r;
   FactorSet fs[2];            // [MODE_POLISH], [MODE_ADMM]
   double *kff, *X, *U;
-  double *Hs;                 // fused path: stage Hessian H of the Q-function (packed), for the multipliers
-  double *lin;                // lean Dubins variant: sparse stage [N2 | B | c] (14 doubles) handed from bsweep to fsweep
+  double *hand;               // fused path: per-stage hand-off block [sparse stage | K | k | H01] from bsweep to fsweep (fused.inl)
   double *wu, *yu, *wx, *yx;
   signed char *act, *actn;    // per (particle, stage, control): -1 lower, +1 upper, 0 free
   // per problem
