@@ -508,3 +508,59 @@ def test_extreme_shapes_properties(gpu, M, N, Nc):
     assert max(sd["kkt"] for sd in data["solver_data"]) < 1e-8
     f, _, _ = car(X[:, :-1], U)
     assert np.abs(f - X[:, 1:]).max() < 1e-6
+
+
+def test_random_shape_sweep_qp_parity(gpu):
+    """Seeded sweep over problem shapes the fixed CASES do not hit (odd particle counts around the warp size, every
+    compiled kernel shape via zero-padding, Nc from 0 to N, slew on / off, box on / off): one convex sub-problem through
+    the C ABI against the exact oracle, 1e-8."""
+    rng = np.random.default_rng(2026)
+    worst = 0.0
+    for trial in range(24):
+        n = int(rng.integers(1, 7)); m = int(rng.integers(1, min(n, 3) + 1))
+        M = int(rng.choice([1, 2, 3, 7, 31, 32, 33, 65])); N = int(rng.integers(1, 9))
+        Nc = int(rng.choice([-1, 0, 1, 2, N])); Nc = min(Nc, N)
+        slew = bool(rng.integers(0, 2)); box = [None, 0.15, 0.4][int(rng.integers(0, 3))]
+        args, kw = rand_problem(rng, M, N, n, m, slew, box, None, per_particle_slew=False)
+        if slew:
+            kw["slew_reg0"] = np.full(M, float(rng.uniform(0.3, 1.2)))  # the Python path broadcasts one scalar
+        Xo, Uo, _ = lqp.lqp_solve(*args, Nc=Nc, **kw)
+        X, U = _aff(args, kw, Nc)
+        err = max(np.abs(X - Xo).max(), np.abs(U - Uo).max())
+        worst = max(worst, err)
+        assert err < 1e-8, (trial, (M, N, n, m, Nc, slew, box), err)
+    assert worst < 1e-8
+
+
+def test_full_size_c3_batch_properties(gpu):
+    """BASELINE config 3 at its full per-problem size (N=30, M=16, Nc=1), 1024 of the 16384 problems in one launch
+    (two particle-problems' worth of idle lanes per warp: M=16 in 32-lane tiles): status, stop rule, consensus, box,
+    nonlinear-dynamics fixed point; three problems re-solved individually must agree bit for bit."""
+    B = 1024
+    d, p = config_c3(B=B)
+    args = dict(X_ref=d["X_ref"], U_ref=d["U_ref"], X_prev=d["X_prev"], U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"],
+                max_it=d["max_it"], res_tol=d["res_tol"], reg_x=d["reg_x"], reg_u=d["reg_u"], slew_rate=0.0, Nc=1)
+    X, U, info, ds = pmpc_b200.solve_batch(p, np.ascontiguousarray(d["Q"]), np.ascontiguousarray(d["R"]), d["x0"], **args)
+    assert (info["status"] == 0).all() and (info["scp_iters"] < d["max_it"]).all()
+    assert np.all(U[:, :, :1] == U[:, :1, :1]) and np.abs(U).max() <= 1 + 1e-12 and np.isfinite(X).all()
+    for b in (0, 511, 1023):
+        car = DubinsCar(p[b])
+        f, _, _ = car(X[b, :, :-1], U[b])
+        assert np.abs(f - X[b, :, 1:]).max() < 1e-4
+        X1, U1, data = pmpc_b200.solve(car, d["Q"][b], d["R"][b], d["x0"][b], X_ref=d["X_ref"][b], U_ref=d["U_ref"][b],
+                                       X_prev=d["X_prev"][b], U_prev=d["U_prev"][b], u_l=d["u_l"][b], u_u=d["u_u"][b],
+                                       max_it=d["max_it"], res_tol=d["res_tol"], reg_x=d["reg_x"], reg_u=d["reg_u"],
+                                       solver_settings=d["solver_settings"])
+        assert np.array_equal(X1, X[b]) and np.array_equal(U1, U[b]) and len(data["hist"]) == info["scp_iters"][b]
+
+
+def test_full_size_c4_properties(gpu):
+    """BASELINE config 4 at full size (n=12, m=4, N=100, M=64, slew, control and state boxes, Nc=1): the LTV system is
+    exactly linear, so the solution must satisfy the dynamics to rounding; consensus, boxes, device KKT certificate."""
+    d, A, Bm = config_c4()
+    X, U, data = pmpc_b200.solve(LTV(A, Bm), **d)
+    assert data["device"]["status"] == 0 and data["hist"][-1]["resid"] < 1e-6
+    f = np.einsum("mjrt,mjt->mjr", A, X[:, :-1]) + np.einsum("mjrt,mjt->mjr", Bm, U)
+    assert np.abs(f - X[:, 1:]).max() < 1e-12
+    assert np.all(U[:, :1] == U[:1, :1]) and np.abs(U).max() <= 1 + 1e-12 and np.abs(X).max() <= 20 + 1e-9
+    assert max(sd["kkt"] for sd in data["solver_data"]) < 1e-8
