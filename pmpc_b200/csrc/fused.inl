@@ -280,7 +280,6 @@
                                                  size_t wb, int Nc) {
     double* dst = sm.ring + sl * SLOT;
     uint64_t* bar = sm.bars + sl;
-    const FactorSet& F = pb.fs[MODE_POLISH];
     // rows of the hand-off block this stage needs: the sparse stage on every stage (SPD), K | k | H01 on the free ones
     const int r0 = SPD ? 0 : H_K, r1 = (jj >= Nc) ? NH : (SPD ? H_K : 0);
     uint32_t bytes = (NX + NU) * 256 + (r1 > r0 ? (r1 - r0) * 256 : 0);

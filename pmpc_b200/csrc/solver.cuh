@@ -150,7 +150,10 @@ template <int NX, int NU, bool GROUPED>
 struct Solver {
   static constexpr int NQ = NX * (NX + 1) / 2;
   static constexpr int NR = NU * (NU + 1) / 2;
-  static constexpr int UNR = (NX <= 4) ? 64 : 1;  // full unroll keeps small systems in registers
+  // inner-loop unroll factor: full unroll keeps small systems in registers; for the larger shapes (per-thread matrices
+  // in local memory) it turns the dynamic indices into constant offsets and lets the loads pipeline — C4 (n = 12):
+  // 1.53 s without unrolling, 0.45 s at 8, 0.21 s fully unrolled; bounded above by compile time and code size
+  static constexpr int UNR = (NX <= 4) ? 64 : (NX <= 12 ? 16 : (NX <= 16 ? 8 : 4));
 
   const DevProb& pb;
   const size_t P;
