@@ -215,7 +215,7 @@ def main():
                     help="independent C2 problems per GPU per step (0 = --waves full waves: SMs x resident CTAs per SM x waves)")
     ap.add_argument("--waves", type=int, default=8)
     ap.add_argument("--latency-solves", type=int, default=200)
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="sub-batches of the pipelined end-to-end leg (1 = no pipelining; default = one wave each)")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="sub-batches of the pipelined end-to-end leg (1 = no pipelining; default = half a wave each: kernels of consecutive sub-batches co-reside)")
     ap.add_argument("--cpu-sample-its", type=int, default=16)
     ap.add_argument("--ref-sample-its", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
