@@ -37,12 +37,14 @@ if "c3" in which:
     Q, R = np.ascontiguousarray(d["Q"]), np.ascontiguousarray(d["R"])
     st = {}
     def run():
-        X, U, info, ds = pmpc_b200.solve_batch(p, Q, R, d["x0"], solver=st.get("ds"), reuse_buffers=True, **args)
+        X, U, info, ds = pmpc_b200.solve_batch(p, Q, R, d["x0"], solver=st.get("ds"), reuse_buffers=True,
+                                               chunks=int(os.environ.get("C3_CHUNKS", 16)), **args)
         st["ds"] = ds
         return X, U, info, ds
     t, (X, U, info, ds) = timed(run, 3)
     print(json.dumps(dict(config="C3 %d independent Dubins problems N=30 M=16 Nc=1" % B, e2e_s=t, solves_per_s=B / t,
                           kernel_ms=ds.last_kernel_ms(), device_solves_per_s=B / (ds.last_kernel_ms() * 1e-3),
+                          chunks=int(os.environ.get("C3_CHUNKS", 16)),
                           scp_iters=[int(info["scp_iters"].min()), float(info["scp_iters"].mean()), int(info["scp_iters"].max())],
                           status_ok=bool((info["status"] == 0).all()), consensus=bool(np.all(U[:, :, 0] == U[:, :1, 0])))), flush=True)
 
