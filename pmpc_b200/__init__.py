@@ -9,7 +9,7 @@ from .scp_mpc import (  # noqa: F401
 )
 from .accelerated import accelerated_scp_solve  # noqa: F401
 from .static_backend import aff_solve, is_precompiled_backend_available, lqp_solve  # noqa: F401
-from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics  # noqa: F401
+from .dynamics import BuiltinDynamics, DubinsCar, LTI, LTV, UserDynamics  # noqa: F401
 from .handle import DeviceSolver  # noqa: F401
 from .batch import solve_batch  # noqa: F401
 from ._lib import PmpcError, pinned_copy, pinned_empty  # noqa: F401

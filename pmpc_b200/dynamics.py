@@ -114,3 +114,17 @@ class LTV(BuiltinDynamics):
         if self.c is not None:
             f = f + self.c
         return f, A, B
+
+
+class LTI(LTV):
+    """Time-invariant special case ``x+ = A x + B u + c`` with ONE ``A (n,n)``, ``B (n,m)`` (optionally per particle:
+    ``(M,n,n)``, ``(M,n,m)``) — broadcast over the horizon; everything else is :class:`LTV`."""
+
+    kind = "ltv"
+
+    def __init__(self, A, B, c=None):
+        A, B = np.asarray(A, np.float64), np.asarray(B, np.float64)
+        if A.ndim not in (2, 3) or B.ndim != A.ndim:
+            raise ValueError("LTI expects A (n,n) / (M,n,n) and B (n,m) / (M,n,m)")
+        lift = (lambda a: a[:, None]) if A.ndim == 3 else (lambda a: a)  # (M,n,n) -> (M,1,n,n): broadcasts over stages
+        super().__init__(lift(A), lift(B), None if c is None else lift(np.asarray(c, np.float64)))

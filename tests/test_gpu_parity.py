@@ -564,3 +564,19 @@ def test_full_size_c4_properties(gpu):
     assert np.abs(f - X[:, 1:]).max() < 1e-12
     assert np.all(U[:, :1] == U[:1, :1]) and np.abs(U).max() <= 1 + 1e-12 and np.abs(X).max() <= 20 + 1e-9
     assert max(sd["kkt"] for sd in data["solver_data"]) < 1e-8
+
+
+def test_lti_device_loop_matches_oracle(gpu):
+    """LTI system (one A, B for the whole horizon; north_star's "LTI/LTV") through the device loop, with consensus, slew and
+    a control box, against the oracle's SCP loop with the same linear model as a plain callable."""
+    rng = np.random.default_rng(8)
+    M, N, n, m = 5, 14, 2, 1
+    A, Bm = np.array([[1.0, 0.1], [0.0, 1.0]]), np.array([[0.005], [0.1]])
+    dyn = pmpc_b200.LTI(A, Bm)
+    d = dict(Q=np.tile(np.eye(n), (M, N, 1, 1)), R=np.tile(0.1 * np.eye(m), (M, N, 1, 1)), x0=np.tile(np.array([3.0, -1.0]), (M, 1)) + 0.2 * rng.standard_normal((M, n)),
+             X_prev=np.zeros((M, N, n)), U_prev=np.zeros((M, N, m)), u_l=-0.5 * np.ones((M, N, m)), u_u=0.5 * np.ones((M, N, m)),
+             reg_x=1.0, reg_u=1e-2, slew_rate=0.2, max_it=60, res_tol=1e-8, solver_settings=dict(solver="osqp", Nc=2))
+    X, U, data = pmpc_b200.solve(dyn, **d)
+    Xo, Uo, do = oscp.scp_solve(lambda X_, U_: dyn(X_, U_), **d)
+    assert len(data["hist"]) == len(do["hist"]) and rel(X, Xo) < 1e-5 and rel(U, Uo) < 1e-5
+    assert np.all(U[:, :2] == U[:1, :2])
