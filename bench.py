@@ -360,7 +360,6 @@ def main():
             t0 = time.perf_counter()
             X1, U1, data1 = pmpc_b200.solve(car, arrs["Q"][0], arrs["R"][0], arrs["x0"][0], **kw)
             dt = time.perf_counter() - t0
-            kw["solver_settings"]["_device_solver"] = data1["device_solver"]
             if i >= 3:
                 lat.append(dt)
 

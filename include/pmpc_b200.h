@@ -53,6 +53,13 @@ void c_lcone_solve(double *X_out, double *U_out, size_t xdim, size_t udim, size_
                    double *slew_reg, double *slew_reg0, double *slew_um1, long long verbose,
                    double smooth_alpha, char *solver);
 
+/* Runtime hooks of the reference's ahead-of-time compiled Julia library (`PMPC.jl/pmpcjl/include/julia_init.h:1-2`),
+ * called by its pybind shim at import (`module.cpp:122-125`).  No-ops here — exported so that the reference's
+ * UNMODIFIED `module.cpp` links against libpmpc_b200.so in place of libPMPC.so + libjulia.so (INTEGRATION.md level 1,
+ * built by oracle/ref_install.sh and exercised by tests/test_reference_dropin.py). */
+void init_julia(int argc, char *argv[]);
+void shutdown_julia(int retcode);
+
 /* ------------------------------------------------------------------------------------------
  * 2. Handle API (the fast path): problem data stays resident in HBM, the whole SCP loop of
  *    `pmpc/scp_mpc.py:337-428` runs on the device for built-in dynamics.
@@ -162,7 +169,7 @@ int pmpc_get_solution(pmpc_handle_t h, double *X, double *U);
 /* Same with X in trajectory form (n,N+1,B*M): stage 0 is x0, what `solve` returns (static_backend.py:311). */
 int pmpc_get_trajectory(pmpc_handle_t h, double *X, double *U);
 /* Per problem b: info[b*8 + k], k = 0 scp_iters, 1 total ADMM iterations, 2 factorisations,
- * 3 polish passes, 4 status (0 ok, 1 NaN failure, 2 ADMM hit max_iter in some QP),
+ * 3 polish passes, 4 status bits (0 ok, 1 NaN failure, 2 ADMM hit max_iter in some QP, 4 sharded exchange timed out),
  * 5 QPs finished by polish, 6 QPs finished by ADMM tolerance, 7 sweeps over the horizon. */
 int pmpc_get_info(pmpc_handle_t h, long long *info);
 /* hist (4, max_it, B): obj, resid, admm_iters(it), kkt_violation of the accepted QP solution. */
@@ -197,6 +204,17 @@ int pmpc_microbench(int device, int kind, double *result);
  * ------------------------------------------------------------------------------------------ */
 int pmpc_comm_export(pmpc_handle_t h, void *ipc_handle_64);
 int pmpc_comm_connect(pmpc_handle_t h, int rank, int world, const void *ipc_handles, size_t M_total);
+/* The same exchange between handles of ONE process (several handles on one device — their kernels run
+ * concurrently on the handles' own streams — or on peer-accessible devices): plain device pointers, no
+ * IPC.  handles[r] is rank r's handle (handles[rank] == h); pmpc_comm_export must have been called on
+ * every one of them (it allocates the exchange buffer).  Launch the solves of all ranks with
+ * pmpc_scp_solve_async before waiting on any of them. */
+int pmpc_comm_connect_local(pmpc_handle_t h, int rank, int world, const pmpc_handle_t *handles,
+                            size_t M_total);
+/* The in-kernel exchange spins on the peers' sequence flags for at most this long (default 30 s); on
+ * expiry the launch is abandoned, status bit 2 (value 4) is set in info[4] and pmpc_sync returns
+ * PMPC_ERR_STATE — a failed rank does not hang the node. */
+int pmpc_comm_set_timeout(pmpc_handle_t h, double seconds);
 
 /* ------------------------------------------------------------------------------------------
  * 3. int-returning variant of the compat entry with explicit settings and statistics.

@@ -80,11 +80,15 @@ _SIG = {
     "pmpc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pmpc_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmpc_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "pmpc_comm_connect_local": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
+    "pmpc_comm_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
     "pmpc_launch_count": (C.c_longlong, []),
     "pmpc_get_occupancy": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pmpc_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pmpc_lqp_solve": (C.c_int, [_DP, _DP, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_longlong] + [_DP] * 14
                        + [C.c_double, C.c_double] + [_DP] * 3 + [C.POINTER(Settings), c_ll_p]),
+    "init_julia": (None, [C.c_int, C.c_void_p]),
+    "shutdown_julia": (None, [C.c_int]),
     "c_lqp_solve": (None, [_DP, _DP, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_longlong] + [_DP] * 14
                     + [C.c_double, C.c_double] + [_DP] * 3 + [C.c_longlong]),
     "c_lcone_solve": (None, [_DP, _DP, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_longlong] + [_DP] * 14

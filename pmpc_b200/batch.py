@@ -21,14 +21,22 @@ def _sig(p: Dict[str, Any]):
         return None
     if any(p.get(k) is not None and p.get(k) != "" for k in ("lin_cost_fn", "extra_cstrs_fns")) or p.get("filter_method", ""):
         return None
+    ss = p.get("solver_settings") or {}
+    # anything `solve` would route to its host loop (scp_mpc.scp_solve: device_ok) is solved by `solve`, one by one
+    if (ss.get("host_loop", False) or p.get("debug", False) or p.get("return_min_viol", False)
+            or float(p.get("time_limit", 1000.0)) < 1000.0):
+        return None
     x0 = np.asarray(p["x0"])
     Q, R = np.asarray(p["Q"]), np.asarray(p["R"])
-    ss = p.get("solver_settings") or {}
     present = tuple(p.get(k) is not None and np.size(p.get(k)) > 0 for k in ("x_l", "x_u", "u_l", "u_u"))
     user = (dyn.src, dyn.fn_name, dyn.params is None) if isinstance(dyn, UserDynamics) else None
-    return (type(dyn).__name__, user, getattr(dyn, "eps", None), x0.ndim, Q.shape, R.shape, ss.get("Nc", -1), ss.get("slew_reg"),
-            float(p.get("reg_x", 1.0)), float(p.get("reg_u", 1e-2)), p.get("slew_rate", 0.0), p.get("u0_slew") is None,
-            present, int(p.get("max_it", 100)), float(p.get("res_tol", 1e-5)))
+    # an LTV model with and one without an affine term must not share a launch (the group's set_ltv call is decided once)
+    affine = (getattr(dyn, "c", None) is None) if isinstance(dyn, LTV) else None
+    b200 = tuple(sorted((ss.get("b200") or {}).items()))  # device solver settings select the kernel's behaviour
+    cone = (str(ss.get("solver", "ecos")).lower(), "smooth_cstr" in ss, "smooth_alpha" in ss)
+    return (type(dyn).__name__, user, affine, b200, cone, getattr(dyn, "eps", None), x0.ndim, Q.shape, R.shape, ss.get("Nc", -1),
+            ss.get("slew_reg"), float(p.get("reg_x", 1.0)), float(p.get("reg_u", 1e-2)), p.get("slew_rate", 0.0),
+            p.get("u0_slew") is None, present, int(p.get("max_it", 100)), float(p.get("res_tol", 1e-5)))
 
 
 def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: Optional[DeviceSolver] = None,
@@ -51,9 +59,14 @@ def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: O
             return default
         return np.stack([np.asarray(v, np.float64).reshape(shape) for v in vals])
 
+    from .scp_mpc import _device_settings, _check_formulation
+
+    _check_formulation(ss, M)
+    settings = dict(settings or {}, **_device_settings(ss))  # solver_settings["b200"], as `solve` honours it
     ds = solver
     if ds is None or (ds.B, ds.M, ds.N, ds.n, ds.m, ds.Nc) != (B, M, N, n, m, Nc):
-        ds = DeviceSolver(M, N, n, m, Nc, B=B, device=device, settings=settings)
+        ds = DeviceSolver(M, N, n, m, Nc, B=B, device=device)
+    ds.set_settings(**settings)
     X_ref, U_ref = stack("X_ref", (M, N, n)), stack("U_ref", (M, N, m))
     slew_rate = p0.get("slew_rate", 0.0)
     ds.set_problem(stack("x0", (M, n)), stack("Q", (M, N, n, n)), stack("R", (M, N, m, m)), X_ref, U_ref,

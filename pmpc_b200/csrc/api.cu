@@ -84,6 +84,8 @@ struct pmpc_handle_s {
   unsigned long long seq = 0;  // exchange sequence base, advanced identically on every rank per launch
   double *lin_f = nullptr, *lin_fx = nullptr, *lin_fu = nullptr;  // reference-layout linearisation
   int* uniform = nullptr;     // per problem: cost / reference / bound data identical for all particles
+  int* xerr = nullptr;        // device flag raised when an in-kernel exchange times out (particle sharding)
+  double* hist = nullptr;     // (4, hist_len, B) iteration history, grown to max_it by pmpc_scp_solve_async
   bool have_problem = false, have_dyn = false, solved = false;
   pmpc_settings settings{};
   float last_ms = 0.f;
@@ -347,6 +349,8 @@ static void apply_settings(pmpc_handle_t h) {
   pb.ring = s.ring;
 }
 
+static void userdyn_free(pmpc_userdyn_s* u);
+
 int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, size_t xdim, size_t udim,
                 long long Nc) {
   if (!out || B < 1 || M < 1 || N < 1 || xdim < 1 || udim < 1) return fail(PMPC_ERR_BAD_ARG, "bad sizes");
@@ -358,6 +362,11 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   if (M > 1024) return fail(PMPC_ERR_UNSUPPORTED, "M > 1024 particles per problem per GPU: shard the particles");
   if (Nc < 0 || Nc > (long long)N) Nc = (long long)N;  // main.jl:127-128
   pmpc_handle_s* h = new pmpc_handle_s();
+  // every error return below releases what has been created so far (the slab alone can be tens of GB)
+  struct Guard {
+    pmpc_handle_s* h;
+    ~Guard() { if (h) pmpc_destroy(h); }
+  } guard{h};
   if (device >= 0) {
     CU(cudaSetDevice(device));
     h->device = device;
@@ -408,7 +417,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   want(&pb.wu, Nn * NU * P); want(&pb.yu, Nn * NU * P); want(&pb.wx, Nn * NX * P); want(&pb.yx, Nn * NX * P);
   want(&pb.gc, B * D + 1); want(&pb.uc, B * D + 1); want(&pb.muc, B * D + 1);
   want(&pb.scratch, B * pb.scratch_stride);
-  want(&pb.hist, (size_t)4 * pb.hist_len * B); want(&pb.rho, B);
+  want(&pb.rho, B);
   size_t total = 0;
   for (auto& r : req) total += (r.second + 31) / 32 * 32;
   const size_t act_bytes = 2 * (Nn * NU * P) + 2 * (B * D + 32) + 64;
@@ -416,7 +425,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   h->slab_bytes = total * sizeof(double) + act_bytes + info_bytes + 256;
   cudaError_t e = cudaMalloc(&h->slab, h->slab_bytes);
   if (e != cudaSuccess) {
-    delete h;
+    h->slab = nullptr;
     return fail(PMPC_ERR_CUDA, std::string("cudaMalloc slab: ") + cudaGetErrorString(e));
   }
   CU(cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
@@ -441,30 +450,39 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaMalloc(&h->uniform, B * sizeof(int)));
   CU(cudaMemsetAsync(h->uniform, 0, B * sizeof(int), h->stream));
   pb.uniform = h->uniform;
+  CU(cudaMalloc(&h->hist, (size_t)4 * pb.hist_len * B * sizeof(double)));
+  CU(cudaMemsetAsync(h->hist, 0, (size_t)4 * pb.hist_len * B * sizeof(double), h->stream));
+  pb.hist = h->hist;
+  CU(cudaMalloc(&h->xerr, sizeof(int)));
+  CU(cudaMemsetAsync(h->xerr, 0, sizeof(int), h->stream));
+  pb.xerr = h->xerr;
+  pb.xtimeout_ns = 30ull * 1000000000ull;
   fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);
   ++g_launches;
   CU(cudaGetLastError());
+  guard.h = nullptr;
   *out = h;
   return PMPC_OK;
 }
 
-static void userdyn_free(pmpc_userdyn_s* u);
-
 int pmpc_destroy(pmpc_handle_t h) {
   if (!h) return PMPC_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   userdyn_free(h->user);
-  cudaEventDestroy(h->uev0); cudaEventDestroy(h->uev1);
+  for (cudaEvent_t ev : {h->uev0, h->uev1, h->ev0, h->ev1, h->tev0, h->tev1})
+    if (ev) cudaEventDestroy(ev);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
-  cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw);
+  cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw); cudaFree(h->hist); cudaFree(h->xerr);
   for (int r = 0; r < 8; ++r)
     if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_open[r]);
   cudaFree(h->comm);
-  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-  cudaEventDestroy(h->tev0); cudaEventDestroy(h->tev1);
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
   return PMPC_OK;
 }
 
@@ -754,13 +772,21 @@ int pmpc_scp_solve_async(pmpc_handle_t h, int max_it, double res_tol) {
   if (max_it < 1) return fail(PMPC_ERR_BAD_ARG, "max_it < 1");
   CU(cudaSetDevice(h->device));
   h->user_timed = false;
+  if (max_it > h->pb.hist_len) {  // the history holds every iteration of the launch (the reference keeps them all)
+    CU(cudaStreamSynchronize(h->stream));
+    double* nh = nullptr;
+    const size_t cnt = (size_t)4 * max_it * h->pb.B;
+    CU(cudaMalloc(&nh, cnt * sizeof(double)));
+    cudaFree(h->hist);
+    h->hist = nh;
+    h->pb.hist = nh;
+    h->pb.hist_len = max_it;
+    CU(cudaMemsetAsync(nh, 0, cnt * sizeof(double), h->stream));
+  }
   if (h->user) return userdyn_scp(h, max_it, res_tol);  // host-driven loop: synchronous
   h->pb.max_it = max_it;
   h->pb.res_tol = res_tol;
   h->pb.keep_prev = 0;
-  if (max_it > h->pb.hist_len) {
-    // hist buffer is fixed-size; iterations beyond it are simply not recorded
-  }
   return launch(h);
 }
 
@@ -769,6 +795,15 @@ int pmpc_sync(pmpc_handle_t h) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   if (h->solved && !h->user_timed) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  if (h->pb.world > 1) {
+    int xe = 0;
+    CU(cudaMemcpy(&xe, h->xerr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (xe) {
+      CU(cudaMemset(h->xerr, 0, sizeof(int)));
+      return fail(PMPC_ERR_STATE, "particle-sharded exchange timed out: a peer rank never arrived (failed rank, or the "
+                                  "kernels of the ranks were not co-resident)");
+    }
+  }
   return PMPC_OK;
 }
 
@@ -902,6 +937,35 @@ int pmpc_comm_connect(pmpc_handle_t h, int rank, int world, const void* ipc_hand
   return PMPC_OK;
 }
 
+int pmpc_comm_connect_local(pmpc_handle_t h, int rank, int world, const pmpc_handle_t* handles, size_t M_total) {
+  if (!h || !handles || world < 1 || world > 8 || rank < 0 || rank >= world || handles[rank] != h)
+    return fail(PMPC_ERR_BAD_ARG, "rank/world (world <= 8) or handles");
+  for (int r = 0; r < world; ++r) {
+    if (!handles[r] || !handles[r]->comm) return fail(PMPC_ERR_STATE, "pmpc_comm_export on every handle first");
+    if (handles[r]->comm_bytes != h->comm_bytes) return fail(PMPC_ERR_BAD_ARG, "handles differ in B / Nc");
+    if (handles[r]->device != h->device) {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, h->device, handles[r]->device));
+      if (!can) return fail(PMPC_ERR_UNSUPPORTED, "no peer access between the devices of the handles");
+      CU(cudaSetDevice(h->device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(handles[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(PMPC_ERR_CUDA, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    h->pb.peer[r] = handles[r]->comm;
+  }
+  h->pb.rank = rank;
+  h->pb.world = world;
+  h->pb.M_total = (int)M_total;
+  return PMPC_OK;
+}
+
+int pmpc_comm_set_timeout(pmpc_handle_t h, double seconds) {
+  if (!h || !(seconds > 0.0)) return fail(PMPC_ERR_BAD_ARG, "null handle or non-positive timeout");
+  h->pb.xtimeout_ns = (unsigned long long)(seconds * 1e9);
+  return PMPC_OK;
+}
+
 long long pmpc_launch_count(void) { return g_launches.load(); }
 
 #include "userdyn.inl"
@@ -934,7 +998,7 @@ int pmpc_timer_stop(pmpc_handle_t h, float* ms) {
 // compat entry points.  Handles are cached per shape so repeated calls (one per SCP iteration from
 // the Python loop) do not pay for cudaMalloc.
 static std::mutex g_cache_mu;
-static std::map<std::tuple<size_t, size_t, size_t, size_t, long long>, pmpc_handle_t> g_cache;
+static std::map<std::tuple<int, size_t, size_t, size_t, size_t, long long>, pmpc_handle_t> g_cache;
 
 int pmpc_lqp_solve(double* X_out, double* U_out, size_t xdim, size_t udim, size_t N, size_t M, long long Nc,
                    const double* x0, const double* f, const double* fx, const double* fu, const double* X_prev,
@@ -944,8 +1008,17 @@ int pmpc_lqp_solve(double* X_out, double* U_out, size_t xdim, size_t udim, size_
                    const pmpc_settings* settings, long long* info8) {
   if (!X_out || !U_out) return fail(PMPC_ERR_BAD_ARG, "null outputs");
   std::lock_guard<std::mutex> lock(g_cache_mu);
+  if (pmpc_device_count() < 1) return fail(PMPC_ERR_NO_DEVICE, "no CUDA device: pmpc_b200 has no CPU fallback");
   const long long Nce = (Nc < 0 || Nc > (long long)N) ? (long long)N : Nc;
-  auto key = std::make_tuple(xdim, udim, N, M, Nce);
+  // handles live on the device that was current when they were made: the caller's current device is part of the key
+  // and is current again when the call returns (the handle API switches to its own device internally)
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  struct Restore {
+    int d;
+    ~Restore() { cudaSetDevice(d); }
+  } restore{dev};
+  auto key = std::make_tuple(dev, xdim, udim, N, M, Nce);
   pmpc_handle_t h = nullptr;
   auto it = g_cache.find(key);
   if (it == g_cache.end()) {
@@ -972,6 +1045,11 @@ int pmpc_lqp_solve(double* X_out, double* U_out, size_t xdim, size_t udim, size_
   if (info8 && (rc = pmpc_get_info(h, info8))) return rc;
   return PMPC_OK;
 }
+
+// The reference's pybind shim starts the embedded Julia runtime at import (module.cpp:122-125, julia_init.h:1-2).
+// Exported as no-ops so that the UNMODIFIED module.cpp links against this library: there is no runtime to start.
+void init_julia(int argc, char* argv[]) { (void)argc; (void)argv; }
+void shutdown_julia(int retcode) { (void)retcode; }
 
 static void nan_fill(double* p, size_t n) {
   if (p) for (size_t i = 0; i < n; ++i) p[i] = NAN;

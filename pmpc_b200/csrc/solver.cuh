@@ -78,6 +78,8 @@ struct DevProb {
   int rank, world, M_total, comm_cap;   // comm_cap: doubles per exchange slot
   unsigned long long seq0;              // exchange sequence number before this launch (same on every rank)
   double* peer[8];                      // exchange buffer of every rank (peer[rank] is this GPU's own)
+  unsigned long long xtimeout_ns;       // bounded spin of the exchange (pmpc_comm_set_timeout; default 30 s)
+  int* xerr;                            // device flag: an exchange timed out (read back by pmpc_sync)
 };
 
 __host__ __device__ constexpr int pk(int r, int t, int n) { return r * n - (r * (r - 1)) / 2 + (t - r); }
@@ -177,10 +179,11 @@ struct Solver {
   bool flip;  // fused path: (Xc, Uc) / (Xpv, Upv) currently are (pb.Xp, pb.Up) / (pb.X, pb.U)
   bool dead;  // whole warp beyond the last problem (thread-per-problem launch tail)
   unsigned long long xseq;  // cross-GPU exchange counter (uniform over the CTA, identical on every rank)
+  bool xdead;               // an exchange timed out (peer missing): no further exchanges, the SCP loop stops
 
   __device__ Solver(const DevProb& pb_, double* red_, double* red2_)
       : pb(pb_), P(pb_.P), N(pb_.N), Nc(GROUPED ? pb_.Nc : 0), D(GROUPED ? pb_.D : 0), T(blockDim.x),
-        tid(threadIdx.x), red(red_), red2(red2_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0) {
+        tid(threadIdx.x), red(red_), red2(red2_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0), xdead(false) {
     // lanes without a particle mirror the last valid lane of their own warp (same warp tile)
     dead = false;
     if (GROUPED) {
@@ -268,6 +271,7 @@ struct Solver {
   __device__ __noinline__ void xreduce(double* vec, int len, bool all_sum, unsigned sum_mask = 0u) {
     if (!GROUPED || pb.world <= 1) return;
     __syncthreads();
+    if (xdead) return;  // a previous exchange timed out: the launch is being abandoned (status bit 2 of info[4])
     ++xseq;
     const size_t slot = (size_t)pb.comm_cap + 1;  // data + flag
     const size_t off = ((size_t)prob * 2 + (size_t)(xseq & 1ull)) * slot;
@@ -278,13 +282,31 @@ struct Solver {
     if (tid == 0) {
       unsigned long long* flag = reinterpret_cast<unsigned long long*>(pb.peer[pb.rank] + off + pb.comm_cap);
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(xseq) : "memory");
-      for (int r = 0; r < pb.world; ++r) {
+      // bounded spin: a peer that never arrives (failed rank, kernel not co-resident) must not hang the node
+      unsigned long long t_start = 0, spins = 0;
+      bool timed_out = false;
+      for (int r = 0; r < pb.world && !timed_out; ++r) {
         const unsigned long long* pf = reinterpret_cast<const unsigned long long*>(pb.peer[r] + off + pb.comm_cap);
         unsigned long long v;
-        do {
+        for (;;) {
           asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(pf) : "memory");
-        } while (v < xseq);
+          if (v >= xseq) break;
+          if ((++spins & 1023ull) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > pb.xtimeout_ns) { timed_out = true; break; }
+          }
+        }
       }
+      red2[RCAP - 1] = timed_out ? 1.0 : 0.0;
+      if (timed_out) *pb.xerr = 1;
+    }
+    __syncthreads();
+    if (red2[RCAP - 1] != 0.0) {
+      xdead = true;
+      __syncthreads();
+      return;
     }
     __syncthreads();
     for (int k = tid; k < len; k += T) {
@@ -298,6 +320,20 @@ struct Solver {
       vec[k] = acc;
     }
     __syncthreads();
+  }
+
+  // End of a launch in sharded mode: leave an EVEN number of exchanges behind.  A slot is overwritten two exchanges
+  // later, which is safe inside a launch (finishing exchange n-1 proves every peer has read n-2); the next launch
+  // starts its own sequence window with an odd number, i.e. in the slot of this launch's second-to-last exchange,
+  // which every peer is known to have finished reading — without the padding a fast rank could overwrite the slot a
+  // slow peer is still reading from the last exchange of the previous launch.
+  __device__ __forceinline__ void xclose() {
+    if (!GROUPED || pb.world <= 1) return;
+    if ((xseq - pb.seq0) & 1ull) {
+      red2[0] = 0.0;
+      __syncthreads();
+      xreduce(red2, 1, true);
+    }
   }
 
   // ---- K1 + cost vectors: linearise about (X_prev, U_prev), build c, q, r --------------------
@@ -1424,6 +1460,11 @@ struct Solver {
         break;
       }
       if (status & 2) cnt[4] |= 2;
+      if (xdead) {  // a peer never arrived at an exchange: abandon the launch (pmpc_sync reports PMPC_ERR_STATE)
+        cnt[4] |= 4;
+        ++it;
+        break;
+      }
       if (fused_done) {
         // residual / objective were accumulated by the forward sweep; X_prev <- X is a buffer swap
         if (!pb.keep_prev) {
@@ -1468,6 +1509,7 @@ struct Solver {
         }
       }
     }
+    xclose();
     cnt[0] = it;
     if (writer) {
       for (int k = 0; k < 8; ++k) pb.info[(size_t)k * pb.B + prob] = cnt[k];

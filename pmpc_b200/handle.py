@@ -213,6 +213,16 @@ class DeviceSolver:
         assert len(blob) == 64 * world
         check(self.lib.pmpc_comm_connect(self._h, int(rank), int(world), C.c_char_p(blob), int(M_total)), "comm_connect")
 
+    def comm_connect_local(self, rank: int, solvers, M_total: int):
+        """Particle sharding between handles of THIS process (``pmpc_comm_connect_local``): ``solvers`` are the
+        ``world`` :class:`DeviceSolver` objects in rank order, ``solvers[rank] is self``; every one must have called
+        :meth:`comm_export` (which allocates its exchange buffer)."""
+        arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+        check(self.lib.pmpc_comm_connect_local(self._h, int(rank), len(solvers), arr, int(M_total)), "comm_connect_local")
+
+    def comm_set_timeout(self, seconds: float):
+        check(self.lib.pmpc_comm_set_timeout(self._h, float(seconds)), "comm_set_timeout")
+
     def timer_start(self):
         """CUDA event on the handle's stream (the stream every kernel of this handle runs on)."""
         check(self.lib.pmpc_timer_start(self._h), "timer_start")

@@ -101,27 +101,15 @@ def shard_particles(arrs: dict, lo: int, hi: int, Nc: int) -> dict:
     return out
 
 
-def solve_consensus_sharded(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_prev=None, u_l=None, u_u=None,
-                            max_it: int = 100, res_tol: float = 1e-5, reg_x: float = 1.0, reg_u: float = 1e-2,
-                            slew_rate=0.0, Nc: int = 1, dyn_eps: float = 1e-6, dist=None, device: int = -1,
-                            ltv=None, settings=None):
-    """ONE consensus problem (arrays with leading particle axis M, as ``pmpc.solve`` takes them) with its
-    particles sharded over the ranks of ``dist`` (one process per GPU of one node).  Dynamics: Dubins car
-    with per-particle parameters ``dyn_params (M, 3)``, or ``ltv=(A, B, c)`` with ``A (M,N,n,n)``.
-    Every rank passes the same full arrays and gets the same full result ``X (M,N+1,n), U (M,N,m), info``.
-    Control box only (a state box needs the unsharded solver)."""
+def _shard_solver(rank, world, dyn_params, full, M, N, n, m, Nc, reg_x, reg_u, slew_rate, dyn_eps, device, ltv, settings):
+    """Handle of rank `rank` of `world`: its slice of the particles uploaded, dynamics set, not yet connected."""
     import numpy as np
 
     from .handle import DeviceSolver
 
-    rank, world = (0, 1) if dist is None else (dist.get_rank(), dist.get_world_size())
-    Q = np.asarray(Q, dtype=np.float64)
-    M, N, n = Q.shape[:3]
-    m = np.asarray(R).shape[-1]
     Nc_eff = N if Nc < 0 else int(Nc)
     lo, hi = shard_bounds(M, rank, world)
     assert hi - lo >= 2, "particle sharding needs at least 2 particles per rank"
-    full = dict(Q=Q, R=R, x0=x0, X_ref=X_ref, U_ref=U_ref, X_prev=X_prev, U_prev=U_prev, u_l=u_l, u_u=u_u)
     loc = shard_particles(full, lo, hi, Nc_eff)
     ds = DeviceSolver(hi - lo, N, n, m, Nc, B=1, device=device, settings=settings)
     ds.set_problem(loc["x0"], loc["Q"], loc["R"], loc["X_ref"], loc["U_ref"], None, None, loc["u_l"], loc["u_u"], reg_x,
@@ -133,6 +121,26 @@ def solve_consensus_sharded(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev
         ds.set_ltv(np.asarray(A)[lo:hi], np.asarray(Bm)[lo:hi], None if c is None else np.asarray(c)[lo:hi])
     else:
         ds.set_dubins(np.asarray(dyn_params, dtype=np.float64)[lo:hi], dyn_eps)
+    return ds
+
+
+def solve_consensus_sharded(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_prev=None, u_l=None, u_u=None,
+                            max_it: int = 100, res_tol: float = 1e-5, reg_x: float = 1.0, reg_u: float = 1e-2,
+                            slew_rate=0.0, Nc: int = 1, dyn_eps: float = 1e-6, dist=None, device: int = -1,
+                            ltv=None, settings=None):
+    """ONE consensus problem (arrays with leading particle axis M, as ``pmpc.solve`` takes them) with its
+    particles sharded over the ranks of ``dist`` (one process per GPU of one node).  Dynamics: Dubins car
+    with per-particle parameters ``dyn_params (M, 3)``, or ``ltv=(A, B, c)`` with ``A (M,N,n,n)``.
+    Every rank passes the same full arrays and gets the same full result ``X (M,N+1,n), U (M,N,m), info``.
+    Control box only (a state box needs the unsharded solver)."""
+    import numpy as np
+
+    rank, world = (0, 1) if dist is None else (dist.get_rank(), dist.get_world_size())
+    Q = np.asarray(Q, dtype=np.float64)
+    M, N, n = Q.shape[:3]
+    m = np.asarray(R).shape[-1]
+    full = dict(Q=Q, R=R, x0=x0, X_ref=X_ref, U_ref=U_ref, X_prev=X_prev, U_prev=U_prev, u_l=u_l, u_u=u_u)
+    ds = _shard_solver(rank, world, dyn_params, full, M, N, n, m, Nc, reg_x, reg_u, slew_rate, dyn_eps, device, ltv, settings)
     if world > 1:
         handles = gather_objects(ds.comm_export(), dist)
         ds.comm_connect(rank, world, handles, M)
@@ -145,3 +153,45 @@ def solve_consensus_sharded(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev
     if world > 1:
         dist.barrier()  # nobody unmaps while a peer may still read
     return np.concatenate([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts], 0), info
+
+
+def solve_consensus_sharded_local(world: int, dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_prev=None,
+                                  u_l=None, u_u=None, max_it: int = 100, res_tol: float = 1e-5, reg_x: float = 1.0,
+                                  reg_u: float = 1e-2, slew_rate=0.0, Nc: int = 1, dyn_eps: float = 1e-6, devices=None,
+                                  ltv=None, settings=None, timeout_s=None):
+    """The same particle sharding driven from ONE process: ``world`` handles, handle r on ``devices[r]`` (default: all on
+    the current device, where their kernels run concurrently on the handles' own streams and exchange the consensus
+    terms through the same in-kernel protocol, plain device pointers instead of IPC mappings).  All solves are launched
+    asynchronously before any is waited for.  Returns ``X (M,N+1,n), U (M,N,m), infos`` (one info dict per rank)."""
+    import numpy as np
+
+    Q = np.asarray(Q, dtype=np.float64)
+    M, N, n = Q.shape[:3]
+    m = np.asarray(R).shape[-1]
+    devices = [-1] * world if devices is None else list(devices)
+    full = dict(Q=Q, R=R, x0=x0, X_ref=X_ref, U_ref=U_ref, X_prev=X_prev, U_prev=U_prev, u_l=u_l, u_u=u_u)
+    solvers = [_shard_solver(r, world, dyn_params, full, M, N, n, m, Nc, reg_x, reg_u, slew_rate, dyn_eps, devices[r], ltv,
+                             settings) for r in range(world)]
+    try:
+        if world > 1:
+            for ds in solvers:
+                ds.comm_export()
+            for r, ds in enumerate(solvers):
+                ds.comm_connect_local(r, solvers, M)
+                if timeout_s is not None:
+                    ds.comm_set_timeout(timeout_s)
+        for ds in solvers:
+            ds.scp_solve_async(max_it, res_tol)
+        for ds in solvers:
+            ds.sync()
+        parts, infos = [], []
+        for ds in solvers:
+            X, U = ds.trajectory()
+            parts.append((X[0], U[0]))
+            info = {k: int(v[0]) for k, v in ds.info().items()}
+            info["kernel_ms"] = ds.last_kernel_ms()
+            infos.append(info)
+    finally:
+        for ds in solvers:
+            ds.close()
+    return np.concatenate([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts], 0), infos

@@ -15,7 +15,9 @@ u_l, u_u``), same defaults, same return values ``(X, U, data)`` and array layout
 from __future__ import annotations
 
 import math
+import threading
 import time
+from collections import OrderedDict
 from copy import copy
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -116,20 +118,62 @@ def _device_settings(solver_settings):
     return s
 
 
+def _check_formulation(solver_settings, M):
+    """Same notice as the host path (``static_backend.aff_solve``): a cone / smoothed request (the reference's default
+    ``solver="ecos"``, ``static_backend.py:242-253``) is served by the QP (sum-of-costs, hard box) formulation."""
+    from . import static_backend as sb
+
+    solver = str(solver_settings.get("solver", "ecos")).lower()
+    smoothing = "smooth_cstr" in solver_settings or not math.isnan(float(solver_settings.get("smooth_alpha", math.nan)))
+    if ((solver in sb._CONE_SOLVERS and M > 1) or smoothing) and "cone" not in sb._warned:
+        sb._warned.add("cone")
+        import warnings
+
+        warnings.warn("pmpc_b200 solves the QP (sum-of-costs, hard box) formulation of lqp_solve; the requested "
+                      "cone/smoothed route is served by it (see DESIGN.md, 'out of scope').")
+
+
+# Handles are cached per (device, shape): a plain reference-style `solve(...)` call re-uses the resident slab, stream and
+# events of the previous call of the same shape instead of paying cudaMalloc / cudaFree every time.
+_HANDLE_CACHE: "OrderedDict[tuple, DeviceSolver]" = OrderedDict()
+_HANDLE_CACHE_MAX = 8
+_HANDLE_LOCK = threading.Lock()
+
+
+def _cached_solver(M, N, xdim, udim, Nc, device=-1):
+    key = (int(device), M, N, xdim, udim, Nc)
+    with _HANDLE_LOCK:
+        ds = _HANDLE_CACHE.pop(key, None)
+        if ds is None or not ds._h.value:
+            ds = DeviceSolver(M, N, xdim, udim, Nc, device=device)
+        _HANDLE_CACHE[key] = ds
+        while len(_HANDLE_CACHE) > _HANDLE_CACHE_MAX:
+            _, old = _HANDLE_CACHE.popitem(last=False)
+            old.close()
+    return ds
+
+
+def clear_handle_cache():
+    """Release the device memory of every cached handle."""
+    with _HANDLE_LOCK:
+        while _HANDLE_CACHE:
+            _, ds = _HANDLE_CACHE.popitem()
+            ds.close()
+
+
 # -- device loop ------------------------------------------------------------------------------------
 def _device_scp(dyn, dims, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u, max_it, res_tol, reg_x, reg_u,
                 slew_rate, u0_slew, solver_settings, verbose, t0):
     M, N, xdim, udim = dims
     Nc = solver_settings.get("Nc", -1)
-    cache = solver_settings.get("_device_solver")
+    _check_formulation(solver_settings, M)
+    cache = solver_settings.get("_device_solver")  # explicit handle (kept for callers that manage their own)
     key = (M, N, xdim, udim, Nc)
-    if isinstance(cache, DeviceSolver) and (cache.M, cache.N, cache.n, cache.m, cache.Nc) == key:
+    if isinstance(cache, DeviceSolver) and (cache.B, cache.M, cache.N, cache.n, cache.m, cache.Nc) == (1,) + key and cache._h.value:
         ds = cache
     else:
-        ds = DeviceSolver(M, N, xdim, udim, Nc)
-    dev = _device_settings(solver_settings)
-    if dev:
-        ds.set_settings(**dev)
+        ds = _cached_solver(M, N, xdim, udim, Nc)
+    ds.set_settings(**_device_settings(solver_settings))  # defaults unless solver_settings["b200"] overrides them
     absent = lambda z: z is None or np.size(z) == 0
     slew_reg = None if slew_rate is None else np.full(M, float(slew_rate))
     slew_reg0 = np.full(M, float(solver_settings["slew_reg"])) if "slew_reg" in solver_settings else None
@@ -356,9 +400,7 @@ def tune_scp(*args, sample_nb: int = 14, reg_rng: Tuple[int, int] = (-3, 3), sol
     for reg in reg_list:
         kwargs.update(reg_x=float(reg), reg_u=float(reg * reg_ratio), verbose=False)
         X, U, data = solve_fn(*args, **kwargs)
-        res_list.append(1e2 if data is None else data["hist"][-1]["resid"])
-        if data is not None and "device_solver" in data:  # reuse the handle for the next sample
-            kwargs["solver_settings"] = dict(kwargs.get("solver_settings") or {}, _device_solver=data["device_solver"])
+        res_list.append(1e2 if data is None else data["hist"][-1]["resid"])  # (the handle is re-used through the cache)
     if savefig is not None:
         try:
             import matplotlib

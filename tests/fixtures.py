@@ -104,3 +104,9 @@ def config_c4(M=64, N=100):
 
 def config_c5(M=1024, N=200):
     return config_ltv(4, M, N, 32, 8, 5, xbox=False)
+
+
+def hooks_lin_cost_fn(X_prev, U_prev, problems):
+    """The `lin_cost_fn` of tests/golden/scp_lin_cost.npz: gradient of the smooth extra cost
+    0.05 sum(sin(x)) + 1e-3 sum(u^3) / 3 at the previous iterate (reference signature, pmpc/scp_mpc.py:171-175)."""
+    return 0.05 * np.cos(X_prev), 1e-3 * U_prev ** 2

@@ -23,7 +23,7 @@ REF = "/root/reference"
 def _header_functions():
     src = open(os.path.join(ROOT, "include", "pmpc_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:void|int|long long|const char \*)\s*\*?\s*((?:pmpc|c)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:void|int|long long|const char \*)\s*\*?\s*((?:pmpc|c)_[a-z0-9_]+|init_julia|shutdown_julia)\s*\(", src)))
 
 
 def test_library_loads_and_exports_every_declared_symbol():
