@@ -182,7 +182,9 @@ int pmpc_last_kernel_ms(pmpc_handle_t h, float *ms);
  * events do not see it), the number of kernels this library has launched in this process, and
  * two micro-benchmarks that measure the roofline denominators on the device at hand:
  * kind 0 = HBM copy bandwidth in GB/s (read + write bytes of a 1 GiB device-to-device copy
- * kernel), kind 1 = fp64 FMA throughput in TFLOP/s (register-resident DFMA chains). */
+ * kernel), kind 1 = fp64 FMA throughput in TFLOP/s (register-resident DFMA chains), kind 2 = fp64 tensor-core
+ * (DMMA m8n8k4) throughput, kinds 3 / 4 = DFMA with one operand read from shared memory by a broadcast LDS.64 per FMA /
+ * LDS.128 per two FMAs (the operand pattern of the warp-per-particle Riccati kernel). */
 int pmpc_timer_start(pmpc_handle_t h);
 int pmpc_timer_stop(pmpc_handle_t h, float *ms);
 long long pmpc_launch_count(void);
