@@ -29,6 +29,28 @@ PMPC_VARIANTS(PMPC_DECL)
 #undef PMPC_DECL
 }  // namespace pmpc
 
+// warp-per-particle kernels for the NX >= 8 shapes (wpp_inst.cu): X(NX, NU, SLEW)
+#include "wpp_plan.h"
+#define PMPC_WPP_VARIANTS(X) X(8, 4, 0) X(8, 4, 1) X(12, 4, 0) X(12, 4, 1) X(16, 8, 0) X(16, 8, 1) X(32, 8, 0) X(32, 8, 1)
+namespace pmpc {
+#define PMPC_WDECL(nx, nu, sl)                                                     \
+  cudaError_t wpp_plan_##nx##_##nu##_##sl(const DevProb&, WppPlan*);               \
+  cudaError_t wpp_launch_##nx##_##nu##_##sl(const DevProb&, const WppPlan&, cudaStream_t);
+PMPC_WPP_VARIANTS(PMPC_WDECL)
+#undef PMPC_WDECL
+}  // namespace pmpc
+struct WppEntry {
+  int nx, nu, slew;
+  cudaError_t (*plan)(const DevProb&, WppPlan*);
+  cudaError_t (*launch)(const DevProb&, const WppPlan&, cudaStream_t);
+};
+static const WppEntry kWpp[] = {
+#define PMPC_WENTRY(nx, nu, sl) {nx, nu, sl, &pmpc::wpp_plan_##nx##_##nu##_##sl, &pmpc::wpp_launch_##nx##_##nu##_##sl},
+    PMPC_WPP_VARIANTS(PMPC_WENTRY)
+#undef PMPC_WENTRY
+};
+static const int kWppDmax = 64;  // == Wpp::DMAX
+
 typedef cudaError_t (*launch_fn)(const DevProb&, int, int, cudaStream_t, int*);
 struct VariantEntry { int nx, nu, kind, var; launch_fn fn; };
 static const VariantEntry kVariants[] = {
@@ -85,6 +107,14 @@ struct pmpc_handle_s {
   double *lin_f = nullptr, *lin_fx = nullptr, *lin_fu = nullptr;  // reference-layout linearisation
   int* uniform = nullptr;     // per problem: cost / reference / bound data identical for all particles
   int* xerr = nullptr;        // device flag raised when an in-kernel exchange times out (particle sharding)
+  // warp-per-particle kernel: team exchange buffers, consensus partials, hand-over flags (DevProb::tm / wscr / fb)
+  double* tm = nullptr;
+  size_t tm_doubles = 0;
+  int tm_Tc = -1, tm_cap = -1;
+  double* wscr = nullptr;
+  size_t wscr_doubles = 0;
+  int* fb = nullptr;
+  unsigned long long tseq = 0;
   double* hist = nullptr;     // (4, hist_len, B) iteration history, grown to max_it by pmpc_scp_solve_async
   bool have_problem = false, have_dyn = false, solved = false;
   pmpc_settings settings{};
@@ -98,10 +128,10 @@ struct pmpc_handle_s {
 // packing kernels: reference layout (particle-major, column-major blocks) -> warp-tiled SoA
 // (solver.cuh "DATA LAYOUT").  One thread per (flat particle gf = b*M + i, stage j), gf fastest so
 // that the tile stores are coalesced.
-struct Lay { int M, Mpad, N; };
+struct Lay { int M, Mpad, N, tile; };  // tile: particles per layout tile (32, or 1 for the NX >= 8 shapes)
 __device__ __forceinline__ size_t slot_of(int gf, Lay L) { return (size_t)(gf / L.M) * L.Mpad + (size_t)(gf % L.M); }
 __device__ __forceinline__ size_t tix(size_t slot, Lay L, int j, int E, int e) {
-  return (((slot >> 5) * (size_t)L.N + (size_t)j) * (size_t)E + (size_t)e) * 32 + (slot & 31);
+  return (((slot / L.tile) * (size_t)L.N + (size_t)j) * (size_t)E + (size_t)e) * L.tile + (slot % L.tile);
 }
 
 enum { FL_XBOX_ABSENT = 0, FL_UBOX_ABSENT, FL_SLEW_ABSENT, FL_SLEW0_ABSENT, FL_SLEW_NONZERO, FL_COUNT = 8 };
@@ -167,7 +197,7 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
   const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
-  const Lay L{pb.M, pb.Mpad, pb.N};
+  const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
   const double* Qb = Q + ((size_t)g * N + j) * n * n;  // column-major: Q[r,t] = Qb[t*n + r]
@@ -220,7 +250,7 @@ __global__ void pack_lin_kernel(DevProb pb, int NX, int NU, const double* __rest
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
   const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
-  const Lay L{pb.M, pb.Mpad, pb.N};
+  const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
   const double* fxb = fx + ((size_t)g * N + j) * n * n;  // fx[r,t] = fxb[t*n + r]
@@ -252,7 +282,7 @@ __global__ void linearize_dubins_kernel(DevProb pb, double* __restrict__ f, doub
   const int N = pb.N;
   if (idx >= (size_t)Ptot * N) return;
   const int g = (int)(idx % Ptot), j = (int)(idx / Ptot);
-  const Lay L{pb.M, pb.Mpad, pb.N};
+  const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
   double x[4], u[2], fo[4], fxo[16], fuo[8];
@@ -274,7 +304,7 @@ __global__ void uniform_check_kernel(DevProb pb, int NX, int NU, int* flags, int
   if (idx >= (size_t)Ptot * N) return;
   const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
   if (gf % pb.M == 0) return;
-  const Lay L{pb.M, pb.Mpad, pb.N};
+  const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   const size_t sl = slot_of(gf, L), s0 = slot_of(gf - gf % pb.M, L);
   const int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2;
   bool same = pb.rdiag0[sl] == pb.rdiag0[s0];
@@ -387,7 +417,8 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   pb.B = (int)B; pb.M = (int)M; pb.N = (int)N; pb.n = (int)xdim; pb.m = (int)udim;
   pb.Nc = (M == 1) ? 0 : (int)Nc;  // one particle: consensus is vacuous (the Nc==0 quirk is applied at pack time)
   pb.D = pb.Nc * sh.NU;
-  pb.Mpad = (M == 1) ? 1 : (int)(((M + 31) / 32) * 32);
+  pb.tile = (sh.NX >= 8) ? 1 : 32;  // == Solver<NX, NU>::TILE
+  pb.Mpad = (M == 1 || pb.tile == 1) ? (int)M : (int)(((M + 31) / 32) * 32);
   pb.P = (int)((((size_t)B * pb.Mpad + 31) / 32) * 32);
   pb.hist_len = 128;
   pb.rank = 0; pb.world = 1; pb.M_total = (int)M; pb.comm_cap = 0; pb.seq0 = 0;
@@ -398,7 +429,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   const int T = (int)(((M + 31) / 32) * 32);
   const size_t D = pb.D;
   size_t cols = D < 8 ? D : 8;
-  pb.scratch_stride = std::max<size_t>(D * D, (size_t)T * std::max<size_t>(D * cols, (size_t)ST_COUNT));
+  pb.scratch_stride = std::max<size_t>(D * D + D + 32, (size_t)T * std::max<size_t>(D * cols, (size_t)ST_COUNT));
   std::vector<std::pair<double**, size_t>> req;
   auto want = [&](double** p, size_t cnt) { req.push_back({p, cnt}); };
   want(&pb.Qs, Nn * NQ * P); want(&pb.Rs, Nn * NR * P); want(&pb.qref, Nn * NX * P); want(&pb.rref, Nn * NU * P);
@@ -457,6 +488,11 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaMemsetAsync(h->xerr, 0, sizeof(int), h->stream));
   pb.xerr = h->xerr;
   pb.xtimeout_ns = 30ull * 1000000000ull;
+  CU(cudaMalloc(&h->fb, B * sizeof(int)));
+  CU(cudaMemsetAsync(h->fb, 0, B * sizeof(int), h->stream));
+  pb.fb = h->fb;
+  pb.resume = 0;
+  pb.tm = nullptr; pb.wscr = nullptr; pb.tm_cap = 0; pb.tseq0 = 0;
   fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);
   ++g_launches;
   CU(cudaGetLastError());
@@ -475,7 +511,7 @@ int pmpc_destroy(pmpc_handle_t h) {
   for (cudaEvent_t ev : {h->uev0, h->uev1, h->ev0, h->ev1, h->tev0, h->tev1})
     if (ev) cudaEventDestroy(ev);
   cudaFree(h->slab); cudaFree(h->stage); cudaFree(h->lin_f); cudaFree(h->lin_fx); cudaFree(h->lin_fu);
-  cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw); cudaFree(h->hist); cudaFree(h->xerr);
+  cudaFree(h->uniform); cudaFree(h->flags); cudaFree(h->raw); cudaFree(h->hist); cudaFree(h->xerr); cudaFree(h->tm); cudaFree(h->wscr); cudaFree(h->fb);
   for (int r = 0; r < 8; ++r)
     if (h->peer_open[r]) cudaIpcCloseMemHandle(h->peer_open[r]);
   cudaFree(h->comm);
@@ -513,7 +549,7 @@ static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, in
     int rc = upload(h, host, h->Ptot * pb.N * Ei, off, &dev);
     if (rc) return rc;
   }
-  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, Lay{pb.M, pb.Mpad, pb.N}, Ei, Eo, fill,
+  pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, Lay{pb.M, pb.Mpad, pb.N, pb.tile}, Ei, Eo, fill,
                                                               nullptr);
   ++g_launches;
   CU(cudaGetLastError());
@@ -594,7 +630,7 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   pack_cost_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, dQ, dR, dXr, dUr, ds, ds0, dum1, (int)Pt,
                                                          h->Nc_orig >= 1 ? 1 : 0, h->row_major, h->flags);
   ++g_launches;
-  const Lay L{pb.M, pb.Mpad, pb.N};
+  const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(dx0, pb.x0, (int)Pt, pb.P, L, n, NX, 0.0);
   ++g_launches;
   const double inf = INFINITY;
@@ -653,7 +689,7 @@ int pmpc_set_dynamics(pmpc_handle_t h, int kind, const double* params, size_t np
     double* d;
     int rc;
     if ((rc = upload(h, params, h->Ptot * 3, 0, &d))) return rc;
-    pack_particle_kernel<<<nblk(h->Ptot), 256, 0, h->stream>>>(d, pb.dynp, (int)h->Ptot, pb.P, Lay{pb.M, pb.Mpad, pb.N}, 3, 4, 0.0);
+    pack_particle_kernel<<<nblk(h->Ptot), 256, 0, h->stream>>>(d, pb.dynp, (int)h->Ptot, pb.P, Lay{pb.M, pb.Mpad, pb.N, pb.tile}, 3, 4, 0.0);
     ++g_launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
@@ -752,14 +788,63 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
     cudaError_t e = fn(pb, blocks, threads, h->stream, occ_out);
     return e == cudaSuccess ? PMPC_OK : fail(PMPC_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
   }
-  if (pb.world > 1) {
-    if (kind == 0) return fail(PMPC_ERR_UNSUPPORTED, "particle sharding needs at least 2 particles per rank");
-    // every launch gets its own window of exchange sequence numbers (flags only ever grow)
-    h->seq += (1ull << 32);
-    h->pb.seq0 = h->seq;
-  }
+  if (pb.world > 1 && kind == 0) return fail(PMPC_ERR_UNSUPPORTED, "particle sharding needs at least 2 particles per rank");
+  auto next_window = [&]() {  // every launch gets its own window of exchange sequence numbers (flags only ever grow)
+    if (h->pb.world > 1) {
+      h->seq += (1ull << 32);
+      h->pb.seq0 = h->seq;
+    }
+  };
+  // NX >= 8: the warp-per-particle kernel runs the SCP loop (wpp.cuh); what it hands over (state bound active,
+  // active-set iteration stalls) is continued by the thread-per-particle kernel launched behind it in resume mode
+  const WppEntry* we = nullptr;
+  if (NX >= 8 && pb.fused && pb.polish && pb.dyn_kind == DYN_AFFINE && ((pb.M == 1) ? 0 : pb.D) <= kWppDmax)
+    for (const WppEntry& w : kWpp)
+      if (w.nx == NX && w.nu == NU && w.slew == (pb.has_slew ? 1 : 0)) we = &w;
   CU(cudaEventRecord(h->ev0, h->stream));
-  cudaError_t e = fn(pb, blocks, threads, h->stream, nullptr);
+  h->pb.resume = 0;
+  if (we) {
+    WppPlan pl;
+    cudaError_t e = we->plan(pb, &pl);
+    if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("warp-per-particle plan: ") + cudaGetErrorString(e));
+    if (pl.tm_doubles > h->tm_doubles || pl.wscr_doubles > h->wscr_doubles) {
+      CU(cudaStreamSynchronize(h->stream));
+      if (pl.tm_doubles > h->tm_doubles) {
+        cudaFree(h->tm);
+        h->tm = nullptr;
+        h->tm_doubles = 0;
+        CU(cudaMalloc(&h->tm, pl.tm_doubles * sizeof(double)));
+        h->tm_doubles = pl.tm_doubles;
+        h->tm_Tc = -1;
+      }
+      if (pl.wscr_doubles > h->wscr_doubles) {
+        cudaFree(h->wscr);
+        h->wscr = nullptr;
+        h->wscr_doubles = 0;
+        CU(cudaMalloc(&h->wscr, pl.wscr_doubles * sizeof(double)));
+        h->wscr_doubles = pl.wscr_doubles;
+      }
+    }
+    if (h->tm_Tc != pl.Tc || h->tm_cap != pl.cap) {  // the flag words move with the team layout: start from zero
+      CU(cudaMemsetAsync(h->tm, 0, h->tm_doubles * sizeof(double), h->stream));
+      h->tm_Tc = pl.Tc;
+      h->tm_cap = pl.cap;
+      h->tseq = 0;
+    }
+    h->tseq += (1ull << 32);
+    h->pb.tm = h->tm;
+    h->pb.wscr = h->wscr;
+    h->pb.tm_cap = pl.cap;
+    h->pb.tseq0 = h->tseq;
+    next_window();
+    e = we->launch(h->pb, pl, h->stream);
+    if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("warp-per-particle kernel launch: ") + cudaGetErrorString(e));
+    ++g_launches;
+    h->pb.resume = 1;
+  }
+  next_window();
+  cudaError_t e = fn(h->pb, blocks, threads, h->stream, nullptr);
+  h->pb.resume = 0;
   if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   ++g_launches;
   CU(cudaEventRecord(h->ev1, h->stream));
@@ -842,7 +927,7 @@ static int get_solution_impl(pmpc_handle_t h, double* X, double* U, int lead) {
   if (nXo + nUo > h->stage_doubles) return fail(PMPC_ERR_STATE, "staging too small");
   double* dX = h->stage;
   double* dU = h->stage + nXo;
-  const Lay L{pb.M, pb.Mpad, pb.N};
+  const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   if (X) {
     unpack_vec_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb.X, dX, (int)Pt, L, h->shape.NX, pb.n, lead, pb.x0, pb.P);
     ++g_launches;
@@ -902,7 +987,7 @@ int pmpc_comm_export(pmpc_handle_t h, void* ipc_handle_64) {
   if (!h->comm) {
     const DevProb& pb = h->pb;
     const size_t D = (size_t)pb.D;
-    const size_t cap = std::max<size_t>(D * D, (size_t)ST_COUNT) + 32;
+    const size_t cap = std::max<size_t>(D * D + D, (size_t)ST_COUNT) + 32;
     h->comm_bytes = (size_t)pb.B * 2 * (cap + 1) * sizeof(double);
     CU(cudaMalloc(&h->comm, h->comm_bytes));
     CU(cudaMemset(h->comm, 0, h->comm_bytes));

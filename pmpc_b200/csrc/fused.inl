@@ -66,21 +66,21 @@
   // wb = (g >> 5) * N: first stage block of this warp's particle tile
   template <typename Tp>
   __device__ __forceinline__ static const Tp* blk(const Tp* a, int j, int E, size_t wb) {
-    return a + ((wb + (size_t)j) * (size_t)E) * 32;
+    return a + ((wb + (size_t)j) * (size_t)E) * TILE;
   }
   // warp-tile SoA index from sweep-local invariants (wb as above, col = g & 31).  The sweeps use these
   // instead of ix()/ld()/at(): the Solver object lives in local memory (it escapes into the noinline
   // helpers), and every asm volatile "memory" clobber of the ring protocol would force its members to be
   // re-read from there (LDL + long-scoreboard stall) at each use.
   __device__ __forceinline__ static size_t ixw(size_t wb, int col, int j, int E, int e) {
-    return ((wb + (size_t)j) * (size_t)E + (size_t)e) * 32 + (size_t)col;
+    return ((wb + (size_t)j) * (size_t)E + (size_t)e) * TILE + (size_t)col;
   }
 
   // dynamic shared memory: [table][ring of every warp][mbarriers of every warp]
   __device__ __forceinline__ void fused_init(unsigned char* smem) {
     lane = tid & 31;
     wid = tid >> 5;
-    col = g & 31;
+    col = g % TILE;
     rcount = 0;
     ring = nullptr;
     bars = nullptr;
@@ -302,7 +302,7 @@
     const size_t P = this->P;
     const bool valid = this->valid, flip = this->flip;
     const double s = this->s;
-    const size_t wb = (size_t)(g >> 5) * (size_t)N;
+    const size_t wb = (size_t)(g / TILE) * (size_t)N;
     uint32_t rcount = this->rcount;
     auto ix = [=](int j, int E, int e) -> size_t { return ixw(wb, col, j, E, e); };
     auto ld = [=](const double* a, int j, int E, int e) -> double { return a[ixw(wb, col, j, E, e)]; };
@@ -745,7 +745,7 @@
     const size_t P = this->P;
     const bool valid = this->valid, flip = this->flip;
     const double s = this->s;
-    const size_t wb = (size_t)(g >> 5) * (size_t)N;
+    const size_t wb = (size_t)(g / TILE) * (size_t)N;
     uint32_t rcount = this->rcount;
     auto ix = [=](int j, int E, int e) -> size_t { return ixw(wb, col, j, E, e); };
     auto ld = [=](const double* a, int j, int E, int e) -> double { return a[ixw(wb, col, j, E, e)]; };

@@ -5,7 +5,8 @@
 //   PMPC.jl/src/lqp_utils.jl:2-393 (QP assembly) + osqp_solver.jl:34-72 (OSQP)  ->  Riccati-ADMM + polish
 // See DESIGN.md for the maths and the data layout.
 //
-// DATA LAYOUT (HBM): warp-tiled structure-of-arrays.  Particle i of problem b owns slot
+// DATA LAYOUT (HBM): warp-tiled structure-of-arrays (TILE = 32 particles per tile; for NX >= 8 TILE = 1, i.e. every
+// particle's stage block is contiguous and Mpad = M — see Solver::TILE).  Particle i of problem b owns slot
 // g = b*Mpad + i (Mpad = M rounded up to a warp for M > 1, so a warp never straddles two problems);
 // per-(particle, stage) arrays are stored as
 //     arr[(((g / 32) * N + j) * E + e) * 32 + g % 32]     j = stage, e = element of E
@@ -38,7 +39,8 @@ struct FactorSet {
 
 struct DevProb {
   int B, M, N, n, m, Nc, D;   // logical sizes; D = Nc * NU (padded control dim)
-  int Mpad;                   // particle slots per problem (M == 1 ? 1 : M rounded up to 32)
+  int Mpad;                   // particle slots per problem (M == 1 ? 1 : M rounded up to the tile)
+  int tile;                   // particles per layout tile: 32, or 1 for NX >= 8 (== Solver::TILE)
   int P;                      // number of particle slots, B * Mpad rounded up to 32
   int dyn_kind;
   int has_ubox, has_xbox, has_slew;
@@ -79,6 +81,15 @@ struct DevProb {
   unsigned long long seq0;              // exchange sequence number before this launch (same on every rank)
   double* peer[8];                      // exchange buffer of every rank (peer[rank] is this GPU's own)
   unsigned long long xtimeout_ns;       // bounded spin of the exchange (pmpc_comm_set_timeout; default 30 s)
+  // warp-per-particle kernel (wpp.cuh): team exchange buffers [per problem: Tc part slots | bcast | flags], their slot
+  // size, the team sequence number before this launch, per-warp / per-CTA consensus partials, and the hand-over flags
+  // (fb[b] = 1: problem b is continued by the thread-per-particle kernel launched behind it with resume = 1)
+  double* tm;
+  int tm_cap;
+  unsigned long long tseq0;
+  double* wscr;
+  int* fb;
+  int resume;
   int* xerr;                            // device flag: an exchange timed out (read back by pmpc_sync)
 };
 
@@ -156,6 +167,10 @@ struct Solver {
   // in local memory) it turns the dynamic indices into constant offsets and lets the loads pipeline — C4 (n = 12):
   // 1.53 s without unrolling, 0.45 s at 8, 0.21 s fully unrolled; bounded above by compile time and code size
   static constexpr int UNR = (NX <= 4) ? 64 : (NX <= 12 ? 16 : (NX <= 16 ? 8 : 4));
+  // particles per layout tile (DATA LAYOUT above): 32 for the thread-per-particle shapes; 1 for NX >= 8, where the
+  // stage block of ONE particle is contiguous — the layout of the warp-per-particle kernel (wpp.cuh), which these
+  // thread-per-particle kernels only back up (state-box ADMM, interior-point fallback)
+  static constexpr int TILE = (NX >= 8) ? 1 : 32;
 
   const DevProb& pb;
   const size_t P;
@@ -200,9 +215,21 @@ struct Solver {
     s = pb.has_slew ? pb.slew[g] : 0.0;
   }
 
+  // Helper instance for the warp-per-particle kernel (wpp.cuh): only the CTA-cooperative shared-block routines and the
+  // cross-GPU exchange are used; it owns no particle.
+  __device__ Solver(const DevProb& pb_, double* red_, double* red2_, int prob_)
+      : pb(pb_), P(pb_.P), N(pb_.N), Nc(GROUPED ? pb_.Nc : 0), D(GROUPED ? pb_.D : 0), T(blockDim.x),
+        tid(threadIdx.x), red(red_), red2(red2_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0), xdead(false) {
+    dead = false;
+    prob = prob_;
+    valid = false;
+    g = prob_ * pb.Mpad;
+    s = 0.0;
+  }
+
   // warp-tile SoA index of element e (of E) of stage j for particle slot gg (see DATA LAYOUT above)
   __device__ __forceinline__ size_t ixg(int j, int E, int e, size_t gg) const {
-    return (((gg >> 5) * (size_t)N + (size_t)j) * (size_t)E + (size_t)e) * 32 + (gg & 31);
+    return (((gg / TILE) * (size_t)N + (size_t)j) * (size_t)E + (size_t)e) * TILE + (gg % TILE);
   }
   __device__ __forceinline__ size_t ix(int j, int E, int e) const { return ixg(j, E, e, (size_t)g); }
   __device__ __forceinline__ double& at(double* a, int j, int E, int e) const { return a[ix(j, E, e)]; }
@@ -1429,6 +1456,14 @@ struct Solver {
                           !((VAR & 2) && pb.has_slew);
     double *solX = Xc, *solU = Uc;
     int it = 0;
+    if (pb.resume) {
+      // launched behind the warp-per-particle kernel: continue only the problems it handed over, at their iteration
+      if (!valid || !pb.fb[prob]) {
+        if (!GROUPED || !pb.fb[prob]) return;
+      }
+      for (int k = 0; k < 8; ++k) cnt[k] = pb.info[(size_t)k * pb.B + prob];
+      it = (int)cnt[0];
+    }
     for (; it < pb.max_it; ++it) {
       const long long admm0 = cnt[1];
       int status = -1;

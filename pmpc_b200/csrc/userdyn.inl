@@ -78,9 +78,9 @@ extern "C" __global__ void pmpc_user_linearize(
   if (j >= N || sl >= (unsigned long long)B * Mpad || (int)(sl % Mpad) >= M) return;
   const int b = (int)(sl / Mpad);
   if (done != nullptr && done[b]) return;
-  const unsigned long long tile = (sl >> 5) * (unsigned long long)N;
-  const int lane = (int)(sl & 31);
-#define PMPC_TIX(jj, E, e) ((((tile + (jj)) * (E)) + (e)) * 32 + lane)
+  const unsigned long long tile = (sl / PMPC_TILE) * (unsigned long long)N;
+  const int lane = (int)(sl % PMPC_TILE);
+#define PMPC_TIX(jj, E, e) ((((tile + (jj)) * (E)) + (e)) * PMPC_TILE + lane)
   double x[PMPC_N], u[PMPC_M], p[PMPC_NP > 0 ? PMPC_NP : 1], f[PMPC_N], fx[PMPC_N * PMPC_N], fu[PMPC_N * PMPC_M];
   for (int e = 0; e < PMPC_N; ++e) x[e] = (j == 0) ? x0[(unsigned long long)e * P + sl] : Xp[PMPC_TIX(j - 1, PMPC_NX, e)];
   for (int e = 0; e < PMPC_M; ++e) u[e] = Up[PMPC_TIX(j, PMPC_NU, e)];
@@ -127,9 +127,9 @@ __global__ void ud_snapshot_kernel(DevProb pb, int NX, int NU, const int* __rest
   const int j = (int)(idx / P);
   if (j >= pb.N || sl >= (size_t)pb.B * pb.Mpad) return;
   if (done[sl / pb.Mpad]) return;
-  const size_t tile = (sl >> 5) * (size_t)pb.N + j, lane = sl & 31;
-  for (int e = 0; e < NX; ++e) Xf[(tile * NX + e) * 32 + lane] = pb.X[(tile * NX + e) * 32 + lane];
-  for (int e = 0; e < NU; ++e) Uf[(tile * NU + e) * 32 + lane] = pb.U[(tile * NU + e) * 32 + lane];
+  const size_t TL = (size_t)pb.tile, tile = (sl / TL) * (size_t)pb.N + j, lane = sl % TL;
+  for (int e = 0; e < NX; ++e) Xf[(tile * NX + e) * TL + lane] = pb.X[(tile * NX + e) * TL + lane];
+  for (int e = 0; e < NU; ++e) Uf[(tile * NU + e) * TL + lane] = pb.U[(tile * NU + e) * TL + lane];
 }
 
 // per problem: accumulate the launch's counters, apply the stop rule (scp_mpc.py:424), count the survivors
@@ -154,16 +154,16 @@ __global__ void ud_restore_kernel(DevProb pb, int NX, int NU, const double* __re
   const size_t sl = idx % P;
   const int j = (int)(idx / P);
   if (j >= pb.N || sl >= (size_t)pb.B * pb.Mpad) return;
-  const size_t tile = (sl >> 5) * (size_t)pb.N + j, lane = sl & 31;
+  const size_t TL = (size_t)pb.tile, tile = (sl / TL) * (size_t)pb.N + j, lane = sl % TL;
   for (int e = 0; e < NX; ++e) {
-    const double v = Xf[(tile * NX + e) * 32 + lane];
-    pb.X[(tile * NX + e) * 32 + lane] = v;
-    pb.Xp[(tile * NX + e) * 32 + lane] = v;
+    const double v = Xf[(tile * NX + e) * TL + lane];
+    pb.X[(tile * NX + e) * TL + lane] = v;
+    pb.Xp[(tile * NX + e) * TL + lane] = v;
   }
   for (int e = 0; e < NU; ++e) {
-    const double v = Uf[(tile * NU + e) * 32 + lane];
-    pb.U[(tile * NU + e) * 32 + lane] = v;
-    pb.Up[(tile * NU + e) * 32 + lane] = v;
+    const double v = Uf[(tile * NU + e) * TL + lane];
+    pb.U[(tile * NU + e) * TL + lane] = v;
+    pb.Up[(tile * NU + e) * TL + lane] = v;
   }
 }
 
@@ -221,7 +221,7 @@ int pmpc_register_dynamics(pmpc_handle_t h, const char* cuda_src, const char* fn
   const DevProb& pb = h->pb;
   std::string src = "#define PMPC_N " + std::to_string(pb.n) + "\n#define PMPC_M " + std::to_string(pb.m) +
                     "\n#define PMPC_NX " + std::to_string(h->shape.NX) + "\n#define PMPC_NU " + std::to_string(h->shape.NU) +
-                    "\n#define PMPC_NP " + std::to_string(nparam) + "\n#define PMPC_USER_FN " + fn_name + "\n#line 1 \"user_dynamics.cu\"\n" +
+                    "\n#define PMPC_NP " + std::to_string(nparam) + "\n#define PMPC_TILE " + std::to_string(pb.tile) + "\n#define PMPC_USER_FN " + fn_name + "\n#line 1 \"user_dynamics.cu\"\n" +
                     cuda_src + "\n#line 1 \"pmpc_user_wrapper.cu\"\n" + kUserWrapper;
   void* prog = nullptr;
   int rc = rt->CreateProgram(&prog, src.c_str(), "pmpc_user.cu", 0, nullptr, nullptr);

@@ -1,0 +1,971 @@
+// Warp-per-particle SCP kernel for the larger shapes (NX >= 8: BASELINE configs 4 and 5).
+//
+// north_star: "the KKT system is factored per particle by a warp/CTA-resident fp64 Riccati recursion, with matrices
+// staged in shared memory and reductions by warp shuffles; particles are coupled through a Schur complement on the
+// shared u[0:Nc] block".  Replaces lqp_repr_Pq / lqp_repr_Ab / lqp_repr_Gla + OSQP (lqp_utils.jl:2-393,
+// osqp_solver.jl:34-72) on 12x12 ... 32x32 stage blocks, where the thread-per-particle kernels of solver.cuh keep the
+// matrices in per-thread local memory (7 447 LDL vs 4 660 DFMA in the n = 32 SASS) and one problem on ONE SM.
+//
+// * ONE WARP owns one particle.  Lane l owns column l of the n x n matrices (S = Q + P, A, S A, P') and element l of
+//   the vectors; S, A, B, S B + W, G live in the warp's shared-memory slab, the second operand of every product is a
+//   broadcast LDS, the accumulators (a whole column) stay in registers.  Small m x m systems (H, its masked inverse)
+//   are solved redundantly per lane.
+// * The particles of a problem are spread over a TEAM of CTAs (team size 1 for batches of small problems); the
+//   consensus terms (sum_i H_i, sum_i g_i: the Schur complement on the shared block) and the pass statistics are
+//   combined through global memory with a flag protocol (team_reduce / team_bcast), the team leader solves the
+//   shared block and — for particles sharded over GPUs — runs the cross-GPU exchange of solver.cuh (Solver::xreduce).
+// * Same algorithm, same hand-off format and same acceptance tests as the fused two-sweep active-set pass of
+//   fused.inl (bsweep / fsweep): a QP whose active set is right costs one pass.  What this kernel does not do — a
+//   state bound that wants to be active (ADMM), an active-set iteration that cycles (interior point) — is handed to
+//   the thread-per-particle kernel of the same shape, which resumes the SCP loop at the failed iteration (DevProb::fb).
+//
+// Data layout: TILE = 1 (solver.cuh): element e of stage j of particle slot g is arr[(g * N + j) * E + e].
+#pragma once
+#include <cooperative_groups.h>
+
+#include "solver.cuh"
+
+namespace pmpc {
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int NX, int NU, bool SLEW>
+struct Wpp {
+  static constexpr int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2, NHO = NR - NU;
+  static constexpr int LDF = NX + 1;  // padded leading dimension where lanes read different ROWS of a shared matrix
+  // hand-off block of one (particle, stage), same format as Solver::NH with HL = 0: [K | k | strict upper H]
+  static constexpr int H_K = 0, H_KF = NU * NX, H_H = H_KF + NU, NH = H_H + NHO;
+  __host__ __device__ static constexpr int pko(int a, int b) { return a * NU - (a * (a + 1)) / 2 + (b - a - 1); }  // a < b
+  // per-warp shared-memory slab (doubles)
+  static constexpr int O_S = 0;                       // S = Qs + P, later S A           (NX x NX)
+  static constexpr int O_A = O_S + NX * NX;           // A (bsweep: ld NX; fsweep: ld LDF) (NX x LDF)
+  static constexpr int O_B = O_A + NX * LDF;          // B                               (NX x NU)
+  static constexpr int O_SBW = O_B + NX * NU;         // S B + W                         (NX x NU)
+  static constexpr int O_W = O_SBW + NX * NU;         // W (slew block of the value function) (NX x NU)
+  static constexpr int O_G = O_W + NX * NU;           // G (bsweep) / K or G rows (fsweep) (NU x LDF)
+  static constexpr int O_V = O_G + NU * LDF;          // vectors: c, wv, x, a, dx        (5 x NX)
+  static constexpr int O_M = O_V + 5 * NX;            // H, E, Z                         (3 x NU x NU)
+  static constexpr int O_U = O_M + 3 * NU * NU;       // h0, h, kv, ufix, u, up, z, r, lo, hi, du, kf (12 x NU)
+  static constexpr int SLAB = ((O_U + 12 * NU + 1) / 2) * 2;
+  static constexpr int V_C = 0, V_WV = NX, V_X = 2 * NX, V_AD = 3 * NX, V_DX = 4 * NX;
+  static constexpr int MM_H = 0, MM_E = NU * NU, MM_Z = 2 * NU * NU;
+  static constexpr int U_H0 = 0, U_H = NU, U_KV = 2 * NU, U_UF = 3 * NU, U_U = 4 * NU, U_UP = 5 * NU, U_Z = 6 * NU,
+                       U_R = 7 * NU, U_LO = 8 * NU, U_HI = 9 * NU, U_DU = 10 * NU, U_KF = 11 * NU;
+  static constexpr int DMAX = 64;  // largest shared block (Nc * NU) this kernel takes; beyond it the old kernel runs
+
+  // ------------------------------------------------------------------------------------------------------------
+  // team exchange through global memory (all threads of the CTA call these)
+  struct Team {
+    double* part;                 // [Tc][cap]
+    double* bc;                   // [cap]
+    unsigned long long* pflag;    // [Tc]
+    unsigned long long* bflag;    // [1]
+    int Tc, idx, cap;
+    unsigned long long seq;
+    bool dead;
+  };
+
+  const DevProb& pb;
+  unsigned char* smem;
+  const int lane, wid, W, tid, T;
+  const int lc;        // lane clamped to the matrix dimension (lanes >= NX mirror lane NX - 1 and never store)
+  const bool lact;
+  int prob, N, Nc, D, M;
+  double *Xc, *Uc;             // iterate being written
+  const double *Xpv, *Upv;     // linearisation point
+  bool flip;
+  Team tm;
+  double* cred;                // CTA exchange area in shared memory behind the slabs (cred_doubles)
+  __host__ __device__ static constexpr int cred_doubles(int W_) { return 16 + (W_ + 1) * ST_COUNT; }
+
+  __device__ Wpp(const DevProb& pb_, unsigned char* smem_)
+      : pb(pb_), smem(smem_), lane(threadIdx.x & 31), wid(threadIdx.x >> 5), W(blockDim.x >> 5), tid(threadIdx.x),
+        T(blockDim.x), lc((threadIdx.x & 31) < NX ? (threadIdx.x & 31) : NX - 1), lact((threadIdx.x & 31) < NX) {}
+
+  __device__ __forceinline__ double* slab() const { return reinterpret_cast<double*>(smem) + (size_t)wid * SLAB; }
+  __device__ __forceinline__ static size_t gix(size_t g, int N_, int j, int E) { return (g * (size_t)N_ + (size_t)j) * (size_t)E; }
+
+  __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want) {
+    unsigned long long t0 = 0, spins = 0;
+    while (ld_acquire_gpu(flag) < want) {
+      if ((++spins & 255ull) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > pb.xtimeout_ns) return false;
+      }
+    }
+    return true;
+  }
+
+  // Every CTA of the team contributes vec[0..len); the leader (idx 0) receives the combination in out (CTA order:
+  // deterministic).  sum_mask bit k (k < 32) set, or all_sum: element k is summed, otherwise max-reduced.
+  __device__ __noinline__ void team_reduce(const double* vec, int len, double* out, bool all_sum, unsigned sum_mask) {
+    if (tm.Tc == 1) {
+      if (out != vec) {
+        __syncthreads();
+        for (int k = tid; k < len; k += T) out[k] = vec[k];
+      }
+      __syncthreads();
+      return;
+    }
+    __syncthreads();
+    ++tm.seq;
+    if (tm.dead) return;
+    double* mine = tm.part + (size_t)tm.idx * tm.cap;
+    for (int k = tid; k < len; k += T) __stcg(mine + k, vec[k]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu(tm.pflag + tm.idx, tm.seq);
+    if (tm.idx != 0) return;
+    __shared__ int ok_s;
+    if (tid == 0) ok_s = 1;
+    __syncthreads();
+    for (int c = tid; c < tm.Tc; c += T)
+      if (!spin_until(tm.pflag + c, tm.seq)) ok_s = 0;
+    __syncthreads();
+    if (!ok_s) {
+      if (tid == 0) *pb.xerr = 1;
+      tm.dead = true;
+      return;
+    }
+    for (int k = tid; k < len; k += T) {
+      const bool is_sum = all_sum || (k < 32 && ((sum_mask >> k) & 1u));
+      double acc = __ldcg(tm.part + k);
+      for (int c = 1; c < tm.Tc; ++c) {
+        const double v = __ldcg(tm.part + (size_t)c * tm.cap + k);
+        acc = is_sum ? acc + v : fmax(acc, v);
+      }
+      out[k] = acc;
+    }
+    __syncthreads();
+  }
+
+  // leader: vec -> every CTA of the team (vec is a shared-memory or global buffer of each CTA)
+  __device__ __noinline__ void team_bcast(double* vec, int len) {
+    if (tm.Tc == 1) {
+      __syncthreads();
+      return;
+    }
+    __syncthreads();
+    if (tm.idx == 0) {
+      if (tm.dead) {  // release the others with a poisoned sequence so that they stop as well
+        if (tid == 0) {
+          __stcg(tm.bc + tm.cap - 1, 1.0);
+          __threadfence();
+          st_release_gpu(tm.bflag, tm.seq);
+        }
+        return;
+      }
+      for (int k = tid; k < len; k += T) __stcg(tm.bc + k, vec[k]);
+      if (tid == 0) __stcg(tm.bc + tm.cap - 1, 0.0);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_gpu(tm.bflag, tm.seq);
+      return;
+    }
+    if (tm.dead) return;
+    __shared__ int ok_b;
+    if (tid == 0) ok_b = spin_until(tm.bflag, tm.seq) ? 1 : 0;
+    __syncthreads();
+    if (!ok_b || __ldcg(tm.bc + tm.cap - 1) != 0.0) {
+      if (tid == 0 && !ok_b) *pb.xerr = 1;
+      tm.dead = true;
+      return;
+    }
+    for (int k = tid; k < len; k += T) vec[k] = __ldcg(tm.bc + k);
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Masked inverse E = embed(inv(H[free, free])) of the m x m stage Hessian in shared memory (Hs): every lane
+  // factors the masked matrix redundantly (registers, no exchange), lane t < NU solves for column t and stores it.
+  // The solves multiply by the stored reciprocals of the diagonal instead of dividing.
+  __device__ __forceinline__ static void masked_inverse(const double* Hs, unsigned fmask, int t, double* Es) {
+    double L[NR], idg[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        const bool fx = ((fmask >> a) | (fmask >> b)) & 1u;
+        L[pk(b, a, NU)] = fx ? (a == b ? 1.0 : 0.0) : Hs[a * NU + b];  // L[a][b], b <= a, packed as pk(b, a)
+      }
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      double dk = L[pk(k, k, NU)];
+#pragma unroll
+      for (int q = 0; q < k; ++q) dk -= L[pk(q, k, NU)] * L[pk(q, k, NU)];
+      const double idk = 1.0 / sqrt(dk);
+      idg[k] = idk;
+#pragma unroll
+      for (int i = k + 1; i < NU; ++i) {
+        double v = L[pk(k, i, NU)];
+#pragma unroll
+        for (int q = 0; q < k; ++q) v -= L[pk(q, i, NU)] * L[pk(q, k, NU)];
+        L[pk(k, i, NU)] = v * idk;
+      }
+    }
+    if (t < NU) {
+      double y[NU];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        double v = (i == t) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < i; ++q) v -= L[pk(q, i, NU)] * y[q];
+        y[i] = v * idg[i];
+      }
+#pragma unroll
+      for (int i = NU - 1; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int q = i + 1; q < NU; ++q) v -= L[pk(i, q, NU)] * y[q];
+        y[i] = v * idg[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) Es[i * NU + t] = (((fmask >> i) | (fmask >> t)) & 1u) ? 0.0 : y[i];
+    }
+  }
+
+  __device__ __forceinline__ static double qs_at(const double* Qp, int r, int t) {
+    return Qp[r <= t ? pk(r, t, NX) : pk(t, r, NX)];
+  }
+  __device__ __forceinline__ static double rs_at(const double* Rp, int a, int b) {
+    return Rp[a <= b ? pk(a, b, NU) : pk(b, a, NU)];
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Backward sweep of particle slot g over the free stages j = N-1 .. Nc (fused.inl bsweep, generic branch): masked
+  // Riccati matrix + vector step; writes the hand-off block.  On return (Nc >= 1) the boundary value function sits in
+  // the slab: Pc in O_S, Wc in O_W, Zc in MM_Z, pc in V_WV, zc in U_Z.
+  __device__ __forceinline__ void bsweep(size_t g) {
+    double* sl = slab();
+    double *Sm = sl + O_S, *Am = sl + O_A, *Bm = sl + O_B, *SBWm = sl + O_SBW, *Wm = sl + O_W, *Gm = sl + O_G;
+    double *cv = sl + O_V + V_C, *wvv = sl + O_V + V_WV;
+    double *Hm = sl + O_M + MM_H, *Em = sl + O_M + MM_E, *Zm = sl + O_M + MM_Z;
+    double *h0m = sl + O_U + U_H0, *hm = sl + O_U + U_H, *kvm = sl + O_U + U_KV, *ufm = sl + O_U + U_UF, *zm = sl + O_U + U_Z,
+           *rm = sl + O_U + U_R;
+    const int l = lane;
+    const double s = SLEW ? pb.slew[g] : 0.0;
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    double Pcol[NX], p_l = 0.0;
+#pragma unroll
+    for (int r = 0; r < NX; ++r) Pcol[r] = 0.0;
+    for (int idx = l; idx < NX * NU; idx += 32) Wm[idx] = 0.0;
+    for (int idx = l; idx < NU * NU; idx += 32) Zm[idx] = 0.0;
+    if (l < NU) zm[l] = 0.0;
+    __syncwarp();
+    for (int j = N - 1; j >= Nc; --j) {
+      // ---- P0: stage data into the slab
+      const double* Ag = pb.A + gix(g, N, j, NX * NX);
+      const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
+      const double* Qg = pb.Qs + gix(g, N, j, NQ);
+      const double* Rg = pb.Rs + gix(g, N, j, NR);
+      if (j >= 1) {
+#pragma unroll 8
+        for (int k = 0; k < NX; ++k) {
+          const double a = Ag[k * NX + lc];
+          if (lact) Am[k * NX + l] = a;
+        }
+      }
+      for (int idx = l; idx < NX * NU; idx += 32) Bm[idx] = Bg[idx];
+#pragma unroll
+      for (int r = 0; r < NX; ++r) {
+        const double v = qs_at(Qg, r, lc) + Pcol[r];
+        if (lact) Sm[r * NX + l] = v;
+      }
+      double q_l = 0.0;
+      if (lact) {
+        cv[l] = pb.c[gix(g, N, j, NX) + l];
+        q_l = -pb.qref[gix(g, N, j, NX) + l] - pb.reg_x * Xpv[gix(g, N, j, NX) + l];
+      }
+      bool fixed_l = false;
+      if (l < NU) {
+        const double ub = Upv[gix(g, N, j, NU) + l];
+        rm[l] = -pb.rref[gix(g, N, j, NU) + l] - pb.reg_u * ub;
+        double uf = 0.0;
+        if (pb.has_ubox) {
+          const signed char a = pb.act[gix(g, N, j, NU) + l];
+          if (a != 0) uf = (a > 0) ? pb.uu[gix(g, N, j, NU) + l] : pb.lu[gix(g, N, j, NU) + l];
+          fixed_l = (a != 0);
+        }
+        ufm[l] = uf;
+      }
+      const unsigned fmask = __ballot_sync(0xffffffffu, fixed_l);  // bit a: control a of this stage sits at a bound
+      __syncwarp();
+      // ---- P1: wv = S c + q + p (element l), row l of S B + W.  S is symmetric: row l is read as column l
+      {
+        double wv = q_l + p_l;
+        double acc[NU];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) acc[a] = SLEW ? Wm[lc * NU + a] : 0.0;
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) {
+          const double sk = Sm[k * NX + lc];
+          wv += sk * cv[k];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) acc[a] += sk * Bm[k * NU + a];
+        }
+        if (lact) {
+          wvv[l] = wv;
+#pragma unroll
+          for (int a = 0; a < NU; ++a) SBWm[l * NU + a] = acc[a];
+        }
+      }
+      __syncwarp();
+      // ---- P2: H = Rs + [j>=1] s I + B'(S B + W) + W'B + Z (pairs over lanes), h0 = r + B'wv + W'c + z
+      for (int pi = l; pi < NR; pi += 32) {
+        int a = 0, rem = pi;
+        while (rem >= NU - a) { rem -= NU - a; ++a; }
+        const int b = a + rem;
+        double acc = Rg[pi];
+        if (SLEW) {
+          acc += Zm[a * NU + b];
+          if (a == b && j >= 1) acc += s;
+        }
+        for (int k = 0; k < NX; ++k) {
+          acc += Bm[k * NU + a] * SBWm[k * NU + b];
+          if (SLEW) acc += Wm[k * NU + a] * Bm[k * NU + b];
+        }
+        Hm[a * NU + b] = acc;
+        Hm[b * NU + a] = acc;
+      }
+      if (l < NU) {
+        double acc = rm[l] + (SLEW ? zm[l] : 0.0);
+        for (int k = 0; k < NX; ++k) {
+          acc += Bm[k * NU + l] * wvv[k];
+          if (SLEW) acc += Wm[k * NU + l] * cv[k];
+        }
+        h0m[l] = acc;
+      }
+      __syncwarp();
+      // ---- P3: masked inverse, h = h0 + H ufix, k = ufix - E h
+      masked_inverse(Hm, fmask, l, Em);
+      if (l < NU) {
+        double hv = h0m[l];
+#pragma unroll
+        for (int t = 0; t < NU; ++t) hv += Hm[l * NU + t] * ufm[t];
+        hm[l] = hv;
+      }
+      __syncwarp();
+      if (l < NU) {
+        double kv = ufm[l];
+#pragma unroll
+        for (int b = 0; b < NU; ++b) kv -= Em[l * NU + b] * hm[b];
+        kvm[l] = kv;
+      }
+      __syncwarp();
+      double Kc[NU], Gc[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) { Kc[a] = 0.0; Gc[a] = 0.0; }
+      if (j >= 1) {
+        // ---- P4: column l of G = (S B + W)' A, K = -E G, p' = A' wv + G' k, S A
+        double pn = 0.0;
+        double SAc[NX];
+#pragma unroll
+        for (int r = 0; r < NX; ++r) SAc[r] = 0.0;
+#pragma unroll 2
+        for (int k = 0; k < NX; k += 2) {
+          const double a0 = Am[k * NX + lc], a1 = Am[(k + 1) * NX + lc];
+          pn += a0 * wvv[k] + a1 * wvv[k + 1];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) Gc[a] += SBWm[k * NU + a] * a0 + SBWm[(k + 1) * NU + a] * a1;
+#pragma unroll
+          for (int r = 0; r < NX; ++r) {
+            const double2 sv = *reinterpret_cast<const double2*>(&Sm[r * NX + k]);
+            SAc[r] += sv.x * a0 + sv.y * a1;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          double acc = 0.0;
+#pragma unroll
+          for (int b = 0; b < NU; ++b) acc -= Em[a * NU + b] * Gc[b];
+          Kc[a] = acc;
+          pn += Gc[a] * kvm[a];
+        }
+        __syncwarp();  // every lane has finished reading S
+        if (lact) {
+#pragma unroll
+          for (int r = 0; r < NX; ++r) Sm[r * NX + l] = SAc[r];
+#pragma unroll
+          for (int a = 0; a < NU; ++a) Gm[a * LDF + l] = Gc[a];
+        }
+        __syncwarp();
+        // ---- P' = A' (S A) + G' K, column l
+#pragma unroll
+        for (int r = 0; r < NX; ++r) Pcol[r] = 0.0;
+#pragma unroll 2
+        for (int k = 0; k < NX; ++k) {
+          const double sa = Sm[k * NX + lc];
+#pragma unroll
+          for (int r = 0; r < NX; r += 2) {
+            const double2 av = *reinterpret_cast<const double2*>(&Am[k * NX + r]);
+            Pcol[r] += av.x * sa;
+            Pcol[r + 1] += av.y * sa;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < NU; ++a) {
+          const double ka = Kc[a];
+#pragma unroll
+          for (int r = 0; r < NX; ++r) Pcol[r] += Gm[a * LDF + r] * ka;
+        }
+        p_l = pn;
+      }
+      // ---- P5: hand-off (fixed controls carry G[a,:], h[a] for the multiplier), next stage's slew blocks
+      {
+        double* hg = pb.hand + gix(g, N, j, NH);
+        if (lact) {
+#pragma unroll
+          for (int a = 0; a < NU; ++a) hg[H_K + a * NX + l] = ((fmask >> a) & 1u) ? Gc[a] : Kc[a];
+        }
+        if (l < NU) hg[H_KF + l] = ((fmask >> l) & 1u) ? hm[l] : kvm[l];
+        if (pb.has_ubox) {
+          for (int pi = l; pi < NHO; pi += 32) {
+            int a = 0, rem = pi;
+            while (rem >= NU - 1 - a) { rem -= NU - 1 - a; ++a; }
+            const int b = a + 1 + rem;
+            hg[H_H + pi] = Hm[a * NU + b];
+          }
+        }
+        if (SLEW) {
+          double* Eg = F.E + gix(g, N, j, NR);
+          for (int pi = l; pi < NR; pi += 32) {
+            int a = 0, rem = pi;
+            while (rem >= NU - a) { rem -= NU - a; ++a; }
+            Eg[pi] = Em[a * NU + a + rem];
+          }
+        }
+      }
+      __syncwarp();  // all reads of W, Z, z, E of this stage are done
+      if (SLEW) {
+        if (lact) {
+#pragma unroll
+          for (int a = 0; a < NU; ++a) Wm[l * NU + a] = -s * Kc[a];
+        }
+        for (int idx = l; idx < NU * NU; idx += 32) Zm[idx] = ((idx / NU == idx % NU) ? s : 0.0) - s * s * Em[idx];
+        if (l < NU) zm[l] = (j >= 1) ? -s * kvm[l] : 0.0;
+      }
+      __syncwarp();
+    }
+    // boundary value function for the consensus step
+    if (lact) {
+#pragma unroll
+      for (int r = 0; r < NX; ++r) Sm[r * NX + l] = Pcol[r];
+      wvv[l] = p_l;
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Gradient of the particle's cost w.r.t. the shared controls (Solver::shared_grad): hom: Hessian action on the unit
+  // vector ek, else the gradient at uc = 0 with all linear terms.  The boundary value function is in the slab (see
+  // bsweep).  Result: lane b < NU holds out[j * NU + b] for the stage it is called back with.  Xc rows 0 .. Nc-1 are
+  // used as scratch for the shared-stage states, as in the thread-per-particle kernel.
+  template <typename Emit>
+  __device__ __forceinline__ void shared_grad(size_t g, bool hom, int ek, Emit emit) {
+    double* sl = slab();
+    double *Pc = sl + O_S, *Wc = sl + O_W, *Zc = sl + O_M + MM_Z, *pcv = sl + O_V + V_WV, *zc = sl + O_U + U_Z;
+    double *xv = sl + O_V + V_X, *av = sl + O_V + V_AD;
+    const int l = lane;
+    const double s = SLEW ? pb.slew[g] : 0.0;
+    auto uval = [&](int j, int t) -> double { return (hom && j >= 0 && j < Nc && j * NU + t == ek) ? 1.0 : 0.0; };
+    if (lact) xv[l] = 0.0;
+    __syncwarp();
+    for (int j = 0; j < Nc; ++j) {
+      const double* Ag = pb.A + gix(g, N, j, NX * NX);
+      const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
+      double acc = hom ? 0.0 : pb.c[gix(g, N, j, NX) + lc];
+      if (j >= 1)
+        for (int t = 0; t < NX; ++t) acc += Ag[lc * NX + t] * xv[t];
+      for (int t = 0; t < NU; ++t) acc += Bg[lc * NU + t] * uval(j, t);
+      __syncwarp();
+      if (lact) {
+        xv[l] = acc;
+        Xc[gix(g, N, j, NX) + l] = acc;
+      }
+      __syncwarp();
+    }
+    if (lact) av[l] = 0.0;
+    __syncwarp();
+    for (int j = Nc - 1; j >= 0; --j) {
+      const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
+      const double* Qg = pb.Qs + gix(g, N, j, NQ);
+      const double* Rg = pb.Rs + gix(g, N, j, NR);
+      if (lact) xv[l] = Xc[gix(g, N, j, NX) + l];
+      __syncwarp();
+      double an = 0.0, gu = 0.0;
+      if (!hom) {
+        an = -pb.qref[gix(g, N, j, NX) + lc] - pb.reg_x * Xpv[gix(g, N, j, NX) + lc];
+        if (l < NU) gu = -pb.rref[gix(g, N, j, NU) + l] - pb.reg_u * Upv[gix(g, N, j, NU) + l];
+      }
+      for (int t = 0; t < NX; ++t) an += qs_at(Qg, lc, t) * xv[t];
+      if (l < NU)
+        for (int t = 0; t < NU; ++t) gu += rs_at(Rg, l, t) * uval(j, t);
+      if (j == Nc - 1) {
+        double acc = hom ? 0.0 : pcv[lc];
+        for (int t = 0; t < NX; ++t) acc += Pc[t * NX + lc] * xv[t];  // Pc symmetric: row l read as column l
+        if (SLEW)
+          for (int t = 0; t < NU; ++t) acc += Wc[lc * NU + t] * uval(j, t);
+        an += acc;
+        if (SLEW && l < NU) {
+          double a2 = hom ? 0.0 : zc[l];
+          for (int r = 0; r < NX; ++r) a2 += Wc[r * NU + l] * xv[r];
+          for (int t = 0; t < NU; ++t) a2 += Zc[l * NU + t] * uval(j, t);
+          gu += a2;
+        }
+      } else {
+        const double* An = pb.A + gix(g, N, j + 1, NX * NX);
+        for (int r = 0; r < NX; ++r) an += An[r * NX + lc] * av[r];
+        if (SLEW && l < NU) gu += s * (uval(j, l) - uval(j + 1, l));
+      }
+      if (SLEW && j >= 1 && l < NU) gu += s * (uval(j, l) - uval(j - 1, l));
+      __syncwarp();
+      if (lact) av[l] = an;
+      __syncwarp();
+      if (l < NU) {
+        double acc = gu;
+        for (int r = 0; r < NX; ++r) acc += Bg[r * NU + l] * av[r];
+        emit(j, acc);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Forward sweep of particle slot g (fused.inl fsweep, generic branch): rollout of the policy, multipliers and
+  // primal-dual update of the free-stage active set, SCP bookkeeping.  st: per-warp statistics (valid in every lane).
+  __device__ __forceinline__ void fsweep(size_t g, double* st) {
+    double* sl = slab();
+    double *Am = sl + O_A, *Bm = sl + O_B, *Km = sl + O_G;
+    double *cv = sl + O_V + V_C, *xv = sl + O_V + V_X, *dxv = sl + O_V + V_DX;
+    double *um = sl + O_U + U_U, *upm = sl + O_U + U_UP, *dum_ = sl + O_U + U_DU, *kfm = sl + O_U + U_KF, *lom = sl + O_U + U_LO,
+           *him = sl + O_U + U_HI;
+    double* Hoff = sl + O_M + MM_H;  // strict upper triangle of the stage Hessian (NHO)
+    double* Es = sl + O_M + MM_E;    // packed E (NR) with a slew penalty
+    const int l = lane;
+    const double s = SLEW ? pb.slew[g] : 0.0;
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    const double* uc = (Nc >= 1) ? pb.uc + (size_t)prob * D : nullptr;  // written by the team leader: read through L2
+    const double rdiag = pb.rdiag0[g];
+    double x_l = 0.0;
+    double dxm = 0.0, dum = 0.0, obj = 0.0, nanf = 0.0, kkt_v = 0.0, uviol = 0.0, xviol = 0.0, changed = 0.0, gscale = 1.0,
+           zscale = 1.0;
+    if (lact) xv[l] = 0.0;
+    if (l < NU) upm[l] = 0.0;
+    __syncwarp();
+    for (int j = 0; j < N; ++j) {
+      const double* Ag = pb.A + gix(g, N, j, NX * NX);
+      const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
+      const double* hg = pb.hand + gix(g, N, j, NH);
+      if (j >= 1) {
+#pragma unroll 8
+        for (int k = 0; k < NX; ++k) {
+          const double a = Ag[k * NX + lc];
+          if (lact) Am[k * LDF + l] = a;
+        }
+      }
+      for (int idx = l; idx < NX * NU; idx += 32) Bm[idx] = Bg[idx];
+      if (lact) cv[l] = pb.c[gix(g, N, j, NX) + l];
+      signed char act = 0;
+      double ub = 0.0, lo = -INFINITY, hi = INFINITY;
+      if (l < NU) {
+        ub = Upv[gix(g, N, j, NU) + l];
+        if (pb.has_ubox) {
+          lo = pb.lu[gix(g, N, j, NU) + l];
+          hi = pb.uu[gix(g, N, j, NU) + l];
+        }
+        lom[l] = lo;
+        him[l] = hi;
+      }
+      if (j >= Nc) {
+        if (lact) {
+#pragma unroll
+          for (int a = 0; a < NU; ++a) Km[a * LDF + l] = hg[H_K + a * NX + l];
+        }
+        if (l < NU) {
+          kfm[l] = hg[H_KF + l];
+          if (pb.has_ubox) act = pb.act[gix(g, N, j, NU) + l];
+        }
+        if (pb.has_ubox)
+          for (int pi = l; pi < NHO; pi += 32) Hoff[pi] = hg[H_H + pi];
+        if (SLEW) {
+          const double* Eg = F.E + gix(g, N, j, NR);
+          for (int pi = l; pi < NR; pi += 32) Es[pi] = Eg[pi];
+        }
+      }
+      unsigned amask = __ballot_sync(0xffffffffu, l < NU && act != 0);
+      __syncwarp();
+      // ---- controls
+      double u = 0.0, gx = 0.0;
+      if (l < NU) {
+        if (j < Nc) {
+          u = __ldcg(uc + j * NU + l);
+        } else {
+          if (j >= 1)
+            for (int t = 0; t < NX; ++t) gx += Km[l * LDF + t] * xv[t];
+          u = kfm[l] + gx;
+          if (SLEW && j >= 1)
+            for (int b = 0; b < NU; ++b) u += s * rs_at(Es, l, b) * upm[b];
+          if (act != 0) u = (act > 0) ? hi : lo;
+        }
+        um[l] = u;
+      }
+      __syncwarp();
+      if (l < NU && j >= Nc && pb.has_ubox) {
+        signed char na = 0;
+        if (act != 0) {
+          // dQ/du_a = H[a,:] u + G[a,:] x + h0[a] - s u_{j-1,a};  kf[a] already holds h0[a] + H[a, fixed] u_fixed
+          double acc = kfm[l] + gx;
+          for (int b = 0; b < NU; ++b)
+            if (b != l && !((amask >> b) & 1u)) acc += Hoff[l < b ? pko(l, b) : pko(b, l)] * um[b];
+          if (SLEW && j >= 1) acc -= s * upm[l];
+          const double mu = -acc;
+          if (act > 0) {
+            kkt_v = fmax(kkt_v, fmax(acc, 0.0));
+            if (mu > 0.0) na = 1;
+          } else {
+            kkt_v = fmax(kkt_v, fmax(-acc, 0.0));
+            if (mu < 0.0) na = -1;
+          }
+        } else {
+          uviol = fmax(uviol, fmax(u - hi, lo - u));
+          if (u - hi > 0.0 && hi < INFINITY) na = 1;
+          else if (u - lo < 0.0 && lo > -INFINITY) na = -1;
+        }
+        if (na != act) {
+          changed += 1.0;
+          pb.act[gix(g, N, j, NU) + l] = na;
+        }
+      }
+      // ---- x+ = A x + B u + c (row l; A_0 = 0: lqp_utils.jl:288-296)
+      double xn = cv[lc];
+      if (j >= 1)
+        for (int t = 0; t < NX; ++t) xn += Am[lc * LDF + t] * xv[t];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) xn += Bm[lc * NU + a] * um[a];
+      // ---- bookkeeping (scp_mpc.py:397-405) and the scales of the acceptance test
+      double d2 = 0.0, dx = 0.0;
+      if (lact) {
+        const double xp = Xpv[gix(g, N, j, NX) + l];
+        const double qr = pb.qref[gix(g, N, j, NX) + l];
+        Xc[gix(g, N, j, NX) + l] = xn;
+        const double d = xn - xp;
+        d2 = d * d;
+        dx = xn - pb.xref[gix(g, N, j, NX) + l];
+        if (!(xn == xn)) nanf = 1.0;
+        zscale = fmax(zscale, fabs(xn));
+        gscale = fmax(gscale, fabs(qr + pb.reg_x * xp));
+        if (pb.has_xbox)
+          xviol = fmax(xviol, fmax(xn - pb.ux[gix(g, N, j, NX) + l], pb.lx[gix(g, N, j, NX) + l] - xn));
+      }
+      double e2 = 0.0, du = 0.0;
+      if (l < NU) {
+        Uc[gix(g, N, j, NU) + l] = u;
+        const double d = u - ub;
+        e2 = d * d;
+        du = u - pb.uref[gix(g, N, j, NU) + l];
+        if (!(u == u)) nanf = 1.0;
+        zscale = fmax(zscale, fabs(u));
+        gscale = fmax(gscale, fabs(pb.rref[gix(g, N, j, NU) + l] + pb.reg_u * ub));
+      }
+      __syncwarp();  // every lane has read x, u_prev of the previous stage
+      if (lact) {
+        xv[l] = xn;
+        dxv[l] = dx;
+      }
+      if (l < NU) {
+        upm[l] = u;
+        dum_[l] = du;
+      }
+      dxm = fmax(dxm, warp_sum(d2));
+      dum = fmax(dum, warp_sum(e2));
+      __syncwarp();
+      {
+        const double* Qg = pb.Qs + gix(g, N, j, NQ);
+        const double* Rg = pb.Rs + gix(g, N, j, NR);
+        if (lact) {
+          double acc = 0.0;
+          for (int t = 0; t < NX; ++t) acc += qs_at(Qg, l, t) * dxv[t];
+          obj += dx * (acc - pb.reg_x * dx);
+        }
+        if (l < NU) {
+          double acc = 0.0;
+          for (int t = 0; t < NU; ++t) acc += rs_at(Rg, l, t) * dum_[t];
+          obj += du * (acc - (pb.reg_u + (j == 0 ? rdiag : 0.0)) * du);
+        }
+      }
+      x_l = xn;
+      __syncwarp();
+    }
+    (void)x_l;
+    st[ST_DX] = sqrt(dxm);
+    st[ST_DU] = sqrt(dum);
+    st[ST_OBJ] = warp_sum(obj);
+    st[ST_NAN] = warp_max(nanf);
+    st[ST_KKT] = warp_max(kkt_v);
+    st[ST_UVIOL] = warp_max(uviol);
+    st[ST_XVIOL] = warp_max(xviol);
+    st[ST_CHANGED] = warp_max(changed);
+    st[ST_GSCALE] = warp_max(gscale);
+    st[ST_ZSCALE] = warp_max(zscale);
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // One convex sub-problem: active-set passes (fused.inl fused_qp_impl).  Returns status bits, or -1 when the problem
+  // has to be handed to the thread-per-particle kernel (state bound active / active-set iteration stalls).
+  // S0: a Solver object of the same shape whose CTA-cooperative shared-block routines (factor_shared, apply_shared,
+  // shared_active_update, xreduce) are reused by the team leader.
+  template <typename S0T>
+  __device__ __forceinline__ int qp(S0T& S0, int ppw, int ppc, double* st, long long* cnt) {
+    const bool constrained = pb.has_ubox || pb.has_xbox;
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    const int HG = D * D + D;  // consensus payload: columns of sum_i H_i, then sum_i g_i
+    double* wacc = (Nc >= 1) ? pb.wscr + ((size_t)blockIdx.x * W + wid) * (size_t)tm.cap : nullptr;
+    double* cacc = (Nc >= 1) ? pb.wscr + ((size_t)gridDim.x * W + blockIdx.x) * (size_t)tm.cap : nullptr;
+    for (int tries = 0;; ++tries) {
+      // ---- backward sweeps + consensus terms of this warp's particles
+      for (int q = 0; q < ppw; ++q) {
+        const int i = tm.idx * ppc + q * W + wid;
+        if (i < M) {
+          const size_t g = (size_t)prob * pb.Mpad + i;
+          bsweep(g);
+          if (Nc >= 1) {
+            for (int v = 0; v <= D; ++v) {
+              const bool hom = v < D;
+              shared_grad(g, hom, v, [&](int j, double val) {
+                double* dst = wacc + (size_t)v * D + j * NU + lane;
+                *dst = (q == 0) ? val : *dst + val;
+              });
+            }
+          }
+        } else if (q == 0 && Nc >= 1) {
+          for (int k = lane; k < HG; k += 32) wacc[k] = 0.0;
+        }
+      }
+      cnt[2] += 1;
+      cnt[7] += 1;
+      double kk_c = 0.0, uv_c = 0.0, ch_c = 0.0;
+      if (Nc >= 1) {
+        // ---- CTA partial (warp order), team reduction, shared block solved by the team leader
+        __syncthreads();
+        for (int k = tid; k < HG; k += T) {
+          double acc = 0.0;
+          for (int w = 0; w < W; ++w) acc += pb.wscr[((size_t)blockIdx.x * W + w) * (size_t)tm.cap + k];
+          cacc[k] = acc;
+        }
+        __syncthreads();
+        double* Hc = F.Hc + (size_t)prob * D * D;
+        double* Hi = F.Hci + (size_t)prob * D * D;
+        double* lead = (tm.idx == 0) ? S0.scr() : nullptr;  // leader staging: scratch_stride >= D * D + D (host)
+        team_reduce(cacc, HG, lead, true, 0u);
+        double* res = cred;  // [kk, uv, ch] broadcast with uc
+        if (tm.idx == 0 && !tm.dead) {
+          S0.xreduce(lead, HG, true);  // particles sharded over GPUs: sum over the ranks (no-op for one GPU)
+          // column v of sum H_i sits in lead[v*D ..]; symmetrise (Solver::assemble_shared)
+          for (int idx = tid; idx < D * D; idx += T) {
+            const int a = idx / D, b = idx % D;
+            Hi[idx] = 0.5 * (lead[(size_t)b * D + a] + lead[(size_t)a * D + b]);
+          }
+          for (int a = tid; a < D; a += T) pb.gc[(size_t)prob * D + a] = lead[(size_t)D * D + a];
+          __syncthreads();
+          for (int idx = tid; idx < D * D; idx += T) Hc[idx] = Hi[idx];
+          __syncthreads();
+          // the shared block is a D-dimensional box QP once the particles' value functions are fixed: iterate its
+          // active set here, without sweeping the horizon again (fused_qp_impl)
+          for (int t = 0; t <= 2 * D; ++t) {
+            S0.factor_shared(MODE_POLISH);
+            S0.apply_shared(MODE_POLISH, 0.0);
+            if (!pb.has_ubox) break;
+            kk_c = uv_c = 0.0;
+            ch_c = S0.shared_active_update(&kk_c, &uv_c);
+            if (ch_c == 0.0) break;
+          }
+          if (tid == 0) { res[0] = kk_c; res[1] = uv_c; res[2] = ch_c; }
+          __threadfence();
+          __syncthreads();
+        }
+        double* bb = cred + 8;
+        if (tm.idx == 0 && tid < 3) bb[tid] = res[tid];
+        if (tm.idx == 0 && S0.xdead) tm.dead = true;  // a peer rank never arrived: release the team as well
+        team_bcast(bb, 3);  // (orders the leader's pb.uc stores before the flag the others wait for)
+        if (tm.dead) return 4;
+        kk_c = bb[0]; uv_c = bb[1]; ch_c = bb[2];
+        __syncthreads();
+      }
+      // ---- forward sweeps
+      double acc_st[ST_COUNT];
+      for (int k = 0; k < ST_COUNT; ++k) acc_st[k] = 0.0;
+      acc_st[ST_GSCALE] = acc_st[ST_ZSCALE] = 1.0;
+      for (int q = 0; q < ppw; ++q) {
+        const int i = tm.idx * ppc + q * W + wid;
+        if (i < M) {
+          double s1[ST_COUNT];
+          for (int k = 0; k < ST_COUNT; ++k) s1[k] = 0.0;
+          fsweep((size_t)prob * pb.Mpad + i, s1);
+          for (int k = 0; k < ST_COUNT; ++k) acc_st[k] = (k == ST_OBJ) ? acc_st[k] + s1[k] : fmax(acc_st[k], s1[k]);
+        }
+      }
+      cnt[3] += 1;
+      cnt[7] += 1;
+      // ---- statistics: warps -> CTA -> team (-> ranks) -> everybody
+      __syncthreads();
+      double* wst = cred + 16;  // [W][ST_COUNT]
+      if (lane == 0)
+        for (int k = 0; k < ST_COUNT; ++k) wst[wid * ST_COUNT + k] = acc_st[k];
+      __syncthreads();
+      double* cst = wst + W * ST_COUNT;  // [ST_COUNT]
+      if (tid < ST_COUNT) {
+        double a = wst[tid];
+        for (int w = 1; w < W; ++w) a = (tid == ST_OBJ) ? a + wst[w * ST_COUNT + tid] : fmax(a, wst[w * ST_COUNT + tid]);
+        cst[tid] = a;
+      }
+      __syncthreads();
+      team_reduce(cst, ST_COUNT, cst, false, 1u << ST_OBJ);
+      if (tm.idx == 0 && !tm.dead) S0.xreduce(cst, ST_COUNT, false, 1u << ST_OBJ);
+      if (tm.idx == 0 && S0.xdead) tm.dead = true;
+      team_bcast(cst, ST_COUNT);
+      if (tm.dead || S0.xdead) return 4;
+      for (int k = 0; k < ST_COUNT; ++k) st[k] = cst[k];
+      __syncthreads();
+      st[ST_KKT] = fmax(st[ST_KKT], kk_c);
+      st[ST_UVIOL] = fmax(st[ST_UVIOL], uv_c);
+      st[ST_CHANGED] += ch_c;
+      if (st[ST_NAN] > 0.0) return 1;
+      if (!constrained) {
+        cnt[5] += 1;
+        return 0;
+      }
+      const double tol_g = pb.kkt_tol * st[ST_GSCALE], tol_z = pb.kkt_tol * st[ST_ZSCALE];
+      if (st[ST_KKT] <= tol_g && st[ST_UVIOL] <= tol_z && st[ST_XVIOL] <= tol_z) {
+        cnt[5] += 1;
+        return 0;
+      }
+      if (st[ST_XVIOL] > tol_z) return -1;  // a state bound wants to be active: ADMM (thread-per-particle kernel)
+      if (st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) return -1;  // stalls or cycles: interior point there
+    }
+  }
+  // ------------------------------------------------------------------------------------------------------------
+  // The SCP loop (scp_mpc.py:337-428; Solver::run)
+  template <typename S0T>
+  __device__ __forceinline__ void run(S0T& S0, int Tc, int ppw) {
+    M = pb.M;
+    N = pb.N;
+    Nc = (M == 1) ? 0 : pb.Nc;
+    D = Nc * NU;
+    prob = blockIdx.x / Tc;
+    S0.prob = prob;
+    const int ppc = W * ppw;
+    tm.Tc = Tc;
+    tm.idx = blockIdx.x % Tc;
+    tm.cap = pb.tm_cap;
+    tm.seq = pb.tseq0;
+    tm.dead = false;
+    {
+      // per problem: [Tc part slots | bcast slot | Tc + 1 flags]
+      const size_t per = (size_t)(Tc + 1) * tm.cap + (size_t)Tc + 1;
+      double* base = pb.tm + (size_t)prob * per;
+      tm.part = base;
+      tm.bc = base + (size_t)Tc * tm.cap;
+      tm.pflag = reinterpret_cast<unsigned long long*>(tm.bc + tm.cap);
+      tm.bflag = tm.pflag + Tc;
+    }
+    cred = reinterpret_cast<double*>(smem) + (size_t)W * SLAB;
+    Xc = pb.X; Uc = pb.U; Xpv = pb.Xp; Upv = pb.Up;
+    flip = false;
+    double st[ST_COUNT];
+    for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
+    long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool writer = (tm.idx == 0 && tid == 0);
+    int it = 0;
+    bool handed = false;
+    const double *solX = Xc, *solU = Uc;
+    for (; it < pb.max_it; ++it) {
+      const int status = qp(S0, ppw, ppc, st, cnt);
+      if (status == 4) {  // a team member or a peer rank never arrived
+        cnt[4] |= 4;
+        ++it;
+        break;
+      }
+      if (status < 0) {  // hand the problem to the thread-per-particle kernel at this iteration
+        handed = true;
+        break;
+      }
+      solX = Xc;
+      solU = Uc;
+      if (status & 1) {
+        cnt[4] |= 1;
+        for (int q = 0; q < ppw; ++q) {  // reference convention: NaN output on failure (osqp_solver.jl:69-71)
+          const int i = tm.idx * ppc + q * W + wid;
+          if (i < M) {
+            const size_t g = (size_t)prob * pb.Mpad + i;
+            for (int idx = lane; idx < N * NX; idx += 32) Xc[gix(g, N, 0, NX) + idx] = NAN;
+            for (int idx = lane; idx < N * NU; idx += 32) Uc[gix(g, N, 0, NU) + idx] = NAN;
+          }
+        }
+        ++it;
+        break;
+      }
+      const double kkt_rel = st[ST_KKT] / fmax(st[ST_GSCALE], 1.0);
+      if (!pb.keep_prev) {  // X_prev <- X is a buffer swap
+        double* t0 = Xc; Xc = const_cast<double*>(Xpv); Xpv = t0;
+        double* t1 = Uc; Uc = const_cast<double*>(Upv); Upv = t1;
+        flip = !flip;
+      }
+      const double max_res = fmax(st[ST_DX], st[ST_DU]);
+      const double obj = st[ST_OBJ] / ((double)N * (double)(pb.world > 1 ? pb.M_total : pb.M));
+      const int hrow = it + pb.hist_off;
+      if (writer && hrow < pb.hist_len) {
+        const size_t Bn = (size_t)pb.B;
+        pb.hist[((size_t)0 * pb.hist_len + hrow) * Bn + prob] = obj;
+        pb.hist[((size_t)1 * pb.hist_len + hrow) * Bn + prob] = max_res;
+        pb.hist[((size_t)2 * pb.hist_len + hrow) * Bn + prob] = 0.0;
+        pb.hist[((size_t)3 * pb.hist_len + hrow) * Bn + prob] = kkt_rel;
+      }
+      if (max_res < pb.res_tol) {
+        ++it;
+        break;
+      }
+    }
+    // Leave the last solution in pb.X / pb.U and, unless keep_prev, in pb.Xp / pb.Up as well.  A handed-over problem
+    // needs only its linearisation point in pb.Xp / pb.Up (the other kernel starts with unswapped buffers).
+    if (handed) {
+      solX = Xpv;
+      solU = Upv;
+    }
+    for (int q = 0; q < ppw; ++q) {
+      const int i = tm.idx * ppc + q * W + wid;
+      if (i >= M) continue;
+      const size_t g = (size_t)prob * pb.Mpad + i;
+      for (int idx = lane; idx < N * NX; idx += 32) {
+        const double v = solX[gix(g, N, 0, NX) + idx];
+        if (!handed && solX != pb.X) pb.X[gix(g, N, 0, NX) + idx] = v;
+        if ((handed || !pb.keep_prev) && solX != pb.Xp) pb.Xp[gix(g, N, 0, NX) + idx] = v;
+      }
+      for (int idx = lane; idx < N * NU; idx += 32) {
+        const double v = solU[gix(g, N, 0, NU) + idx];
+        if (!handed && solU != pb.U) pb.U[gix(g, N, 0, NU) + idx] = v;
+        if ((handed || !pb.keep_prev) && solU != pb.Up) pb.Up[gix(g, N, 0, NU) + idx] = v;
+      }
+    }
+    if (tm.idx == 0) S0.xclose();
+    cnt[0] = it;
+    if (writer) {
+      for (int k = 0; k < 8; ++k) pb.info[(size_t)k * pb.B + prob] = cnt[k];
+      pb.fb[prob] = handed ? 1 : 0;
+    }
+  }
+};
+
+}  // namespace pmpc

@@ -1,0 +1,65 @@
+"""Development check of the warp-per-particle kernel (wpp.cuh) against the thread-per-particle kernels of the same
+shapes (solver_settings b200 fused=0 selects the old path): small LTV problems, BASELINE config 4 at full size and
+config 5 reduced / full.     usage: python scripts/dev_wpp_check.py [small] [c4] [c5r] [c5]"""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..")); sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+import pmpc_b200
+from pmpc_b200 import LTV
+from fixtures import config_c4, config_c5, config_ltv
+
+which = sys.argv[1:] or ["small", "c4", "c5r"]
+
+
+def run(d, fn, fused, reps=1):
+    dd = dict(d, solver_settings=dict(d["solver_settings"], b200=dict(fused=fused)))
+    out = None
+    ts = []
+    for _ in range(reps + 1):
+        t = time.perf_counter(); out = pmpc_b200.solve(fn, **dd); ts.append(time.perf_counter() - t)
+    return out, min(ts[1:]) if reps else ts[0]
+
+
+def report(label, d, A, Bm, old=True, reps=1):
+    fn = LTV(A, Bm)
+    (X, U, data), t = run(d, fn, 1, reps)
+    row = dict(case=label)
+    if data is None:
+        row.update(failed=True)
+        print(json.dumps(row), flush=True)
+        return
+    dev = data["device"]
+    Nc = d["solver_settings"]["Nc"]
+    f = np.einsum("mjrt,mjt->mjr", A, X[:, :-1]) + np.einsum("mjrt,mjt->mjr", Bm, U)
+    row.update(wall_s=t, kernel_ms=dev["kernel_ms"], its=len(data["hist"]), status=dev["status"], passes=dev["polish_passes"],
+               sweeps=dev["sweeps"], admm=dev["admm_iters"], resid=data["hist"][-1]["resid"], dyn=float(np.abs(f - X[:, 1:]).max()),
+               consensus=bool(np.all(U[:, :Nc] == U[:1, :Nc])), umax=float(np.abs(U).max()))
+    if old:
+        (Xo, Uo, do), to = run(d, fn, 0, reps)
+        row.update(old_kernel_ms=do["device"]["kernel_ms"], old_its=len(do["hist"]), dX=float(np.abs(X - Xo).max()),
+                   dU=float(np.abs(U - Uo).max()), old_passes=do["device"]["polish_passes"])
+    print(json.dumps(row), flush=True)
+
+
+if "small" in which:
+    for (n, m, M, N, Nc, box, xbox) in [(8, 4, 1, 6, 0, 0.3, False), (8, 4, 3, 6, 1, 0.3, False), (12, 4, 5, 9, 2, 0.3, False),
+                                        (16, 8, 9, 7, 1, 0.3, False), (32, 8, 4, 8, 5, 0.3, False), (32, 8, 20, 12, 2, 1.0, False),
+                                        (12, 4, 64, 20, 1, 0.5, True), (20, 6, 33, 10, 3, 0.3, False)]:
+        d, A, Bm = config_ltv(7 + n + M, M, N, n, m, Nc, xbox=xbox)
+        d["u_l"], d["u_u"] = box * d["u_l"], box * d["u_u"]
+        d["x0"] = 3.0 * d["x0"]
+        report("n%d m%d M%d N%d Nc%d" % (n, m, M, N, Nc), d, A, Bm)
+    # no slew (the lean instantiation)
+    d, A, Bm = config_ltv(99, 6, 10, 12, 4, 2, xbox=False)
+    d["slew_rate"] = 0.0
+    d["u_l"], d["u_u"] = 0.3 * d["u_l"], 0.3 * d["u_u"]
+    report("n12 m4 M6 N10 Nc2 no slew", d, A, Bm)
+if "c4" in which:
+    d, A, Bm = config_c4()
+    report("C4 full", d, A, Bm, reps=3)
+if "c5r" in which:
+    d, A, Bm = config_c5(M=128, N=200)
+    report("C5 M=128 N=200", d, A, Bm, old=bool(int(os.environ.get("C5R_OLD", "1"))))
+if "c5" in which:
+    d, A, Bm = config_c5()
+    report("C5 full", d, A, Bm, old=False, reps=2)

@@ -212,7 +212,7 @@ def test_user_dynamics_wrapper_compiles_for_sm100a_without_a_gpu():
         pytest.skip("libnvrtc.so.12 not available")
     src = open(os.path.join(ROOT, "pmpc_b200", "csrc", "userdyn.inl")).read()
     wrapper = src[src.index('R"SRC(') + 6:src.index(')SRC";')]
-    head = "#define PMPC_N 2\n#define PMPC_M 1\n#define PMPC_NX 2\n#define PMPC_NU 1\n#define PMPC_NP 1\n#define PMPC_USER_FN f\n#line 1 \"user_dynamics.cu\"\n"
+    head = "#define PMPC_N 2\n#define PMPC_M 1\n#define PMPC_NX 2\n#define PMPC_NU 1\n#define PMPC_NP 1\n#define PMPC_TILE 32\n#define PMPC_USER_FN f\n#line 1 \"user_dynamics.cu\"\n"
     good = ("__device__ void f(const double* x, const double* u, const double* p, double* f, double* fx, double* fu) {"
             " f[0] = x[0] + p[0] * x[1]; f[1] = x[1] + p[0] * (u[0] - sin(x[0])); fx[0] = 1; fx[1] = p[0];"
             " fx[2] = -p[0] * cos(x[0]); fx[3] = 1; fu[1] = p[0]; }")
