@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 
 #include "solver.cuh"
+#include "tma.cuh"
 
 namespace pmpc {
 
@@ -44,25 +45,31 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 template <int NX, int NU, bool SLEW>
 struct Wpp {
   static constexpr int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2, NHO = NR - NU;
-  static constexpr int LDF = NX + 1;  // padded leading dimension where lanes read different ROWS of a shared matrix
   // hand-off block of one (particle, stage), same format as Solver::NH with HL = 0: [K | k | strict upper H]
   static constexpr int H_K = 0, H_KF = NU * NX, H_H = H_KF + NU, NH = H_H + NHO;
   __host__ __device__ static constexpr int pko(int a, int b) { return a * NU - (a * (a + 1)) / 2 + (b - a - 1); }  // a < b
-  // per-warp shared-memory slab (doubles)
-  static constexpr int O_S = 0;                       // S = Qs + P, later S A           (NX x NX)
-  static constexpr int O_A = O_S + NX * NX;           // A (bsweep: ld NX; fsweep: ld LDF) (NX x LDF)
-  static constexpr int O_B = O_A + NX * LDF;          // B                               (NX x NU)
-  static constexpr int O_SBW = O_B + NX * NU;         // S B + W                         (NX x NU)
-  static constexpr int O_W = O_SBW + NX * NU;         // W (slew block of the value function) (NX x NU)
-  static constexpr int O_G = O_W + NX * NU;           // G (bsweep) / K or G rows (fsweep) (NU x LDF)
-  static constexpr int O_V = O_G + NU * LDF;          // vectors: c, wv, x, a, dx        (5 x NX)
-  static constexpr int O_M = O_V + 5 * NX;            // H, E, Z                         (3 x NU x NU)
-  static constexpr int O_U = O_M + 3 * NU * NU;       // h0, h, kv, ufix, u, up, z, r, lo, hi, du, kf (12 x NU)
-  static constexpr int SLAB = ((O_U + 12 * NU + 1) / 2) * 2;
-  static constexpr int V_C = 0, V_WV = NX, V_X = 2 * NX, V_AD = 3 * NX, V_DX = 4 * NX;
+  // Per-warp shared-memory slab (doubles).  The matrix region is used in two ways:
+  //   backward sweep: S | A | B | S B + W | W | G          (S, W survive into the consensus step as Pc, Wc)
+  //   forward sweep : two ring slots of [A | B | hand-off | E]
+  // Every stage block is brought in by bulk asynchronous copies (TMA engine, cp.async.bulk + mbarrier) issued by lane 0
+  // as soon as its buffer is free and waited for right before its first use (bsweep: A at stage start for the second
+  // half of the stage, Qs and B during the previous stage; fsweep: a two-deep ring).  All sub-buffers start at even
+  // offsets (16-byte aligned, as bulk copies require).
+  static constexpr int O_S = 0, O_A = O_S + NX * NX, O_B = O_A + NX * NX, O_SBW = O_B + NX * NU, O_W = O_SBW + NX * NU,
+                       O_G = O_W + NX * NU, BMAT = O_G + NU * NX;
+  static constexpr int F_A = 0, F_B = F_A + NX * NX, F_H = F_B + NX * NU, F_E = F_H + NH, FSLOT = F_E + NR;
+  static constexpr int MAT = (BMAT > 2 * FSLOT) ? BMAT : 2 * FSLOT;
+  static constexpr int O_Q = MAT;                    // packed Qs of one stage                     (NQ)
+  static constexpr int O_V = O_Q + NQ;                // vectors: c, wv (pc), x, a / dx              (4 x NX)
+  static constexpr int O_M = O_V + 4 * NX;            // H, E, Z (Zc)                                (3 x NU x NU)
+  static constexpr int O_U = O_M + 3 * NU * NU;       // h0, h, kv, ufix, z (zc) | u, up, du         (5 x NU)
+  static constexpr int O_BAR = O_U + 6 * NU;          // mbarriers: A, Q, B (bsweep) / slot 0, slot 1, Q (fsweep)
+  static constexpr int SLAB = O_BAR + 6;
+  static_assert(NX % 2 == 0 && NQ % 2 == 0 && NR % 2 == 0 && NH % 2 == 0 && SLAB % 2 == 0, "16-byte alignment of the sub-buffers");
+  static constexpr int V_C = 0, V_WV = NX, V_X = 2 * NX, V_AD = 3 * NX, V_DX = 3 * NX;
   static constexpr int MM_H = 0, MM_E = NU * NU, MM_Z = 2 * NU * NU;
-  static constexpr int U_H0 = 0, U_H = NU, U_KV = 2 * NU, U_UF = 3 * NU, U_U = 4 * NU, U_UP = 5 * NU, U_Z = 6 * NU,
-                       U_R = 7 * NU, U_LO = 8 * NU, U_HI = 9 * NU, U_DU = 10 * NU, U_KF = 11 * NU;
+  static constexpr int U_H0 = 0, U_H = NU, U_KV = 2 * NU, U_UF = 3 * NU, U_Z = 4 * NU, U_U = 0, U_UP = NU, U_DU = 2 * NU;
+  enum { BAR_A = 0, BAR_Q = 1, BAR_B = 2, BAR_S0 = 3, BAR_S1 = 4, BAR_FQ = 5 };
   static constexpr int DMAX = 64;  // largest shared block (Nc * NU) this kernel takes; beyond it the old kernel runs
 
   // ------------------------------------------------------------------------------------------------------------
@@ -245,16 +252,33 @@ struct Wpp {
   }
 
   // ------------------------------------------------------------------------------------------------------------
+  // bulk-async staging (tma.cuh): lane 0 arms the warp's mbarrier with the byte count and issues the copies; every
+  // lane waits on the barrier's phase.  ph[b] counts the completed uses of barrier b (uniform over the warp).
+  unsigned ph[6];
+  __device__ __forceinline__ uint64_t* bar(int b) const { return reinterpret_cast<uint64_t*>(slab() + O_BAR) + b; }
+  __device__ __forceinline__ void bar_wait(int b) {
+    mbar_wait(bar(b), ph[b] & 1u);
+    ++ph[b];
+  }
+  __device__ __forceinline__ void stage_init() {
+    if (lane == 0) {
+      for (int b = 0; b < 6; ++b) mbar_init(bar(b), 1);
+      fence_mbar_init();
+    }
+    for (int b = 0; b < 6; ++b) ph[b] = 0;
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
   // Backward sweep of particle slot g over the free stages j = N-1 .. Nc (fused.inl bsweep, generic branch): masked
   // Riccati matrix + vector step; writes the hand-off block.  On return (Nc >= 1) the boundary value function sits in
   // the slab: Pc in O_S, Wc in O_W, Zc in MM_Z, pc in V_WV, zc in U_Z.
   __device__ __forceinline__ void bsweep(size_t g) {
     double* sl = slab();
-    double *Sm = sl + O_S, *Am = sl + O_A, *Bm = sl + O_B, *SBWm = sl + O_SBW, *Wm = sl + O_W, *Gm = sl + O_G;
+    double *Sm = sl + O_S, *Am = sl + O_A, *Bm = sl + O_B, *SBWm = sl + O_SBW, *Wm = sl + O_W, *Gm = sl + O_G, *Qb = sl + O_Q;
     double *cv = sl + O_V + V_C, *wvv = sl + O_V + V_WV;
     double *Hm = sl + O_M + MM_H, *Em = sl + O_M + MM_E, *Zm = sl + O_M + MM_Z;
-    double *h0m = sl + O_U + U_H0, *hm = sl + O_U + U_H, *kvm = sl + O_U + U_KV, *ufm = sl + O_U + U_UF, *zm = sl + O_U + U_Z,
-           *rm = sl + O_U + U_R;
+    double *h0m = sl + O_U + U_H0, *hm = sl + O_U + U_H, *kvm = sl + O_U + U_KV, *ufm = sl + O_U + U_UF, *zm = sl + O_U + U_Z;
     const int l = lane;
     const double s = SLEW ? pb.slew[g] : 0.0;
     const FactorSet& F = pb.fs[MODE_POLISH];
@@ -265,44 +289,76 @@ struct Wpp {
     for (int idx = l; idx < NU * NU; idx += 32) Zm[idx] = 0.0;
     if (l < NU) zm[l] = 0.0;
     __syncwarp();
-    for (int j = N - 1; j >= Nc; --j) {
-      // ---- P0: stage data into the slab
-      const double* Ag = pb.A + gix(g, N, j, NX * NX);
-      const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
-      const double* Qg = pb.Qs + gix(g, N, j, NQ);
-      const double* Rg = pb.Rs + gix(g, N, j, NR);
-      if (j >= 1) {
-#pragma unroll 8
-        for (int k = 0; k < NX; ++k) {
-          const double a = Ag[k * NX + lc];
-          if (lact) Am[k * NX + l] = a;
-        }
+    if (N - 1 < Nc) {
+      if (lact) {
+#pragma unroll
+        for (int r = 0; r < NX; ++r) Sm[r * NX + l] = 0.0;
+        wvv[l] = 0.0;
       }
-      for (int idx = l; idx < NX * NU; idx += 32) Bm[idx] = Bg[idx];
+      __syncwarp();
+      return;
+    }
+    // per-lane stage vectors travel through registers, loaded one stage ahead
+    struct Vec { double c, qref, xp, ub, rref, lo, hi, Rp[(NR + 31) / 32]; signed char act; };
+    auto load_vec = [&](int j) -> Vec {
+      Vec v;
+      v.c = pb.c[gix(g, N, j, NX) + lc];
+      v.qref = pb.qref[gix(g, N, j, NX) + lc];
+      v.xp = Xpv[gix(g, N, j, NX) + lc];
+      const int la = l < NU ? l : NU - 1;
+      v.ub = Upv[gix(g, N, j, NU) + la];
+      v.rref = pb.rref[gix(g, N, j, NU) + la];
+      v.lo = v.hi = 0.0;
+      v.act = 0;
+      if (pb.has_ubox) {
+        v.lo = pb.lu[gix(g, N, j, NU) + la];
+        v.hi = pb.uu[gix(g, N, j, NU) + la];
+        v.act = pb.act[gix(g, N, j, NU) + la];
+      }
+#pragma unroll
+      for (int k = 0; k < (NR + 31) / 32; ++k)  // packed Rs entries of the (a, b) pairs this lane assembles in H
+        v.Rp[k] = pb.Rs[gix(g, N, j, NR) + ((l + 32 * k < NR) ? l + 32 * k : 0)];
+      return v;
+    };
+    auto issue_q = [&](int j) {
+      mbar_expect_tx(bar(BAR_Q), NQ * 8);
+      bulk_g2s(Qb, pb.Qs + gix(g, N, j, NQ), NQ * 8, bar(BAR_Q));
+    };
+    auto issue_b = [&](int j) {
+      mbar_expect_tx(bar(BAR_B), NX * NU * 8);
+      bulk_g2s(Bm, pb.Bm + gix(g, N, j, NX * NU), NX * NU * 8, bar(BAR_B));
+    };
+    if (l == 0) {
+      issue_q(N - 1);
+      issue_b(N - 1);
+    }
+    Vec vn = load_vec(N - 1);
+    for (int j = N - 1; j >= Nc; --j) {
+      const Vec vc = vn;
+      if (j - 1 >= Nc) vn = load_vec(j - 1);
+      // ---- P0: A of this stage is needed in the second half only: start its copy now
+      if (l == 0 && j >= 1) {
+        mbar_expect_tx(bar(BAR_A), NX * NX * 8);
+        bulk_g2s(Am, pb.A + gix(g, N, j, NX * NX), NX * NX * 8, bar(BAR_A));
+      }
+      bar_wait(BAR_Q);
+      double Rp[(NR + 31) / 32];
+#pragma unroll
+      for (int k = 0; k < (NR + 31) / 32; ++k) Rp[k] = vc.Rp[k];
 #pragma unroll
       for (int r = 0; r < NX; ++r) {
-        const double v = qs_at(Qg, r, lc) + Pcol[r];
+        const double v = qs_at(Qb, r, lc) + Pcol[r];
         if (lact) Sm[r * NX + l] = v;
       }
-      double q_l = 0.0;
-      if (lact) {
-        cv[l] = pb.c[gix(g, N, j, NX) + l];
-        q_l = -pb.qref[gix(g, N, j, NX) + l] - pb.reg_x * Xpv[gix(g, N, j, NX) + l];
-      }
-      bool fixed_l = false;
-      if (l < NU) {
-        const double ub = Upv[gix(g, N, j, NU) + l];
-        rm[l] = -pb.rref[gix(g, N, j, NU) + l] - pb.reg_u * ub;
-        double uf = 0.0;
-        if (pb.has_ubox) {
-          const signed char a = pb.act[gix(g, N, j, NU) + l];
-          if (a != 0) uf = (a > 0) ? pb.uu[gix(g, N, j, NU) + l] : pb.lu[gix(g, N, j, NU) + l];
-          fixed_l = (a != 0);
-        }
-        ufm[l] = uf;
-      }
+      const double q_l = -vc.qref - pb.reg_x * vc.xp;
+      const double r_l = -vc.rref - pb.reg_u * vc.ub;
+      if (lact) cv[l] = vc.c;
+      const bool fixed_l = (l < NU) && vc.act != 0;
+      if (l < NU) ufm[l] = (vc.act > 0) ? vc.hi : ((vc.act < 0) ? vc.lo : 0.0);
       const unsigned fmask = __ballot_sync(0xffffffffu, fixed_l);  // bit a: control a of this stage sits at a bound
       __syncwarp();
+      if (l == 0 && j - 1 >= Nc) issue_q(j - 1);  // Qb has been consumed
+      bar_wait(BAR_B);
       // ---- P1: wv = S c + q + p (element l), row l of S B + W.  S is symmetric: row l is read as column l
       {
         double wv = q_l + p_l;
@@ -324,30 +380,47 @@ struct Wpp {
       }
       __syncwarp();
       // ---- P2: H = Rs + [j>=1] s I + B'(S B + W) + W'B + Z (pairs over lanes), h0 = r + B'wv + W'c + z
-      for (int pi = l; pi < NR; pi += 32) {
-        int a = 0, rem = pi;
-        while (rem >= NU - a) { rem -= NU - a; ++a; }
-        const int b = a + rem;
-        double acc = Rg[pi];
-        if (SLEW) {
-          acc += Zm[a * NU + b];
-          if (a == b && j >= 1) acc += s;
+#pragma unroll
+      for (int kk = 0; kk < (NR + 31) / 32; ++kk) {
+        const int pi = l + 32 * kk;
+        if (pi < NR) {
+          int a = 0, rem = pi;
+          while (rem >= NU - a) { rem -= NU - a; ++a; }
+          const int b = a + rem;
+          double acc = Rp[kk];
+          if (SLEW) {
+            acc += Zm[a * NU + b];
+            if (a == b && j >= 1) acc += s;
+          }
+          for (int k = 0; k < NX; ++k) {
+            acc += Bm[k * NU + a] * SBWm[k * NU + b];
+            if (SLEW) acc += Wm[k * NU + a] * Bm[k * NU + b];
+          }
+          Rp[kk] = acc;
         }
-        for (int k = 0; k < NX; ++k) {
-          acc += Bm[k * NU + a] * SBWm[k * NU + b];
-          if (SLEW) acc += Wm[k * NU + a] * Bm[k * NU + b];
-        }
-        Hm[a * NU + b] = acc;
-        Hm[b * NU + a] = acc;
       }
+      double h0 = 0.0;
       if (l < NU) {
-        double acc = rm[l] + (SLEW ? zm[l] : 0.0);
+        h0 = r_l + (SLEW ? zm[l] : 0.0);
         for (int k = 0; k < NX; ++k) {
-          acc += Bm[k * NU + l] * wvv[k];
-          if (SLEW) acc += Wm[k * NU + l] * cv[k];
+          h0 += Bm[k * NU + l] * wvv[k];
+          if (SLEW) h0 += Wm[k * NU + l] * cv[k];
         }
-        h0m[l] = acc;
       }
+      __syncwarp();  // every lane has finished with B
+      if (l == 0 && j - 1 >= Nc) issue_b(j - 1);
+#pragma unroll
+      for (int kk = 0; kk < (NR + 31) / 32; ++kk) {
+        const int pi = l + 32 * kk;
+        if (pi < NR) {
+          int a = 0, rem = pi;
+          while (rem >= NU - a) { rem -= NU - a; ++a; }
+          const int b = a + rem;
+          Hm[a * NU + b] = Rp[kk];
+          Hm[b * NU + a] = Rp[kk];
+        }
+      }
+      if (l < NU) h0m[l] = h0;
       __syncwarp();
       // ---- P3: masked inverse, h = h0 + H ufix, k = ufix - E h
       masked_inverse(Hm, fmask, l, Em);
@@ -369,6 +442,7 @@ struct Wpp {
 #pragma unroll
       for (int a = 0; a < NU; ++a) { Kc[a] = 0.0; Gc[a] = 0.0; }
       if (j >= 1) {
+        bar_wait(BAR_A);
         // ---- P4: column l of G = (S B + W)' A, K = -E G, p' = A' wv + G' k, S A
         double pn = 0.0;
         double SAc[NX];
@@ -399,7 +473,7 @@ struct Wpp {
 #pragma unroll
           for (int r = 0; r < NX; ++r) Sm[r * NX + l] = SAc[r];
 #pragma unroll
-          for (int a = 0; a < NU; ++a) Gm[a * LDF + l] = Gc[a];
+          for (int a = 0; a < NU; ++a) Gm[a * NX + l] = Gc[a];
         }
         __syncwarp();
         // ---- P' = A' (S A) + G' K, column l
@@ -419,7 +493,11 @@ struct Wpp {
         for (int a = 0; a < NU; ++a) {
           const double ka = Kc[a];
 #pragma unroll
-          for (int r = 0; r < NX; ++r) Pcol[r] += Gm[a * LDF + r] * ka;
+          for (int r = 0; r < NX; r += 2) {
+            const double2 gv = *reinterpret_cast<const double2*>(&Gm[a * NX + r]);
+            Pcol[r] += gv.x * ka;
+            Pcol[r + 1] += gv.y * ka;
+          }
         }
         p_l = pn;
       }
@@ -448,7 +526,7 @@ struct Wpp {
           }
         }
       }
-      __syncwarp();  // all reads of W, Z, z, E of this stage are done
+      __syncwarp();  // all reads of W, Z, z, E, H and A of this stage are done
       if (SLEW) {
         if (lact) {
 #pragma unroll
@@ -465,6 +543,7 @@ struct Wpp {
       for (int r = 0; r < NX; ++r) Sm[r * NX + l] = Pcol[r];
       wvv[l] = p_l;
     }
+    fence_proxy_async();  // the hand-off written above is bulk-copied by the forward sweep
     __syncwarp();
   }
 
@@ -546,76 +625,98 @@ struct Wpp {
   // ------------------------------------------------------------------------------------------------------------
   // Forward sweep of particle slot g (fused.inl fsweep, generic branch): rollout of the policy, multipliers and
   // primal-dual update of the free-stage active set, SCP bookkeeping.  st: per-warp statistics (valid in every lane).
+  // The stage matrices [A | B | hand-off | E] stream through a two-deep ring of bulk copies; Qs (objective only) is
+  // requested at stage start and waited for at its end; the per-lane vectors travel through registers.
+  // Rows of A (and of K) are read with a rotated column index, (t + row) mod NX, which keeps lanes that read
+  // different rows of an unpadded matrix on different banks.
   __device__ __forceinline__ void fsweep(size_t g, double* st) {
     double* sl = slab();
-    double *Am = sl + O_A, *Bm = sl + O_B, *Km = sl + O_G;
-    double *cv = sl + O_V + V_C, *xv = sl + O_V + V_X, *dxv = sl + O_V + V_DX;
-    double *um = sl + O_U + U_U, *upm = sl + O_U + U_UP, *dum_ = sl + O_U + U_DU, *kfm = sl + O_U + U_KF, *lom = sl + O_U + U_LO,
-           *him = sl + O_U + U_HI;
-    double* Hoff = sl + O_M + MM_H;  // strict upper triangle of the stage Hessian (NHO)
-    double* Es = sl + O_M + MM_E;    // packed E (NR) with a slew penalty
+    double* Qb = sl + O_Q;
+    double *xv = sl + O_V + V_X, *dxv = sl + O_V + V_DX;
+    double *um = sl + O_U + U_U, *upm = sl + O_U + U_UP, *dum_ = sl + O_U + U_DU;
     const int l = lane;
     const double s = SLEW ? pb.slew[g] : 0.0;
     const FactorSet& F = pb.fs[MODE_POLISH];
     const double* uc = (Nc >= 1) ? pb.uc + (size_t)prob * D : nullptr;  // written by the team leader: read through L2
     const double rdiag = pb.rdiag0[g];
-    double x_l = 0.0;
     double dxm = 0.0, dum = 0.0, obj = 0.0, nanf = 0.0, kkt_v = 0.0, uviol = 0.0, xviol = 0.0, changed = 0.0, gscale = 1.0,
            zscale = 1.0;
+    struct Vec { double c, xp, xref, qref, lx, ux, ub, uref, rref, lo, hi, kf; signed char act; };
+    auto load_vec = [&](int j) -> Vec {
+      Vec v;
+      v.c = pb.c[gix(g, N, j, NX) + lc];
+      v.xp = Xpv[gix(g, N, j, NX) + lc];
+      v.xref = pb.xref[gix(g, N, j, NX) + lc];
+      v.qref = pb.qref[gix(g, N, j, NX) + lc];
+      v.lx = -INFINITY; v.ux = INFINITY;
+      if (pb.has_xbox) {
+        v.lx = pb.lx[gix(g, N, j, NX) + lc];
+        v.ux = pb.ux[gix(g, N, j, NX) + lc];
+      }
+      const int la = l < NU ? l : NU - 1;
+      v.ub = Upv[gix(g, N, j, NU) + la];
+      v.uref = pb.uref[gix(g, N, j, NU) + la];
+      v.rref = pb.rref[gix(g, N, j, NU) + la];
+      v.lo = -INFINITY; v.hi = INFINITY; v.act = 0; v.kf = 0.0;
+      if (pb.has_ubox) {
+        v.lo = pb.lu[gix(g, N, j, NU) + la];
+        v.hi = pb.uu[gix(g, N, j, NU) + la];
+      }
+      if (j >= Nc) {
+        v.kf = pb.hand[gix(g, N, j, NH) + H_KF + la];
+        if (pb.has_ubox) v.act = pb.act[gix(g, N, j, NU) + la];
+      }
+      return v;
+    };
+    auto issue_f = [&](int j) {  // lane 0: stage j into ring slot j & 1
+      double* dst = sl + (j & 1) * FSLOT;
+      uint64_t* b = bar(BAR_S0 + (j & 1));
+      uint32_t bytes = NX * NU * 8;
+      if (j >= 1) bytes += NX * NX * 8;
+      if (j >= Nc) bytes += NH * 8 + (SLEW ? NR * 8 : 0);
+      mbar_expect_tx(b, bytes);
+      if (j >= 1) bulk_g2s(dst + F_A, pb.A + gix(g, N, j, NX * NX), NX * NX * 8, b);
+      bulk_g2s(dst + F_B, pb.Bm + gix(g, N, j, NX * NU), NX * NU * 8, b);
+      if (j >= Nc) {
+        bulk_g2s(dst + F_H, pb.hand + gix(g, N, j, NH), NH * 8, b);
+        if (SLEW) bulk_g2s(dst + F_E, F.E + gix(g, N, j, NR), NR * 8, b);
+      }
+    };
     if (lact) xv[l] = 0.0;
     if (l < NU) upm[l] = 0.0;
     __syncwarp();
+    if (l == 0) {
+      issue_f(0);
+      if (N > 1) issue_f(1);
+    }
+    Vec vn = load_vec(0);
     for (int j = 0; j < N; ++j) {
-      const double* Ag = pb.A + gix(g, N, j, NX * NX);
-      const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
-      const double* hg = pb.hand + gix(g, N, j, NH);
-      if (j >= 1) {
-#pragma unroll 8
-        for (int k = 0; k < NX; ++k) {
-          const double a = Ag[k * NX + lc];
-          if (lact) Am[k * LDF + l] = a;
-        }
+      const Vec vc = vn;
+      if (j + 1 < N) vn = load_vec(j + 1);
+      const double* slot = sl + (j & 1) * FSLOT;
+      const double *Am = slot + F_A, *Bm = slot + F_B, *Km = slot + F_H + H_K, *Hoff = slot + F_H + H_H, *Es = slot + F_E;
+      if (l == 0) {  // Qs of this stage is needed for the objective at the end of the stage only
+        mbar_expect_tx(bar(BAR_FQ), (NQ + NR) * 8);
+        bulk_g2s(Qb, pb.Qs + gix(g, N, j, NQ), NQ * 8, bar(BAR_FQ));
+        bulk_g2s(sl + O_M, pb.Rs + gix(g, N, j, NR), NR * 8, bar(BAR_FQ));
       }
-      for (int idx = l; idx < NX * NU; idx += 32) Bm[idx] = Bg[idx];
-      if (lact) cv[l] = pb.c[gix(g, N, j, NX) + l];
-      signed char act = 0;
-      double ub = 0.0, lo = -INFINITY, hi = INFINITY;
-      if (l < NU) {
-        ub = Upv[gix(g, N, j, NU) + l];
-        if (pb.has_ubox) {
-          lo = pb.lu[gix(g, N, j, NU) + l];
-          hi = pb.uu[gix(g, N, j, NU) + l];
-        }
-        lom[l] = lo;
-        him[l] = hi;
-      }
-      if (j >= Nc) {
-        if (lact) {
-#pragma unroll
-          for (int a = 0; a < NU; ++a) Km[a * LDF + l] = hg[H_K + a * NX + l];
-        }
-        if (l < NU) {
-          kfm[l] = hg[H_KF + l];
-          if (pb.has_ubox) act = pb.act[gix(g, N, j, NU) + l];
-        }
-        if (pb.has_ubox)
-          for (int pi = l; pi < NHO; pi += 32) Hoff[pi] = hg[H_H + pi];
-        if (SLEW) {
-          const double* Eg = F.E + gix(g, N, j, NR);
-          for (int pi = l; pi < NR; pi += 32) Es[pi] = Eg[pi];
-        }
-      }
-      unsigned amask = __ballot_sync(0xffffffffu, l < NU && act != 0);
-      __syncwarp();
+      const signed char act = (l < NU) ? vc.act : 0;
+      const double lo = vc.lo, hi = vc.hi;
+      const unsigned amask = __ballot_sync(0xffffffffu, act != 0);
+      bar_wait(BAR_S0 + (j & 1));
       // ---- controls
       double u = 0.0, gx = 0.0;
       if (l < NU) {
         if (j < Nc) {
           u = __ldcg(uc + j * NU + l);
         } else {
-          if (j >= 1)
-            for (int t = 0; t < NX; ++t) gx += Km[l * LDF + t] * xv[t];
-          u = kfm[l] + gx;
+          if (j >= 1) {
+            for (int t = 0; t < NX; ++t) {
+              const int tt = (t + l >= NX) ? t + l - NX : t + l;
+              gx += Km[l * NX + tt] * xv[tt];
+            }
+          }
+          u = vc.kf + gx;
           if (SLEW && j >= 1)
             for (int b = 0; b < NU; ++b) u += s * rs_at(Es, l, b) * upm[b];
           if (act != 0) u = (act > 0) ? hi : lo;
@@ -627,7 +728,7 @@ struct Wpp {
         signed char na = 0;
         if (act != 0) {
           // dQ/du_a = H[a,:] u + G[a,:] x + h0[a] - s u_{j-1,a};  kf[a] already holds h0[a] + H[a, fixed] u_fixed
-          double acc = kfm[l] + gx;
+          double acc = vc.kf + gx;
           for (int b = 0; b < NU; ++b)
             if (b != l && !((amask >> b) & 1u)) acc += Hoff[l < b ? pko(l, b) : pko(b, l)] * um[b];
           if (SLEW && j >= 1) acc -= s * upm[l];
@@ -650,37 +751,40 @@ struct Wpp {
         }
       }
       // ---- x+ = A x + B u + c (row l; A_0 = 0: lqp_utils.jl:288-296)
-      double xn = cv[lc];
-      if (j >= 1)
-        for (int t = 0; t < NX; ++t) xn += Am[lc * LDF + t] * xv[t];
+      double xn = vc.c;
+      if (j >= 1) {
+#pragma unroll 4
+        for (int t = 0; t < NX; ++t) {
+          const int tt = (t + lc >= NX) ? t + lc - NX : t + lc;
+          xn += Am[lc * NX + tt] * xv[tt];
+        }
+      }
 #pragma unroll
       for (int a = 0; a < NU; ++a) xn += Bm[lc * NU + a] * um[a];
       // ---- bookkeeping (scp_mpc.py:397-405) and the scales of the acceptance test
       double d2 = 0.0, dx = 0.0;
       if (lact) {
-        const double xp = Xpv[gix(g, N, j, NX) + l];
-        const double qr = pb.qref[gix(g, N, j, NX) + l];
         Xc[gix(g, N, j, NX) + l] = xn;
-        const double d = xn - xp;
+        const double d = xn - vc.xp;
         d2 = d * d;
-        dx = xn - pb.xref[gix(g, N, j, NX) + l];
+        dx = xn - vc.xref;
         if (!(xn == xn)) nanf = 1.0;
         zscale = fmax(zscale, fabs(xn));
-        gscale = fmax(gscale, fabs(qr + pb.reg_x * xp));
-        if (pb.has_xbox)
-          xviol = fmax(xviol, fmax(xn - pb.ux[gix(g, N, j, NX) + l], pb.lx[gix(g, N, j, NX) + l] - xn));
+        gscale = fmax(gscale, fabs(vc.qref + pb.reg_x * vc.xp));
+        if (pb.has_xbox) xviol = fmax(xviol, fmax(xn - vc.ux, vc.lx - xn));
       }
       double e2 = 0.0, du = 0.0;
       if (l < NU) {
         Uc[gix(g, N, j, NU) + l] = u;
-        const double d = u - ub;
+        const double d = u - vc.ub;
         e2 = d * d;
-        du = u - pb.uref[gix(g, N, j, NU) + l];
+        du = u - vc.uref;
         if (!(u == u)) nanf = 1.0;
         zscale = fmax(zscale, fabs(u));
-        gscale = fmax(gscale, fabs(pb.rref[gix(g, N, j, NU) + l] + pb.reg_u * ub));
+        gscale = fmax(gscale, fabs(vc.rref + pb.reg_u * vc.ub));
       }
-      __syncwarp();  // every lane has read x, u_prev of the previous stage
+      __syncwarp();  // every lane has read x, u_prev and the ring slot of this stage
+      if (l == 0 && j + 2 < N) issue_f(j + 2);
       if (lact) {
         xv[l] = xn;
         dxv[l] = dx;
@@ -692,24 +796,25 @@ struct Wpp {
       dxm = fmax(dxm, warp_sum(d2));
       dum = fmax(dum, warp_sum(e2));
       __syncwarp();
+      bar_wait(BAR_FQ);
       {
-        const double* Qg = pb.Qs + gix(g, N, j, NQ);
-        const double* Rg = pb.Rs + gix(g, N, j, NR);
+        const double* Rb = sl + O_M;
         if (lact) {
           double acc = 0.0;
-          for (int t = 0; t < NX; ++t) acc += qs_at(Qg, l, t) * dxv[t];
+          for (int t = 0; t < NX; ++t) {
+            const int tt = (t + l >= NX) ? t + l - NX : t + l;
+            acc += qs_at(Qb, l, tt) * dxv[tt];
+          }
           obj += dx * (acc - pb.reg_x * dx);
         }
         if (l < NU) {
           double acc = 0.0;
-          for (int t = 0; t < NU; ++t) acc += rs_at(Rg, l, t) * dum_[t];
+          for (int t = 0; t < NU; ++t) acc += rs_at(Rb, l, t) * dum_[t];
           obj += du * (acc - (pb.reg_u + (j == 0 ? rdiag : 0.0)) * du);
         }
       }
-      x_l = xn;
-      __syncwarp();
+      __syncwarp();  // Qb / Rs staging free for the next stage
     }
-    (void)x_l;
     st[ST_DX] = sqrt(dxm);
     st[ST_DU] = sqrt(dum);
     st[ST_OBJ] = warp_sum(obj);
@@ -882,6 +987,7 @@ struct Wpp {
       tm.bflag = tm.pflag + Tc;
     }
     cred = reinterpret_cast<double*>(smem) + (size_t)W * SLAB;
+    stage_init();
     Xc = pb.X; Uc = pb.U; Xpv = pb.Xp; Upv = pb.Up;
     flip = false;
     double st[ST_COUNT];
