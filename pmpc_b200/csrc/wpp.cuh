@@ -42,6 +42,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// The kernel's dynamic shared memory, named at namespace scope: every slab pointer is derived from this symbol inside the
+// sweeps, so that the accesses compile to LDS / STS (a pointer parked in the object is a generic address: LD.E / ST.E
+// through the generic path, measured 2.5x slower in the thread-per-particle kernels).
+extern __shared__ __align__(16) unsigned char wpp_smem[];
+
 template <int NX, int NU, bool SLEW>
 struct Wpp {
   static constexpr int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2, NHO = NR - NU;
@@ -101,7 +106,7 @@ struct Wpp {
       : pb(pb_), smem(smem_), lane(threadIdx.x & 31), wid(threadIdx.x >> 5), W(blockDim.x >> 5), tid(threadIdx.x),
         T(blockDim.x), lc((threadIdx.x & 31) < NX ? (threadIdx.x & 31) : NX - 1), lact((threadIdx.x & 31) < NX) {}
 
-  __device__ __forceinline__ double* slab() const { return reinterpret_cast<double*>(smem) + (size_t)wid * SLAB; }
+  __device__ __forceinline__ double* slab() const { return reinterpret_cast<double*>(wpp_smem) + (threadIdx.x >> 5) * SLAB; }
   __device__ __forceinline__ static size_t gix(size_t g, int N_, int j, int E) { return (g * (size_t)N_ + (size_t)j) * (size_t)E; }
 
   __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want) {
@@ -200,28 +205,32 @@ struct Wpp {
   // factors the masked matrix redundantly (registers, no exchange), lane t < NU solves for column t and stores it.
   // The solves multiply by the stored reciprocals of the diagonal instead of dividing.
   __device__ __forceinline__ static void masked_inverse(const double* Hs, unsigned fmask, int t, double* Es) {
-    double L[NR], idg[NU];
+    double L[NU][NU], idg[NU];  // lower triangle only; plain 2-D constant indices keep it in registers
 #pragma unroll
     for (int a = 0; a < NU; ++a)
 #pragma unroll
-      for (int b = 0; b <= a; ++b) {
-        const bool fx = ((fmask >> a) | (fmask >> b)) & 1u;
-        L[pk(b, a, NU)] = fx ? (a == b ? 1.0 : 0.0) : Hs[a * NU + b];  // L[a][b], b <= a, packed as pk(b, a)
-      }
+      for (int b = 0; b < NU; ++b)
+        if (b <= a) {
+          const bool fx = ((fmask >> a) | (fmask >> b)) & 1u;
+          L[a][b] = fx ? (a == b ? 1.0 : 0.0) : Hs[a * NU + b];
+        }
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-      double dk = L[pk(k, k, NU)];
+      double dk = L[k][k];
 #pragma unroll
-      for (int q = 0; q < k; ++q) dk -= L[pk(q, k, NU)] * L[pk(q, k, NU)];
+      for (int q = 0; q < NU; ++q)
+        if (q < k) dk -= L[k][q] * L[k][q];
       const double idk = 1.0 / sqrt(dk);
       idg[k] = idk;
 #pragma unroll
-      for (int i = k + 1; i < NU; ++i) {
-        double v = L[pk(k, i, NU)];
+      for (int i = 0; i < NU; ++i)
+        if (i > k) {
+          double v = L[i][k];
 #pragma unroll
-        for (int q = 0; q < k; ++q) v -= L[pk(q, i, NU)] * L[pk(q, k, NU)];
-        L[pk(k, i, NU)] = v * idk;
-      }
+          for (int q = 0; q < NU; ++q)
+            if (q < k) v -= L[i][q] * L[k][q];
+          L[i][k] = v * idk;
+        }
     }
     if (t < NU) {
       double y[NU];
@@ -229,14 +238,16 @@ struct Wpp {
       for (int i = 0; i < NU; ++i) {
         double v = (i == t) ? 1.0 : 0.0;
 #pragma unroll
-        for (int q = 0; q < i; ++q) v -= L[pk(q, i, NU)] * y[q];
+        for (int q = 0; q < NU; ++q)
+          if (q < i) v -= L[i][q] * y[q];
         y[i] = v * idg[i];
       }
 #pragma unroll
       for (int i = NU - 1; i >= 0; --i) {
         double v = y[i];
 #pragma unroll
-        for (int q = i + 1; q < NU; ++q) v -= L[pk(i, q, NU)] * y[q];
+        for (int q = 0; q < NU; ++q)
+          if (q > i) v -= L[q][i] * y[q];
         y[i] = v * idg[i];
       }
 #pragma unroll
@@ -254,18 +265,18 @@ struct Wpp {
   // ------------------------------------------------------------------------------------------------------------
   // bulk-async staging (tma.cuh): lane 0 arms the warp's mbarrier with the byte count and issues the copies; every
   // lane waits on the barrier's phase.  ph[b] counts the completed uses of barrier b (uniform over the warp).
-  unsigned ph[6];
+  unsigned phA, phQ, phB, phS0, phS1, phFQ;
   __device__ __forceinline__ uint64_t* bar(int b) const { return reinterpret_cast<uint64_t*>(slab() + O_BAR) + b; }
-  __device__ __forceinline__ void bar_wait(int b) {
-    mbar_wait(bar(b), ph[b] & 1u);
-    ++ph[b];
+  __device__ __forceinline__ void bar_wait(int b, unsigned& ph) {
+    mbar_wait(bar(b), ph & 1u);
+    ++ph;
   }
   __device__ __forceinline__ void stage_init() {
     if (lane == 0) {
       for (int b = 0; b < 6; ++b) mbar_init(bar(b), 1);
       fence_mbar_init();
     }
-    for (int b = 0; b < 6; ++b) ph[b] = 0;
+    phA = phQ = phB = phS0 = phS1 = phFQ = 0;
     __syncwarp();
   }
 
@@ -341,7 +352,7 @@ struct Wpp {
         mbar_expect_tx(bar(BAR_A), NX * NX * 8);
         bulk_g2s(Am, pb.A + gix(g, N, j, NX * NX), NX * NX * 8, bar(BAR_A));
       }
-      bar_wait(BAR_Q);
+      bar_wait(BAR_Q, phQ);
       double Rp[(NR + 31) / 32];
 #pragma unroll
       for (int k = 0; k < (NR + 31) / 32; ++k) Rp[k] = vc.Rp[k];
@@ -358,7 +369,7 @@ struct Wpp {
       const unsigned fmask = __ballot_sync(0xffffffffu, fixed_l);  // bit a: control a of this stage sits at a bound
       __syncwarp();
       if (l == 0 && j - 1 >= Nc) issue_q(j - 1);  // Qb has been consumed
-      bar_wait(BAR_B);
+      bar_wait(BAR_B, phB);
       // ---- P1: wv = S c + q + p (element l), row l of S B + W.  S is symmetric: row l is read as column l
       {
         double wv = q_l + p_l;
@@ -442,7 +453,7 @@ struct Wpp {
 #pragma unroll
       for (int a = 0; a < NU; ++a) { Kc[a] = 0.0; Gc[a] = 0.0; }
       if (j >= 1) {
-        bar_wait(BAR_A);
+        bar_wait(BAR_A, phA);
         // ---- P4: column l of G = (S B + W)' A, K = -E G, p' = A' wv + G' k, S A
         double pn = 0.0;
         double SAc[NX];
@@ -451,13 +462,17 @@ struct Wpp {
 #pragma unroll 2
         for (int k = 0; k < NX; k += 2) {
           const double a0 = Am[k * NX + lc], a1 = Am[(k + 1) * NX + lc];
-          pn += a0 * wvv[k] + a1 * wvv[k + 1];
+          pn = fma(a0, wvv[k], pn);
+          pn = fma(a1, wvv[k + 1], pn);
 #pragma unroll
-          for (int a = 0; a < NU; ++a) Gc[a] += SBWm[k * NU + a] * a0 + SBWm[(k + 1) * NU + a] * a1;
+          for (int a = 0; a < NU; ++a) Gc[a] = fma(SBWm[k * NU + a], a0, Gc[a]);
 #pragma unroll
-          for (int r = 0; r < NX; ++r) {
+          for (int a = 0; a < NU; ++a) Gc[a] = fma(SBWm[(k + 1) * NU + a], a1, Gc[a]);
+#pragma unroll
+          for (int r = 0; r < NX; ++r) {  // two multiply-adds per broadcast LDS.128 (not a*b + c*d: that costs three)
             const double2 sv = *reinterpret_cast<const double2*>(&Sm[r * NX + k]);
-            SAc[r] += sv.x * a0 + sv.y * a1;
+            SAc[r] = fma(sv.x, a0, SAc[r]);
+            SAc[r] = fma(sv.y, a1, SAc[r]);
           }
         }
 #pragma unroll
@@ -703,7 +718,8 @@ struct Wpp {
       const signed char act = (l < NU) ? vc.act : 0;
       const double lo = vc.lo, hi = vc.hi;
       const unsigned amask = __ballot_sync(0xffffffffu, act != 0);
-      bar_wait(BAR_S0 + (j & 1));
+      if (j & 1) bar_wait(BAR_S1, phS1);
+      else bar_wait(BAR_S0, phS0);
       // ---- controls
       double u = 0.0, gx = 0.0;
       if (l < NU) {
@@ -796,7 +812,7 @@ struct Wpp {
       dxm = fmax(dxm, warp_sum(d2));
       dum = fmax(dum, warp_sum(e2));
       __syncwarp();
-      bar_wait(BAR_FQ);
+      bar_wait(BAR_FQ, phFQ);
       {
         const double* Rb = sl + O_M;
         if (lact) {
@@ -986,7 +1002,7 @@ struct Wpp {
       tm.pflag = reinterpret_cast<unsigned long long*>(tm.bc + tm.cap);
       tm.bflag = tm.pflag + Tc;
     }
-    cred = reinterpret_cast<double*>(smem) + (size_t)W * SLAB;
+    cred = reinterpret_cast<double*>(wpp_smem) + (size_t)W * SLAB;
     stage_init();
     Xc = pb.X; Uc = pb.U; Xpv = pb.Xp; Upv = pb.Up;
     flip = false;

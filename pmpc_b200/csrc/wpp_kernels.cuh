@@ -14,11 +14,10 @@ struct WppCfg {
 
 template <int NX, int NU, bool SLEW>
 __global__ void __launch_bounds__(32 * WppCfg<NX>::WMAX, 1) wpp_kernel(const __grid_constant__ DevProb pb, int Tc, int ppw) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ double red[ST_COUNT];
   __shared__ double red2[RCAP];
   Solver<NX, NU, true> S0(pb, red, red2, (int)blockIdx.x / Tc);
-  Wpp<NX, NU, SLEW> wk(pb, dyn_smem);
+  Wpp<NX, NU, SLEW> wk(pb, wpp_smem);
   wk.run(S0, Tc, ppw);
 }
 
