@@ -41,6 +41,24 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 M, N, NX, NU, NC = 128, 50, 4, 2, 1
 MAX_IT, RES_TOL = 100, 1e-5
 METRIC = "particle-SCP solves/sec (Dubins N=50 M=128 Nc=1, box control limits, res_tol 1e-5)"
+WORKLOAD = "C2 Dubins N=50 M=128 Nc=1 particle consensus"
+WORKLOADS = {  # BASELINE.json configs[1] (the one `metric` is quoted on) and configs[2]
+    "c2": dict(M=128, N=50, metric=METRIC, name=WORKLOAD),
+    "c3": dict(M=16, N=30, metric="particle-SCP solves/sec (batched independent MPC: 16384 Dubins problems N=30 M=16 Nc=1, box control "
+                                  "limits, res_tol 1e-5)", name="C3 16384 independent Dubins problems N=30 M=16 Nc=1, sharded over the GPUs"),
+}
+
+
+def set_workload(name):
+    global M, N, METRIC, WORKLOAD
+    w = WORKLOADS[name]
+    M, N, METRIC, WORKLOAD = w["M"], w["N"], w["metric"], w["name"]
+
+
+def config_dict():
+    """Identical in both arms (the driver compares it): the workload and its stop rule, and how L2 is kept cold."""
+    return {"workload": WORKLOAD, "max_it": MAX_IT, "res_tol": RES_TOL,
+            "l2": "inputs larger than L2: the batch working set is several GB per GPU (> 126 MB L2); no flush needed"}
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -63,7 +81,26 @@ def make_batch(B: int, seed: int):
     arrs = dict(Q=tile(d0["Q"]), R=tile(d0["R"]), x0=np.ascontiguousarray(x0), X_ref=tile(d0["X_ref"]),
                 U_ref=tile(d0["U_ref"]), X_prev=tile(d0["X_prev"]), U_prev=tile(d0["U_prev"]), u_l=tile(d0["u_l"]),
                 u_u=tile(d0["u_u"]))
+    if M == 16:  # C3: X_ref = 0.1 N(0,1) per problem, x0 ~ N(1, 0.1^2)
+        arrs["X_ref"] = np.ascontiguousarray(np.repeat(0.1 * rng.standard_normal((B, 1, N, NX)), M, axis=1))
+        arrs["x0"] = np.ascontiguousarray(np.repeat(1.0 + 0.1 * rng.standard_normal((B, 1, NX)), M, axis=1))
     return arrs, np.ascontiguousarray(p), d0
+
+
+def untiled(arrs):
+    """The same batch as `make_batch` builds, with every input that is identical for all particles given once: one block
+    (N, .) for the whole batch (costs, bounds, warm start), one block per problem for X_ref, one x0 per problem.  This is
+    what the end-to-end leg uploads (solve_batch expands on the device, pmpc_set_broadcast)."""
+    out = {}
+    for k, a in arrs.items():
+        if k == "x0":
+            out[k] = np.ascontiguousarray(a[:, 0])
+        elif k == "X_ref" and M == 16:
+            out[k] = np.ascontiguousarray(a[:, 0])
+        else:
+            assert np.array_equal(a[0, 0], a[-1, -1])
+            out[k] = np.ascontiguousarray(a[0, 0])
+    return out
 
 
 class ClockSampler:
@@ -143,6 +180,12 @@ def alg_bytes_flops(info, n=NX, m=NU, nlin=10):
     return float(per * (passes * b_pass).sum()), float(per * (passes * f_fac + I * f_vec).sum())
 
 
+def survey_resident_bytes(info, n=NX, m=NU):
+    """SURVEY.md 8(d)'s figure for a problem whose factors stay on chip: the problem data
+    8 (2 n^2 + n m + m^2 + 4 n + 4 m) = 544 B per (particle, stage) streamed ONCE per SCP iteration."""
+    return float(M * N * 8 * (2 * n * n + n * m + m * m + 4 * n + 4 * m) * info["scp_iters"].astype(np.float64).sum())
+
+
 def survey_streaming_bytes(info, n=NX, m=NU, nparam=3):
     """SURVEY.md 8(d)'s *streaming* model (every factorisation streams Q, fx, fu, R in and K, P out; every vector pass
     streams fx, fu, K and the stage vectors; every SCP iteration streams the linearisation once) — what an unfused
@@ -186,17 +229,20 @@ def reference_arm(args):
     full_its = c2_iters_fixture()["c_port_scp_iters"]
     sample_its = args.ref_sample_its
     for _ in range(args.warmup):
-        cpu_sample(cores, sample_its)
+        cpu_sample(cores, 1)  # warm-up: caches and thread pool only; one SCP iteration each
     times = [cpu_sample(cores, sample_its, seed=k) for k in range(args.steps)]
     step = float(np.mean(times))
     value = cores * (sample_its / full_its) / step
     sample = (f"{cores} host threads, each the first {sample_its} of {full_its} SCP iterations of its own C2 problem "
               f"(plain-C restatement: OSQP 0.6.2 at the reference's defaults eps=1e-3), scaled to full solves")
+    import shutil
+
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 Dubins N=50 M=128 Nc=1 particle consensus", "host_cores": cores,
-                       "reference": "restated CPU baseline (oracle/c), not PMPC.jl: Julia/OSQP absent from the image"},
+            "config": config_dict(),
+            "details": {"host_cores": cores, "julia_on_this_box": shutil.which("julia"),
+                        "reference": "restated CPU baseline (oracle/c), not PMPC.jl: Julia/OSQP absent from the image"},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -217,9 +263,13 @@ def main():
     ap.add_argument("--latency-solves", type=int, default=200)
     ap.add_argument("--e2e-chunks", type=int, default=16, help="sub-batches of the pipelined end-to-end leg (1 = no pipelining; default = half a wave each: kernels of consecutive sub-batches co-reside)")
     ap.add_argument("--cpu-sample-its", type=int, default=16)
-    ap.add_argument("--ref-sample-its", type=int, default=4)
+    ap.add_argument("--ref-sample-its", type=int, default=16,
+                    help="SCP iterations every host thread runs per step in the reference arm (62 = whole solves; early iterations "
+                         "are the cheaper ones, so a short sample favours the CPU)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE configs[1] (the metric's config), c3 = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    set_workload(args.workload)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -251,6 +301,8 @@ def main():
 
     K, W = args.steps, max(args.warmup, 0)
     B = args.batch
+    if B <= 0 and args.workload == "c3":
+        B = 16384 // world  # BASELINE configs[2]: 16384 problems sharded over the GPUs (strong scaling)
     if B <= 0:
         # one CTA per problem: size the batch in whole waves of the solve kernel (148 SMs x resident CTAs)
         a1, p1, d1 = make_batch(1, 0)
@@ -312,6 +364,11 @@ def main():
                          "out+in; X,U,act out (DESIGN.md 5)",
                 "fp64_tflops_dense_equivalent": aflops / (kernel_ms * 1e-3) / 1e12,
                 "unfused_streaming_model_bytes_per_launch": survey_streaming_bytes(info)}
+    # the same kernel on SURVEY.md 8(d)'s own denominator (problem data once per SCP iteration, 544 B per unit): what an
+    # implementation that kept the whole factorisation on chip would have to move
+    sbytes = survey_resident_bytes(info)
+    roofline.update(frac_survey=sbytes / (kernel_ms * 1e-3) / 1e9 / peak, survey_bytes_per_launch=sbytes,
+                    survey_model="SURVEY 8(d) on-chip-resident case: 8(2n^2+nm+m^2+4n+4m) = 544 B per (particle, stage) per SCP iteration")
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
@@ -326,9 +383,11 @@ def main():
                 roofline[key] = r.value
 
     # ---- end to end through the public API with host buffers ---------------------------------------
+    ua = {k: pmpc_b200.pinned_copy(v) for k, v in untiled(arrs).items()}
+
     def e2e_step(solver):
-        return pmpc_b200.solve_batch(p, arrs["Q"], arrs["R"], arrs["x0"], arrs["X_ref"], arrs["U_ref"], arrs["X_prev"],
-                                     arrs["U_prev"], None, None, arrs["u_l"], arrs["u_u"], max_it=MAX_IT, res_tol=RES_TOL,
+        return pmpc_b200.solve_batch(p, ua["Q"], ua["R"], ua["x0"], ua["X_ref"], ua["U_ref"], ua["X_prev"],
+                                     ua["U_prev"], None, None, ua["u_l"], ua["u_u"], max_it=MAX_IT, res_tol=RES_TOL,
                                      reg_x=d0["reg_x"], reg_u=d0["reg_u"], slew_rate=0.0, Nc=NC, device=local, solver=solver,
                                      reuse_buffers=True, chunks=args.e2e_chunks)
 
@@ -342,11 +401,12 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_s = parallel.reduce_max(e2e_s, dist, dev_t)
-    h2d = sum(a.nbytes for a in arrs.values()) + p.nbytes + 8 * B * M  # inputs + params + slew vector
+    h2d = sum(a.nbytes for a in ua.values()) + p.nbytes + 8 * B * M  # inputs as uploaded + params + slew vector
     d2h = Xe.nbytes + Ue.nbytes + 8 * 8 * B
     e2e = {"value": world * B * K / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": 1e3 * e2e_s / K, "api": "pmpc_b200.solve_batch (page-locked host numpy arrays in, page-locked host arrays out; the batch is "
-                  "pipelined in %d sub-batches so that uploads / downloads overlap the solve kernels)" % args.e2e_chunks}
+                  "pipelined in %d sub-batches so that uploads / downloads overlap the solve kernels; inputs that are "
+                  "identical for all particles are passed once and expanded on the device)" % args.e2e_chunks}
     ok = ok and np.array_equal(Xe[:, :, 1:], X.reshape(Xe[:, :, 1:].shape)) and bool((infoe["status"] == 0).all())
 
     # ---- single-solve latency through pmpc_b200.solve (the call a reference user makes) -----------
@@ -376,12 +436,13 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": ("strong" if args.workload == "c3" and args.batch <= 0 else "weak"),
+                "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "C2 Dubins N=50 M=128 Nc=1 particle consensus", "problems_per_gpu_per_step": B,
-                           "ctas_per_sm": occ[0], "sms": occ[1],
-                           "max_it": MAX_IT, "res_tol": RES_TOL, "l2": "working set %.1f GB per GPU > 126 MB L2" % (
-                               B * M * N * 135 * 8 / 1e9), "parallelism": "problem batch sharded, no collective"},
+                "config": config_dict(),
+                "details": {"problems_per_gpu_per_step": B, "ctas_per_sm": occ[0], "sms": occ[1],
+                            "working_set_gb_per_gpu": B * M * N * 135 * 8 / 1e9, "parallelism": "problem batch sharded, no collective",
+                            "julia_on_this_box": __import__("shutil").which("julia")},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu, "parity_ok": ok,
                 "scp_iters": {"min": int(info["scp_iters"].min()), "max": int(info["scp_iters"].max()),
@@ -389,7 +450,7 @@ def main():
                 "qp_passes_per_solve": {"factorizations": float(info["factorizations"].mean()),
                                         "polish": float(info["polish_passes"].mean()), "admm": float(info["admm_iters"].mean())},
                 "latency_ms": ({"p50": 1e3 * float(np.median(lat)), "min": 1e3 * float(min(lat)), "n": len(lat),
-                                "api": "pmpc_b200.solve, one C2 problem, host arrays"} if lat else None),
+                                "api": "plain pmpc_b200.solve(...) call, one problem, host arrays (handles are cached inside solve)"} if lat else None),
                 "wall_ms_per_step": 1e3 * wall / K}
         _emit(line)
     if dist is not None:

@@ -117,6 +117,13 @@ int pmpc_set_problem(pmpc_handle_t h, const double *x0, const double *Q, const d
  * 0 (default) = column-major blocks, the reference C ABI; 1 = row-major blocks, i.e. NumPy C-order
  * (M,N,rows,cols) arrays as `pmpc.solve` receives them, so that no host-side transpose is needed. */
 int pmpc_set_layout(pmpc_handle_t h, int row_major_matrices);
+/* Inputs that are identical for many particles need not be tiled on the host (the reference's API makes the caller
+ * tile Q, R, references and bounds over the particle axis, `tests/simple.py:20-30`; for a batch that is most of the
+ * upload).  Bit k of all_mask: input k of pmpc_set_problem / pmpc_set_warm_start is ONE (N, .) block shared by every
+ * particle of every problem; bit k of per_problem_mask: one block per problem, (B, N, .), shared by its particles.
+ * Bits: 0 Q, 1 R, 2 X_ref, 3 U_ref, 4 lx, 5 ux, 6 lu, 7 uu, 8 X_prev, 9 U_prev.  The expansion happens in the device
+ * packing kernels; sticky until changed; default 0 (every input carries the full (B*M, N, .) layout). */
+int pmpc_set_broadcast(pmpc_handle_t h, unsigned all_mask, unsigned per_problem_mask);
 /* Page-locked host buffers (cudaHostAlloc) for inputs / outputs of the handle API: H2D / D2H copies from
  * them run at full PCIe / C2C speed and asynchronously. */
 int pmpc_host_alloc(void **p, size_t bytes);

@@ -59,6 +59,7 @@ _SIG = {
     "pmpc_set_problem": (C.c_int, [C.c_void_p] + [_DP] * 9 + [C.c_double, C.c_double] + [_DP] * 3),
     "pmpc_set_warm_start": (C.c_int, [C.c_void_p, _DP, _DP]),
     "pmpc_set_layout": (C.c_int, [C.c_void_p, C.c_int]),
+    "pmpc_set_broadcast": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint]),
     "pmpc_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pmpc_host_free": (C.c_int, [C.c_void_p]),
     "pmpc_set_dynamics": (C.c_int, [C.c_void_p, C.c_int, _DP, C.c_size_t, C.c_double]),

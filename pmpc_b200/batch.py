@@ -127,9 +127,15 @@ def solve_batch(dyn_params, Q, R, x0, X_ref=None, U_ref=None, X_prev=None, U_pre
     ``chunks > 1`` pipelines the batch: it is cut into ``chunks`` contiguous sub-batches, each on its own handle
     (own CUDA stream); the host-to-device upload and packing of sub-batch k+1 and the device-to-host read of
     sub-batch k-1 overlap the solve kernel of sub-batch k, so PCIe time leaves the critical path except for the
-    first upload and the last download.  Results are identical to ``chunks=1`` (problems are independent)."""
+    first upload and the last download.  Results are identical to ``chunks=1`` (problems are independent).
+
+    Inputs that are the same for every particle need not be tiled (the reference's API makes the caller tile them,
+    ``tests/simple.py:20-30``): ``Q, R, X_ref, U_ref, X_prev, U_prev`` and the bounds may be given as ONE block
+    ``(N, ...)`` for the whole batch or one block per problem ``(B, N, ...)``, ``x0`` as ``(B, n)``; the device packing
+    kernels expand them (``pmpc_set_broadcast``), which removes most of the host-to-device traffic of a batch."""
     Q = np.asarray(Q)
-    B, M, N, n = Q.shape[:4]
+    B, M = np.asarray(dyn_params).shape[:2]
+    N, n = Q.shape[-3], Q.shape[-1]
     m = np.asarray(R).shape[-1]
     if chunks > 1 and B >= chunks:
         return _solve_batch_pipelined(dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u, max_it, res_tol,
@@ -167,7 +173,8 @@ def _solve_batch_pipelined(dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x
                            slew_rate, Nc, dyn_eps, device, solver, settings, reuse_buffers, chunks):
     from ._lib import pinned_empty
 
-    B, M, N, n = Q.shape[:4]
+    B, M = np.asarray(dyn_params).shape[:2]
+    N, n = Q.shape[-3], Q.shape[-1]
     m = np.asarray(R).shape[-1]
     key = (B, M, N, n, m, Nc, chunks, device)
     pipe = solver if isinstance(solver, BatchPipeline) and solver.key == key else None
@@ -181,11 +188,17 @@ def _solve_batch_pipelined(dyn_params, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x
         X, U = pipe.out
     else:
         X, U = np.empty((B, M, N + 1, n)), np.empty((B, M, N, m))
-    cut = lambda a, lo, hi: None if a is None else np.asarray(a)[lo:hi]
+    def cut(a, lo, hi, full_ndim=4):
+        """sub-batch [lo, hi) of an input: arrays without a problem axis (one block for the whole batch) pass through"""
+        if a is None:
+            return None
+        a = np.asarray(a)
+        return a if a.ndim <= full_ndim - 2 else a[lo:hi]
+
     # uploads run one after the other (each gets the full PCIe bandwidth); every solve is asynchronous on its own stream,
     # so sub-batch k+1 is uploaded and packed while sub-batch k is being solved
     for (lo, hi), ds in zip(pipe.bounds, pipe.solvers):
-        _upload_and_launch(ds, cut(dyn_params, lo, hi), Q[lo:hi], cut(R, lo, hi), cut(x0, lo, hi), cut(X_ref, lo, hi),
+        _upload_and_launch(ds, np.asarray(dyn_params)[lo:hi], cut(Q, lo, hi, 5), cut(R, lo, hi, 5), np.asarray(x0)[lo:hi], cut(X_ref, lo, hi),
                            cut(U_ref, lo, hi), cut(X_prev, lo, hi), cut(U_prev, lo, hi), cut(x_l, lo, hi), cut(x_u, lo, hi),
                            cut(u_l, lo, hi), cut(u_u, lo, hi), max_it, res_tol, reg_x, reg_u, slew_rate, dyn_eps)
     infos = []

@@ -100,6 +100,7 @@ struct pmpc_handle_s {
   size_t raw_doubles = 0;
   int* flags = nullptr;       // device-side NaN-sentinel analysis of the optional arguments (FL_*)
   int row_major = 0;          // matrices given as C-order (rows, cols) blocks instead of column-major
+  unsigned bc_all = 0, bc_prob = 0;  // pmpc_set_broadcast: inputs given once for the whole batch / once per problem
   double* comm = nullptr;     // particle sharding: this rank's exchange buffer (IPC-exported to the peers)
   size_t comm_bytes = 0;
   void* peer_open[8] = {nullptr};  // peers' buffers opened with cudaIpcOpenMemHandle (to close on destroy)
@@ -134,6 +135,10 @@ __device__ __forceinline__ size_t tix(size_t slot, Lay L, int j, int E, int e) {
   return (((slot / L.tile) * (size_t)L.N + (size_t)j) * (size_t)E + (size_t)e) * L.tile + (slot % L.tile);
 }
 
+// pmpc_set_broadcast: which block of an input array particle gf reads — its own (mode 0), its problem's (1), the only one (2)
+enum { BC_Q = 0, BC_R, BC_XREF, BC_UREF, BC_LX, BC_UX, BC_LU, BC_UU, BC_XPREV, BC_UPREV, BC_COUNT };
+__host__ __device__ __forceinline__ size_t src_row(int gf, int M, int mode) { return mode == 2 ? 0 : (mode == 1 ? (size_t)(gf / M) : (size_t)gf); }
+
 enum { FL_XBOX_ABSENT = 0, FL_UBOX_ABSENT, FL_SLEW_ABSENT, FL_SLEW0_ABSENT, FL_SLEW_NONZERO, FL_COUNT = 8 };
 
 // flag = 1 when any element is NaN (the reference's "option absent" sentinel, c_interface.jl:56-70)
@@ -152,16 +157,17 @@ __global__ void nonzero_flag_kernel(const double* __restrict__ a, size_t n, int*
 
 // absent: optional device flag; when set the whole array counts as absent -> `fill`
 __global__ void pack_vec_kernel(const double* __restrict__ in, double* __restrict__ out, int Ptot, Lay L, int Ei, int Eo,
-                                double fill, const int* __restrict__ absent) {
+                                double fill, const int* __restrict__ absent, int mode = 0) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = L.N;
   if (idx >= (size_t)Ptot * N) return;
   if (absent != nullptr && *absent) in = nullptr;
   const int gf = (int)(idx % Ptot), j = (int)(idx / Ptot);
   const size_t sl = slot_of(gf, L);
+  const size_t gs = src_row(gf, L.M, mode);
   for (int e = 0; e < Eo; ++e) {
     double v = fill;
-    if (in != nullptr && e < Ei) v = in[((size_t)gf * N + j) * Ei + e];
+    if (in != nullptr && e < Ei) v = in[(gs * N + j) * Ei + e];
     out[tix(sl, L, j, Eo, e)] = v;
   }
 }
@@ -192,7 +198,7 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
                                  const double* __restrict__ Xref, const double* __restrict__ Uref,
                                  const double* __restrict__ s, const double* __restrict__ s0,
                                  const double* __restrict__ um1, int Ptot, int quirk_keep_um1, int row_major,
-                                 const int* __restrict__ flags) {
+                                 const int* __restrict__ flags, unsigned bc_all, unsigned bc_prob) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = pb.N, n = pb.n, m = pb.m;
   if (idx >= (size_t)Ptot * N) return;
@@ -200,14 +206,15 @@ __global__ void pack_cost_kernel(DevProb pb, int NX, int NU, const double* __res
   const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   const size_t sl = slot_of(g, L);
   const size_t P = pb.P;
-  const double* Qb = Q + ((size_t)g * N + j) * n * n;  // column-major: Q[r,t] = Qb[t*n + r]
-  const double* Rb = R + ((size_t)g * N + j) * m * m;
+  auto mode = [&](int k) { return ((bc_all >> k) & 1u) ? 2 : (((bc_prob >> k) & 1u) ? 1 : 0); };
+  const double* Qb = Q + (src_row(g, pb.M, mode(BC_Q)) * N + j) * n * n;  // column-major: Q[r,t] = Qb[t*n + r]
+  const double* Rb = R + (src_row(g, pb.M, mode(BC_R)) * N + j) * m * m;
   // element (r, t) of an (a x a) block: column-major (reference C ABI) or row-major (NumPy C order)
   const int qr = row_major ? n : 1, qt = row_major ? 1 : n, rr_ = row_major ? m : 1, rt = row_major ? 1 : m;
   if (flags[FL_SLEW_ABSENT]) s = nullptr;
   if (flags[FL_SLEW0_ABSENT]) { s0 = nullptr; um1 = nullptr; }
-  const double* xr = Xref ? Xref + ((size_t)g * N + j) * n : nullptr;
-  const double* ur = Uref ? Uref + ((size_t)g * N + j) * m : nullptr;
+  const double* xr = Xref ? Xref + (src_row(g, pb.M, mode(BC_XREF)) * N + j) * n : nullptr;
+  const double* ur = Uref ? Uref + (src_row(g, pb.M, mode(BC_UREF)) * N + j) * m : nullptr;
   const int NQ = NX * (NX + 1) / 2, NR = NU * (NU + 1) / 2;
   for (int r = 0; r < NX; ++r) {
     for (int t = r; t < NX; ++t) {
@@ -542,15 +549,16 @@ static int upload(pmpc_handle_t h, const double* src, size_t cnt, size_t off, do
 }
 
 // stream-ordered: no synchronisation here; `off` keeps concurrent uploads apart in the staging buffer
-static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, int Eo, double fill, size_t off = 0) {
+static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, int Eo, double fill, size_t off = 0, int mode = 0) {
   const DevProb& pb = h->pb;
   double* dev = nullptr;
   if (host) {
-    int rc = upload(h, host, h->Ptot * pb.N * Ei, off, &dev);
+    const size_t blocks = mode == 2 ? 1 : (mode == 1 ? (size_t)pb.B : h->Ptot);
+    int rc = upload(h, host, blocks * pb.N * Ei, off, &dev);
     if (rc) return rc;
   }
   pack_vec_kernel<<<nblk(h->Ptot * pb.N), 256, 0, h->stream>>>(dev, out, (int)h->Ptot, Lay{pb.M, pb.Mpad, pb.N, pb.tile}, Ei, Eo, fill,
-                                                              nullptr);
+                                                              nullptr, mode);
   ++g_launches;
   CU(cudaGetLastError());
   return PMPC_OK;
@@ -559,6 +567,13 @@ static int pack_vec(pmpc_handle_t h, const double* host, double* out, int Ei, in
 int pmpc_set_layout(pmpc_handle_t h, int row_major_matrices) {
   if (!h) return fail(PMPC_ERR_BAD_ARG, "null");
   h->row_major = row_major_matrices ? 1 : 0;
+  return PMPC_OK;
+}
+
+int pmpc_set_broadcast(pmpc_handle_t h, unsigned all_mask, unsigned per_problem_mask) {
+  if (!h || (all_mask >> BC_COUNT) || (per_problem_mask >> BC_COUNT)) return fail(PMPC_ERR_BAD_ARG, "null handle or unknown input bit");
+  h->bc_all = all_mask;
+  h->bc_prob = per_problem_mask & ~all_mask;
   return PMPC_OK;
 }
 
@@ -586,8 +601,11 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   const int n = pb.n, m = pb.m, N = pb.N, NX = h->shape.NX, NU = h->shape.NU;
   const size_t Pt = h->Ptot;
   pb.reg_x = reg_x; pb.reg_u = reg_u;
-  const size_t nQ = Pt * N * n * n, nR = Pt * N * m * m, nX = Pt * N * n, nU = Pt * N * m;
-  const size_t total = nQ + nR + 3 * nX + 3 * nU + Pt * (2 + m) + Pt * n + 64;
+  auto bmode = [&](int k) { return ((h->bc_all >> k) & 1u) ? 2 : (((h->bc_prob >> k) & 1u) ? 1 : 0); };
+  auto rows = [&](int k) -> size_t { return bmode(k) == 2 ? 1 : (bmode(k) == 1 ? (size_t)pb.B : Pt); };  // blocks of input k
+  const size_t nQ = rows(BC_Q) * N * n * n, nR = rows(BC_R) * N * m * m, nXr = rows(BC_XREF) * N * n, nUr = rows(BC_UREF) * N * m;
+  const size_t nLx = rows(BC_LX) * N * n, nUx = rows(BC_UX) * N * n, nLu = rows(BC_LU) * N * m, nUu = rows(BC_UU) * N * m;
+  const size_t total = nQ + nR + nXr + nUr + nLx + nUx + nLu + nUu + Pt * (2 + m) + Pt * n + 64;
   if (total > h->raw_doubles) {
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->raw);
@@ -614,31 +632,31 @@ int pmpc_set_problem(pmpc_handle_t h, const double* x0, const double* Q, const d
   init[FL_SLEW_ABSENT] = !slew_reg;
   init[FL_SLEW0_ABSENT] = (!slew_reg0 || !slew_um1);
   CU(cudaMemcpyAsync(h->flags, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-  if ((rc = up(lx, nX, &dlx)) || (rc = up(ux, nX, &dux)) || (rc = up(lu, nU, &dlu)) || (rc = up(uu, nU, &duu)) ||
+  if ((rc = up(lx, nLx, &dlx)) || (rc = up(ux, nUx, &dux)) || (rc = up(lu, nLu, &dlu)) || (rc = up(uu, nUu, &duu)) ||
       (rc = up(slew_reg, Pt, &ds)) || (rc = up(slew_reg0, Pt, &ds0)) || (rc = up(slew_um1, Pt * m, &dum1)) ||
-      (rc = up(x0, Pt * n, &dx0)) || (rc = up(X_ref, nX, &dXr)) || (rc = up(U_ref, nU, &dUr)) || (rc = up(R, nR, &dR)) ||
+      (rc = up(x0, Pt * n, &dx0)) || (rc = up(X_ref, nXr, &dXr)) || (rc = up(U_ref, nUr, &dUr)) || (rc = up(R, nR, &dR)) ||
       (rc = up(Q, nQ, &dQ)))
     return rc;
   auto nanflag = [&](const double* d, size_t cnt, int k) {
     if (d) { nan_flag_kernel<<<std::min(nblk(cnt), 1184), 256, 0, h->stream>>>(d, cnt, h->flags + k); ++g_launches; }
   };
-  nanflag(dlx, nX, FL_XBOX_ABSENT); nanflag(dux, nX, FL_XBOX_ABSENT);
-  nanflag(dlu, nU, FL_UBOX_ABSENT); nanflag(duu, nU, FL_UBOX_ABSENT);
+  nanflag(dlx, nLx, FL_XBOX_ABSENT); nanflag(dux, nUx, FL_XBOX_ABSENT);
+  nanflag(dlu, nLu, FL_UBOX_ABSENT); nanflag(duu, nUu, FL_UBOX_ABSENT);
   nanflag(ds, Pt, FL_SLEW_ABSENT);
   nanflag(ds0, Pt, FL_SLEW0_ABSENT); nanflag(dum1, Pt * m, FL_SLEW0_ABSENT);
   if (ds) { nonzero_flag_kernel<<<std::min(nblk(Pt), 1184), 256, 0, h->stream>>>(ds, Pt, h->flags + FL_SLEW_NONZERO); ++g_launches; }
   pack_cost_kernel<<<nblk(Pt * N), 256, 0, h->stream>>>(pb, NX, NU, dQ, dR, dXr, dUr, ds, ds0, dum1, (int)Pt,
-                                                         h->Nc_orig >= 1 ? 1 : 0, h->row_major, h->flags);
+                                                         h->Nc_orig >= 1 ? 1 : 0, h->row_major, h->flags, h->bc_all, h->bc_prob);
   ++g_launches;
   const Lay L{pb.M, pb.Mpad, pb.N, pb.tile};
   pack_particle_kernel<<<nblk(Pt), 256, 0, h->stream>>>(dx0, pb.x0, (int)Pt, pb.P, L, n, NX, 0.0);
   ++g_launches;
   const double inf = INFINITY;
   const int nb = nblk(Pt * N);
-  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dlu, pb.lu, (int)Pt, L, m, NU, -inf, h->flags + FL_UBOX_ABSENT);
-  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(duu, pb.uu, (int)Pt, L, m, NU, inf, h->flags + FL_UBOX_ABSENT);
-  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dlx, pb.lx, (int)Pt, L, n, NX, -inf, h->flags + FL_XBOX_ABSENT);
-  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dux, pb.ux, (int)Pt, L, n, NX, inf, h->flags + FL_XBOX_ABSENT);
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dlu, pb.lu, (int)Pt, L, m, NU, -inf, h->flags + FL_UBOX_ABSENT, bmode(BC_LU));
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(duu, pb.uu, (int)Pt, L, m, NU, inf, h->flags + FL_UBOX_ABSENT, bmode(BC_UU));
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dlx, pb.lx, (int)Pt, L, n, NX, -inf, h->flags + FL_XBOX_ABSENT, bmode(BC_LX));
+  pack_vec_kernel<<<nb, 256, 0, h->stream>>>(dux, pb.ux, (int)Pt, L, n, NX, inf, h->flags + FL_XBOX_ABSENT, bmode(BC_UX));
   g_launches += 4;
   fill_int_kernel<<<nblk(pb.B), 256, 0, h->stream>>>(h->uniform, pb.B, 1);
   ++g_launches;
@@ -660,8 +678,9 @@ int pmpc_set_warm_start(pmpc_handle_t h, const double* X_prev, const double* U_p
   CU(cudaSetDevice(h->device));
   DevProb& pb = h->pb;
   int rc;
-  if ((rc = pack_vec(h, X_prev, pb.Xp, pb.n, h->shape.NX, 0.0, 0))) return rc;
-  if ((rc = pack_vec(h, U_prev, pb.Up, pb.m, h->shape.NU, 0.0, h->Ptot * pb.N * pb.n))) return rc;
+  auto bmode = [&](int k) { return ((h->bc_all >> k) & 1u) ? 2 : (((h->bc_prob >> k) & 1u) ? 1 : 0); };
+  if ((rc = pack_vec(h, X_prev, pb.Xp, pb.n, h->shape.NX, 0.0, 0, bmode(BC_XPREV)))) return rc;
+  if ((rc = pack_vec(h, U_prev, pb.Up, pb.m, h->shape.NU, 0.0, h->Ptot * pb.N * pb.n, bmode(BC_UPREV)))) return rc;
   // reset ADMM / active-set state
   const size_t P = pb.P, N = pb.N, NX = h->shape.NX, NU = h->shape.NU;
   CU(cudaMemsetAsync(pb.wu, 0, N * NU * P * sizeof(double), h->stream));

@@ -220,7 +220,7 @@ struct Wpp {
 #pragma unroll
       for (int q = 0; q < NU; ++q)
         if (q < k) dk -= L[k][q] * L[k][q];
-      const double idk = 1.0 / sqrt(dk);
+      const double idk = rsqrt(dk);
       idg[k] = idk;
 #pragma unroll
       for (int i = 0; i < NU; ++i)
@@ -339,6 +339,8 @@ struct Wpp {
       mbar_expect_tx(bar(BAR_B), NX * NU * 8);
       bulk_g2s(Bm, pb.Bm + gix(g, N, j, NX * NU), NX * NU * 8, bar(BAR_B));
     };
+    fence_proxy_async();  // plain stores of the previous phase into buffers the bulk copies are about to overwrite
+    __syncwarp();
     if (l == 0) {
       issue_q(N - 1);
       issue_b(N - 1);
@@ -563,75 +565,164 @@ struct Wpp {
   }
 
   // ------------------------------------------------------------------------------------------------------------
-  // Gradient of the particle's cost w.r.t. the shared controls (Solver::shared_grad): hom: Hessian action on the unit
-  // vector ek, else the gradient at uc = 0 with all linear terms.  The boundary value function is in the slab (see
-  // bsweep).  Result: lane b < NU holds out[j * NU + b] for the stage it is called back with.  Xc rows 0 .. Nc-1 are
-  // used as scratch for the shared-stage states, as in the thread-per-particle kernel.
+  // Gradients of the particle's cost w.r.t. the shared controls (Solver::shared_grad), VB directions at a time:
+  // direction v < D is the Hessian action on the unit vector e_v (homogeneous pass), direction v == D the gradient at
+  // uc = 0 with all linear terms.  Blocking the directions lets every matrix entry (A, Qs, Pc, B rows, read per lane
+  // from global memory / the slab) serve VB products and gives VB independent dependency chains.  The boundary value
+  // function is in the slab (see bsweep).  emit(v, j, value) is called in lane b < NU with d/du_{j,b}.
+  // Scratch for the shared-stage states of the VB directions: the ADMM factor set's K array of this particle
+  // (re-built by the thread-per-particle kernel whenever it starts an ADMM block).
+  static constexpr int VB = 4;
   template <typename Emit>
-  __device__ __forceinline__ void shared_grad(size_t g, bool hom, int ek, Emit emit) {
+  __device__ __forceinline__ void shared_grads(size_t g, int v0, Emit emit) {
     double* sl = slab();
     double *Pc = sl + O_S, *Wc = sl + O_W, *Zc = sl + O_M + MM_Z, *pcv = sl + O_V + V_WV, *zc = sl + O_U + U_Z;
-    double *xv = sl + O_V + V_X, *av = sl + O_V + V_AD;
+    double *xv = sl + O_A, *av = sl + O_A + VB * NX;  // [VB][NX] each (the A buffer is idle between the sweeps)
+    double* xs = pb.fs[MODE_ADMM].K + gix(g, N, 0, NU * NX);  // [Nc][VB][NX]
     const int l = lane;
     const double s = SLEW ? pb.slew[g] : 0.0;
-    auto uval = [&](int j, int t) -> double { return (hom && j >= 0 && j < Nc && j * NU + t == ek) ? 1.0 : 0.0; };
-    if (lact) xv[l] = 0.0;
+    // u_{j,t} of direction vb: unit vector for v < D, zero for the inhomogeneous direction (and beyond it)
+    auto uval = [&](int vb, int j, int t) -> double { return (v0 + vb < D && j >= 0 && j < Nc && j * NU + t == v0 + vb) ? 1.0 : 0.0; };
+    auto inhom = [&](int vb) -> bool { return v0 + vb == D; };
+    if (lact) {
+#pragma unroll
+      for (int vb = 0; vb < VB; ++vb) xv[vb * NX + l] = 0.0;
+    }
     __syncwarp();
     for (int j = 0; j < Nc; ++j) {
       const double* Ag = pb.A + gix(g, N, j, NX * NX);
       const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
-      double acc = hom ? 0.0 : pb.c[gix(g, N, j, NX) + lc];
-      if (j >= 1)
-        for (int t = 0; t < NX; ++t) acc += Ag[lc * NX + t] * xv[t];
-      for (int t = 0; t < NU; ++t) acc += Bg[lc * NU + t] * uval(j, t);
+      const double cj = pb.c[gix(g, N, j, NX) + lc];
+      double acc[VB];
+#pragma unroll
+      for (int vb = 0; vb < VB; ++vb) acc[vb] = inhom(vb) ? cj : 0.0;
+      if (j >= 1) {
+#pragma unroll 4
+        for (int t = 0; t < NX; ++t) {
+          const double a = Ag[lc * NX + t];
+#pragma unroll
+          for (int vb = 0; vb < VB; ++vb) acc[vb] = fma(a, xv[vb * NX + t], acc[vb]);
+        }
+      }
+      for (int t = 0; t < NU; ++t) {
+        const double b = Bg[lc * NU + t];
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) acc[vb] = fma(b, uval(vb, j, t), acc[vb]);
+      }
       __syncwarp();
       if (lact) {
-        xv[l] = acc;
-        Xc[gix(g, N, j, NX) + l] = acc;
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) {
+          xv[vb * NX + l] = acc[vb];
+          xs[(j * VB + vb) * NX + l] = acc[vb];
+        }
       }
       __syncwarp();
     }
-    if (lact) av[l] = 0.0;
+    if (lact) {
+#pragma unroll
+      for (int vb = 0; vb < VB; ++vb) av[vb * NX + l] = 0.0;
+    }
     __syncwarp();
     for (int j = Nc - 1; j >= 0; --j) {
       const double* Bg = pb.Bm + gix(g, N, j, NX * NU);
       const double* Qg = pb.Qs + gix(g, N, j, NQ);
       const double* Rg = pb.Rs + gix(g, N, j, NR);
-      if (lact) xv[l] = Xc[gix(g, N, j, NX) + l];
-      __syncwarp();
-      double an = 0.0, gu = 0.0;
-      if (!hom) {
-        an = -pb.qref[gix(g, N, j, NX) + lc] - pb.reg_x * Xpv[gix(g, N, j, NX) + lc];
-        if (l < NU) gu = -pb.rref[gix(g, N, j, NU) + l] - pb.reg_u * Upv[gix(g, N, j, NU) + l];
+      if (lact) {
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) xv[vb * NX + l] = xs[(j * VB + vb) * NX + l];
       }
-      for (int t = 0; t < NX; ++t) an += qs_at(Qg, lc, t) * xv[t];
-      if (l < NU)
-        for (int t = 0; t < NU; ++t) gu += rs_at(Rg, l, t) * uval(j, t);
+      __syncwarp();
+      double an[VB], gu[VB];
+      {
+        const double q0 = -pb.qref[gix(g, N, j, NX) + lc] - pb.reg_x * Xpv[gix(g, N, j, NX) + lc];
+        const int la = l < NU ? l : NU - 1;
+        const double r0 = -pb.rref[gix(g, N, j, NU) + la] - pb.reg_u * Upv[gix(g, N, j, NU) + la];
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) {
+          an[vb] = inhom(vb) ? q0 : 0.0;
+          gu[vb] = inhom(vb) ? r0 : 0.0;
+        }
+      }
+#pragma unroll 4
+      for (int t = 0; t < NX; ++t) {
+        const double qv = qs_at(Qg, lc, t);
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) an[vb] = fma(qv, xv[vb * NX + t], an[vb]);
+      }
+      if (l < NU) {
+        for (int t = 0; t < NU; ++t) {
+          const double rv = rs_at(Rg, l, t);
+#pragma unroll
+          for (int vb = 0; vb < VB; ++vb) gu[vb] = fma(rv, uval(vb, j, t), gu[vb]);
+        }
+      }
       if (j == Nc - 1) {
-        double acc = hom ? 0.0 : pcv[lc];
-        for (int t = 0; t < NX; ++t) acc += Pc[t * NX + lc] * xv[t];  // Pc symmetric: row l read as column l
-        if (SLEW)
-          for (int t = 0; t < NU; ++t) acc += Wc[lc * NU + t] * uval(j, t);
-        an += acc;
-        if (SLEW && l < NU) {
-          double a2 = hom ? 0.0 : zc[l];
-          for (int r = 0; r < NX; ++r) a2 += Wc[r * NU + l] * xv[r];
-          for (int t = 0; t < NU; ++t) a2 += Zc[l * NU + t] * uval(j, t);
-          gu += a2;
+        const double pcl = pcv[lc];
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb)
+          if (inhom(vb)) an[vb] += pcl;
+#pragma unroll 4
+        for (int t = 0; t < NX; ++t) {
+          const double pv = Pc[t * NX + lc];  // Pc symmetric: row l read as column l
+#pragma unroll
+          for (int vb = 0; vb < VB; ++vb) an[vb] = fma(pv, xv[vb * NX + t], an[vb]);
+        }
+        if (SLEW) {
+          for (int t = 0; t < NU; ++t) {
+            const double wv = Wc[lc * NU + t];
+#pragma unroll
+            for (int vb = 0; vb < VB; ++vb) an[vb] = fma(wv, uval(vb, j, t), an[vb]);
+          }
+          if (l < NU) {
+            const double zl = zc[l];
+#pragma unroll
+            for (int vb = 0; vb < VB; ++vb)
+              if (inhom(vb)) gu[vb] += zl;
+            for (int r = 0; r < NX; ++r) {
+              const double wv = Wc[r * NU + l];
+#pragma unroll
+              for (int vb = 0; vb < VB; ++vb) gu[vb] = fma(wv, xv[vb * NX + r], gu[vb]);
+            }
+            for (int t = 0; t < NU; ++t) {
+              const double zv = Zc[l * NU + t];
+#pragma unroll
+              for (int vb = 0; vb < VB; ++vb) gu[vb] = fma(zv, uval(vb, j, t), gu[vb]);
+            }
+          }
         }
       } else {
         const double* An = pb.A + gix(g, N, j + 1, NX * NX);
-        for (int r = 0; r < NX; ++r) an += An[r * NX + lc] * av[r];
-        if (SLEW && l < NU) gu += s * (uval(j, l) - uval(j + 1, l));
+#pragma unroll 4
+        for (int r = 0; r < NX; ++r) {
+          const double a = An[r * NX + lc];
+#pragma unroll
+          for (int vb = 0; vb < VB; ++vb) an[vb] = fma(a, av[vb * NX + r], an[vb]);
+        }
+        if (SLEW && l < NU) {
+#pragma unroll
+          for (int vb = 0; vb < VB; ++vb) gu[vb] += s * (uval(vb, j, l) - uval(vb, j + 1, l));
+        }
       }
-      if (SLEW && j >= 1 && l < NU) gu += s * (uval(j, l) - uval(j - 1, l));
+      if (SLEW && j >= 1 && l < NU) {
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) gu[vb] += s * (uval(vb, j, l) - uval(vb, j - 1, l));
+      }
       __syncwarp();
-      if (lact) av[l] = an;
+      if (lact) {
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) av[vb * NX + l] = an[vb];
+      }
       __syncwarp();
       if (l < NU) {
-        double acc = gu;
-        for (int r = 0; r < NX; ++r) acc += Bg[r * NU + l] * av[r];
-        emit(j, acc);
+        for (int r = 0; r < NX; ++r) {
+          const double b = Bg[r * NU + l];
+#pragma unroll
+          for (int vb = 0; vb < VB; ++vb) gu[vb] = fma(b, av[vb * NX + r], gu[vb]);
+        }
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb)
+          if (v0 + vb <= D) emit(v0 + vb, j, gu[vb]);
       }
     }
     __syncwarp();
@@ -699,6 +790,7 @@ struct Wpp {
     };
     if (lact) xv[l] = 0.0;
     if (l < NU) upm[l] = 0.0;
+    fence_proxy_async();  // the ring slots overlay buffers the backward sweep / consensus step wrote with plain stores
     __syncwarp();
     if (l == 0) {
       issue_f(0);
@@ -863,9 +955,8 @@ struct Wpp {
           const size_t g = (size_t)prob * pb.Mpad + i;
           bsweep(g);
           if (Nc >= 1) {
-            for (int v = 0; v <= D; ++v) {
-              const bool hom = v < D;
-              shared_grad(g, hom, v, [&](int j, double val) {
+            for (int v0 = 0; v0 <= D; v0 += VB) {
+              shared_grads(g, v0, [&](int v, int j, double val) {
                 double* dst = wacc + (size_t)v * D + j * NU + lane;
                 *dst = (q == 0) ? val : *dst + val;
               });

@@ -67,6 +67,26 @@ class DeviceSolver:
         assert a.size == self.B * self.M * self.N * r * c, (a.shape, (self.B, self.M, self.N, r, c))
         return f64c(a).reshape(self.B * self.M, self.N, r, c)
 
+    # inputs that are identical for every particle (of every problem) may be given once: ``(N, d)`` / ``(N, r, c)`` for the
+    # whole batch, or one block per problem ``(B, N, ...)``; the device packing kernels expand them (pmpc_set_broadcast)
+    _BC_BITS = dict(Q=0, R=1, X_ref=2, U_ref=3, x_l=4, x_u=5, u_l=6, u_u=7, X_prev=8, U_prev=9)
+
+    def _bcast(self, a, tail, key, masks):
+        """C-contiguous float64 view of input ``key`` and its broadcast level recorded in ``masks = [all, per_problem]``."""
+        if a is None:
+            return None
+        a = f64c(a)
+        per = self.N * int(np.prod(tail))
+        if a.size == self.B * self.M * per:
+            return a.reshape((self.B * self.M, self.N) + tuple(tail))
+        if a.size == per:
+            masks[0] |= 1 << self._BC_BITS[key]
+            return a.reshape((1, self.N) + tuple(tail))
+        if a.size == self.B * per:
+            masks[1] |= 1 << self._BC_BITS[key]
+            return a.reshape((self.B, self.N) + tuple(tail))
+        raise AssertionError((key, a.shape, (self.B, self.M, self.N) + tuple(tail)))
+
     def _per_particle(self, a, d=None):
         if a is None:
             return None
@@ -87,18 +107,30 @@ class DeviceSolver:
                     reg_u=1e-2, slew_reg=None, slew_reg0=None, slew_um1=None):
         n, m = self.n, self.m
         absent = lambda z: z is None or np.size(z) == 0
+        masks = [0, 0]
+        x0 = f64c(np.asarray(x0, float))
+        if x0.size == self.B * n and self.M > 1:  # one initial state per problem: every particle starts there
+            x0 = np.repeat(x0.reshape(self.B, 1, n), self.M, axis=1)
         keep = [  # keep references alive for the duration of the call
-            f64c(np.asarray(x0, float).reshape(self.B * self.M, n)), self._mat(Q, n, n), self._mat(R, m, m),
-            self._vec(X_ref, n), self._vec(U_ref, m),
-            None if absent(x_l) else self._vec(x_l, n), None if absent(x_u) else self._vec(x_u, n),
-            None if absent(u_l) else self._vec(u_l, m), None if absent(u_u) else self._vec(u_u, m),
+            f64c(x0.reshape(self.B * self.M, n)), self._bcast(Q, (n, n), "Q", masks), self._bcast(R, (m, m), "R", masks),
+            self._bcast(X_ref, (n,), "X_ref", masks), self._bcast(U_ref, (m,), "U_ref", masks),
+            None if absent(x_l) else self._bcast(x_l, (n,), "x_l", masks), None if absent(x_u) else self._bcast(x_u, (n,), "x_u", masks),
+            None if absent(u_l) else self._bcast(u_l, (m,), "u_l", masks), None if absent(u_u) else self._bcast(u_u, (m,), "u_u", masks),
         ]
         sl = [self._per_particle(slew_reg), self._per_particle(slew_reg0), self._per_particle(slew_um1, m)]
+        self._masks = masks
+        check(self.lib.pmpc_set_broadcast(self._h, masks[0], masks[1]), "set_broadcast")
         check(self.lib.pmpc_set_problem(self._h, *[dptr(a) for a in keep], float(reg_x), float(reg_u),
                                         *[dptr(a) for a in sl]), "set_problem")
 
     def set_warm_start(self, X_prev=None, U_prev=None):
-        a, b = self._vec(X_prev, self.n), self._vec(U_prev, self.m)
+        masks = list(getattr(self, "_masks", [0, 0]))
+        for k in ("X_prev", "U_prev"):
+            masks[0] &= ~(1 << self._BC_BITS[k])
+            masks[1] &= ~(1 << self._BC_BITS[k])
+        a, b = self._bcast(X_prev, (self.n,), "X_prev", masks), self._bcast(U_prev, (self.m,), "U_prev", masks)
+        self._masks = masks
+        check(self.lib.pmpc_set_broadcast(self._h, masks[0], masks[1]), "set_broadcast")
         check(self.lib.pmpc_set_warm_start(self._h, dptr(a), dptr(b)), "set_warm_start")
 
     def set_dubins(self, p, eps=1e-6):

@@ -289,7 +289,22 @@ def test_particle_sharded_consensus_two_gpus(gpu, tmp_path):
     import sys
 
     if _gpu_count() < 2:
-        pytest.skip("needs 2 GPUs")
+        # one-GPU box: the same exchange between two handles of this process (their kernels are co-resident on the one
+        # device; two PROCESSES would be time-sliced, which a spin-wait exchange cannot live with).  The IPC plumbing
+        # itself needs the second GPU.
+        from pmpc_b200 import parallel
+
+        for (M, N, Nc, box) in [(64, 20, 1, 1.0), (64, 20, 2, 5.0)]:
+            d, p = config_c2(M, N)
+            d["u_l"], d["u_u"] = box * d["u_l"], box * d["u_u"]
+            kw = dict(X_ref=d["X_ref"], U_ref=d["U_ref"], X_prev=d["X_prev"], U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"],
+                      reg_x=d["reg_x"], reg_u=d["reg_u"], max_it=d["max_it"], res_tol=d["res_tol"], Nc=Nc)
+            X, U, infos = parallel.solve_consensus_sharded_local(2, p, d["Q"], d["R"], d["x0"], **kw)
+            X1, U1, data1 = pmpc_b200.solve(DubinsCar(p), d["Q"], d["R"], d["x0"], **dict(kw, Nc=None) if False else
+                                            dict({k: v for k, v in kw.items() if k != "Nc"}, solver_settings=dict(d["solver_settings"], Nc=Nc)))
+            assert all(i["status"] == 0 and i["scp_iters"] == len(data1["hist"]) for i in infos)
+            assert np.all(U[:, :Nc] == U[:1, :Nc]) and np.abs(X - X1).max() < 1e-8 and np.abs(U - U1).max() < 1e-8
+        return
     out = tmp_path / "sharded.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29531", os.path.join(os.path.dirname(__file__), "sharded_worker.py"), str(out)]
