@@ -300,8 +300,8 @@ def test_particle_sharded_consensus_two_gpus(gpu, tmp_path):
             kw = dict(X_ref=d["X_ref"], U_ref=d["U_ref"], X_prev=d["X_prev"], U_prev=d["U_prev"], u_l=d["u_l"], u_u=d["u_u"],
                       reg_x=d["reg_x"], reg_u=d["reg_u"], max_it=d["max_it"], res_tol=d["res_tol"], Nc=Nc)
             X, U, infos = parallel.solve_consensus_sharded_local(2, p, d["Q"], d["R"], d["x0"], **kw)
-            X1, U1, data1 = pmpc_b200.solve(DubinsCar(p), d["Q"], d["R"], d["x0"], **dict(kw, Nc=None) if False else
-                                            dict({k: v for k, v in kw.items() if k != "Nc"}, solver_settings=dict(d["solver_settings"], Nc=Nc)))
+            kw1 = dict({k: v for k, v in kw.items() if k != "Nc"}, solver_settings=dict(d["solver_settings"], Nc=Nc))
+            X1, U1, data1 = pmpc_b200.solve(DubinsCar(p), d["Q"], d["R"], d["x0"], **kw1)
             assert all(i["status"] == 0 and i["scp_iters"] == len(data1["hist"]) for i in infos)
             assert np.all(U[:, :Nc] == U[:1, :Nc]) and np.abs(X - X1).max() < 1e-8 and np.abs(U - U1).max() < 1e-8
         return
