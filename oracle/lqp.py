@@ -97,6 +97,7 @@ def build_lqp(
     slew_reg0=None,
     slew_um1=None,
     Nc=-1,
+    lin_rows=None,
 ) -> LQP:
     f = np.asarray(f, dtype=np.float64)
     M, N, n = f.shape
@@ -200,6 +201,24 @@ def build_lqp(
     else:
         G = sp.csc_matrix((0, nz))
         l, u = np.zeros(0), np.zeros(0)
+    if lin_rows is not None:
+        # general stage-local linear rows  Gu[i,j,k,:] u_{i,j} + Gx[i,j,k,:] x_{i,j} <= h[i,j,k]  (storage stage j: the control
+        # and the state it produces share the index, README.md:232-239) -- what the reference admits as the `l` rows of an
+        # `extra_cstrs` tuple (main.jl:293-316, cone_utils.jl:97-150: G_left z <= h), appended below the box rows
+        Gu, Gx, hh = (np.asarray(a, float) for a in lin_rows)
+        L = hh.shape[-1]
+        Gu, Gx, hh = Gu.reshape(M, N, L, m), Gx.reshape(M, N, L, n), hh.reshape(M, N, L)
+        rr = np.arange(M * N * L).reshape(M, N, L)
+        Gl = sp.coo_matrix(
+            (np.concatenate([Gu.ravel(), Gx.ravel()]),
+             (np.concatenate([np.broadcast_to(rr[..., None], Gu.shape).ravel(), np.broadcast_to(rr[..., None], Gx.shape).ravel()]),
+              np.concatenate([np.broadcast_to(iu[:, :, None, :], Gu.shape).ravel(), np.broadcast_to(ix[:, :, None, :], Gx.shape).ravel()]))),
+            shape=(M * N * L, nz)).tocsc()
+        keep = np.isfinite(hh.ravel())
+        Gl = Gl[np.flatnonzero(keep)]
+        G = sp.vstack([G, Gl], format="csc")
+        l = np.concatenate([l, np.full(int(keep.sum()), -np.inf)])
+        u = np.concatenate([u, hh.ravel()[keep]])
     return LQP(P, q, A, b, G, l, u, M, N, n, m, Nc, iu, ix)
 
 
@@ -241,7 +260,8 @@ def kkt_certificate(prob: LQP, z, nu, mu, iterations=0) -> Certificate:
         # mu > 0 only at the upper bound, mu < 0 only at the lower bound
         bad = np.where(mu > 0, ~at_u, np.where(mu < 0, ~at_l, False))
         dsign = np.abs(mu[bad]).max(initial=0.0) / ms
-        comp = np.abs(np.minimum(np.abs(Gz - u), np.abs(Gz - l)) * mu).max(initial=0.0) / (ms * zs)
+        gap = np.minimum(np.abs(Gz - u), np.abs(Gz - l))
+        comp = np.abs(np.where(mu != 0, gap, 0.0) * mu).max(initial=0.0) / (ms * zs)
     else:
         pbox = dsign = comp = 0.0
     obj = 0.5 * z @ Pz + q @ z
@@ -257,10 +277,7 @@ def solve_exact(prob: LQP, max_iter: int = 200, act0=None):
     """
     P, q, A, b, G, l, u = prob.P, prob.q, prob.A, prob.b, prob.G, prob.l, prob.u
     nz, ne, ni = prob.nz, A.shape[0], G.shape[0]
-    gcol = G.indices if ni else np.zeros(0, dtype=np.int64)  # one unit entry per row, rows in order
-    if ni:
-        Gc = G.tocsr()
-        gcol = Gc.indices
+    Gr = G.tocsr()  # box rows are unit selection rows; `lin_rows` add general ones
     act = np.zeros(ni, dtype=np.int8) if act0 is None else act0.copy()
     z = np.zeros(nz)
     nu = np.zeros(ne)
@@ -269,7 +286,7 @@ def solve_exact(prob: LQP, max_iter: int = 200, act0=None):
     for it in range(1, max_iter + 1):
         idx = np.flatnonzero(act)
         na = idx.size
-        Ga = sp.coo_matrix((np.ones(na), (np.arange(na), gcol[idx])), shape=(na, nz)).tocsc()
+        Ga = Gr[idx].tocsc() if na else sp.csc_matrix((0, nz))
         rhs_a = np.where(act[idx] > 0, u[idx], l[idx])
         # tiny regularisation on the multiplier blocks + iterative refinement (OSQP-polish style)
         delta = 1e-10
@@ -292,7 +309,7 @@ def solve_exact(prob: LQP, max_iter: int = 200, act0=None):
         mu[idx] = sol[nz + ne :]
         if ni == 0:
             break
-        Gz = z[gcol]
+        Gz = Gr @ z
         c = 1.0
         new = np.zeros(ni, dtype=np.int8)
         new[(mu + c * (Gz - u)) > 0] = 1

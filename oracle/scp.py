@@ -25,7 +25,7 @@ from .osqp_port import lqp_solve_osqp as _lqp_osqp
 
 def aff_solve(
     f, fx, fu, x0, X_prev, U_prev, Q, R, X_ref, U_ref, reg_x, reg_u, slew_rate, u_slew,
-    x_l, x_u, u_l, u_u, solver_settings=None, qp="exact", osqp_settings=None,
+    x_l, x_u, u_l, u_u, solver_settings=None, qp="exact", osqp_settings=None, lin_rows=None,
 ):
     """static_backend.py:198-312 semantics on Python-layout arrays; returns (X_traj, U, info)."""
     solver_settings = dict(solver_settings or {})
@@ -46,6 +46,9 @@ def aff_solve(
         Nc=Nc,
     )
     args = (x0, f, fx, fu, X_prev, U_prev, Q, R, X_ref, U_ref)
+    if lin_rows is not None:
+        assert qp == "exact"
+        kw["lin_rows"] = lin_rows
     if qp == "exact":
         X, U, info = _lqp_exact(*args, **kw)
     else:
@@ -78,6 +81,7 @@ def scp_solve(
     solver_settings: Optional[Dict[str, Any]] = None,
     qp: str = "exact",
     osqp_settings=None,
+    lin_rows=None,
 ):
     t0 = time.time()
     x0, reg_x, reg_u = np.array(x0, float), float(reg_x), float(reg_u)
@@ -107,7 +111,7 @@ def scp_solve(
         t1 = time.time()
         X, U, info = aff_solve(
             f, fx, fu, x0, X_prev, U_prev, Q, R, X_ref, U_ref, reg_x, reg_u, slew_rate, u0_slew,
-            x_l, x_u, u_l, u_u, solver_settings, qp=qp, osqp_settings=osqp_settings,
+            x_l, x_u, u_l, u_u, solver_settings, qp=qp, osqp_settings=osqp_settings, lin_rows=lin_rows,
         )
         t1 = time.time() - t1
         if np.isnan(X).any() or np.isnan(U).any():  # :391-394

@@ -1,6 +1,8 @@
 // Kernel entry point and launch helper of the warp-per-particle kernel (wpp.cuh); one translation unit per
 // (NX, NU, SLEW) instantiation (wpp_inst.cu).
 #pragma once
+#include <stdlib.h>
+
 #include "wpp.cuh"
 #include "wpp_plan.h"
 
@@ -26,7 +28,19 @@ cudaError_t wpp_plan(const DevProb& pb, WppPlan* pl) {
   using K = Wpp<NX, NU, SLEW>;
   const int M = pb.M, B = pb.B;
   const int D = (M == 1) ? 0 : pb.D;
-  pl->W = std::min(WppCfg<NX>::WMAX, M);
+  int dev0 = 0, sms0 = 148;
+  cudaGetDevice(&dev0);
+  cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+  // Warps per CTA: a warp's sweep is a dependent chain, and warps that share an SM slow each other down (C5 with 128
+  // particles: 175 ms at 7 warps per SM, 131 ms at 2; C4: 21.9 ms at 8, 18.0 ms at 1-4), so use only as many warps per
+  // CTA as it takes to give every particle of the launch a warp: ceil(B M / SMs), at least 2, at most WMAX.
+  const long long need = ((long long)B * M + sms0 - 1) / sms0;
+  pl->W = (int)std::min<long long>(WppCfg<NX>::WMAX, std::max<long long>(2, need));
+  pl->W = std::min(pl->W, M);
+  if (const char* e = getenv("PMPC_WPP_W")) {  // experiments: warps per CTA (fewer warps = more SMs per problem)
+    const int w = atoi(e);
+    if (w >= 1) pl->W = std::min(pl->W, w);
+  }
   pl->threads = 32 * pl->W;
   pl->smem = ((size_t)pl->W * K::SLAB + K::cred_doubles(pl->W)) * sizeof(double);
   auto kern = wpp_kernel<NX, NU, SLEW>;

@@ -23,6 +23,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from . import lin_cstrs
 from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics
 from .handle import DeviceSolver
 from .static_backend import aff_solve
@@ -263,8 +264,6 @@ def scp_solve(
     the device solver's own settings (``include/pmpc_b200.h: pmpc_settings``)."""
     if cost_fn is not None:
         raise ValueError("cost_fn is deprecated, use lin_cost_fn instead.")
-    if extra_cstrs_fns is not None:
-        raise NotImplementedError("extra_cstrs_fns needs the cone route, which pmpc_b200 does not provide (DESIGN.md)")
     t0 = time.time()
     reg_x, reg_u = float(reg_x), float(reg_u)
     single, dims, Q, R, x0, X_ref, U_ref, X_prev, U_prev, x_l, x_u, u_l, u_u = _normalise(
@@ -279,7 +278,11 @@ def scp_solve(
             return X.reshape(N + 1, xdim), U.reshape(N, udim), data
         return X.reshape(M, N + 1, xdim), U.reshape(M, N, udim), data
 
-    device_ok = (isinstance(f_fx_fu_fn, BuiltinDynamics) and filter_method == "" and lin_cost_fn is None
+    # general stage-local linear rows: static ones through solver_settings["lin_cstrs"] = (Gu, Gx, h), per-iteration ones
+    # through the reference's `extra_cstrs_fns` hook (linear rows only; lin_cstrs.py)
+    static_lin = lin_cstrs.normalise(solver_settings.pop("lin_cstrs", None), M, N, xdim, udim)
+    has_lin = static_lin is not None or extra_cstrs_fns is not None or "extra_cstrs" in solver_settings
+    device_ok = (isinstance(f_fx_fu_fn, BuiltinDynamics) and filter_method == "" and lin_cost_fn is None and not has_lin
                  and not debug and not return_min_viol and time_limit >= 1000.0
                  and not solver_settings.get("host_loop", False))
     if device_ok:
@@ -312,10 +315,25 @@ def scp_solve(
                         U_ref=U_ref)
         X_ref_, U_ref_ = _augment_cost(lin_cost_fn, X_prev, U_prev, Q, R, X_ref, U_ref, problems)
         solver_settings["solver_state"] = solver_state
+        lin = static_lin
+        if extra_cstrs_fns is not None:  # scp_mpc.py:353-354 calls it; README.md:217 says "a list of functions": both work
+            fns = extra_cstrs_fns if isinstance(extra_cstrs_fns, (list, tuple)) else [extra_cstrs_fns]
+            solver_settings["extra_cstrs"] = tuple(c for fn in fns for c in fn(X_prev, U_prev, problems))
+        if "extra_cstrs" in solver_settings:
+            dyn = lin_cstrs.from_extra_cstrs(solver_settings["extra_cstrs"], M, N, xdim, udim, solver_settings.get("Nc", -1))
+            lin = dyn if lin is None else tuple(np.concatenate([a, b], 2) for a, b in zip(lin, dyn))
 
         t_aff = time.time()
-        X, U, solver_data = aff_solve(f, fx, fu, x0, X_prev, U_prev, Q, R, X_ref_, U_ref_, reg_x, reg_u, slew_rate,
-                                      u0_slew, x_l, x_u, u_l, u_u, solver_settings=solver_settings)
+        if lin is None:
+            X, U, solver_data = aff_solve(f, fx, fu, x0, X_prev, U_prev, Q, R, X_ref_, U_ref_, reg_x, reg_u, slew_rate,
+                                          u0_slew, x_l, x_u, u_l, u_u, solver_settings=solver_settings)
+        else:  # the row values ride along as extra states whose box is the constraint (lin_cstrs.py)
+            fa, fxa, fua, x0a, Xpa, Qa, Xra, xla, xua = lin_cstrs.augment(lin, f, fx, fu, x0, X_prev, U_prev, Q, R, X_ref_,
+                                                                          reg_x, x_l, x_u)
+            ss = {k: v for k, v in solver_settings.items() if k not in ("extra_cstrs", "lin_cstrs")}
+            Xa, U, solver_data = aff_solve(fa, fxa, fua, x0a, Xpa, U_prev, Qa, R, Xra, U_ref_, reg_x, reg_u, slew_rate,
+                                           u0_slew, xla, xua, u_l, u_u, solver_settings=ss)
+            X = Xa[..., :xdim]
         t_aff = time.time() - t_aff
         solver_state = solver_data.get("solver_state", None)
         X, U = X.reshape((M, N + 1, xdim)), U.reshape((M, N, udim))

@@ -6,7 +6,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..")); sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import pmpc_b200
 from pmpc_b200 import LTV
-from fixtures import config_c4, config_c5, config_ltv
+from fixtures import config_c4, config_c5, config_ltv  # noqa
 
 which = sys.argv[1:] or ["small", "c4", "c5r"]
 
@@ -63,3 +63,19 @@ if "c5r" in which:
 if "c5" in which:
     d, A, Bm = config_c5()
     report("C5 full", d, A, Bm, old=False, reps=2)
+if "c4lin" in which:
+    # BASELINE config 4 as specified: with n_lin = 8 random linear rows per (particle, stage) (host loop, rows as extra states)
+    M4, N4 = int(os.environ.get("C4_M", 64)), int(os.environ.get("C4_N", 100))
+    d, A, Bm = config_c4(M=M4, N=N4, n_lin=8)
+    fn = LTV(A, Bm)
+    t = time.perf_counter()
+    X, U, data = pmpc_b200.solve(fn, **d)
+    t = time.perf_counter() - t
+    Gu, Gx, h = d["solver_settings"]["lin_cstrs"]
+    val = np.einsum("ijka,ija->ijk", Gu, U) + np.einsum("ijkr,ijr->ijk", Gx, X[:, 1:])
+    f = np.einsum("mjrt,mjt->mjr", A, X[:, :-1]) + np.einsum("mjrt,mjt->mjr", Bm, U)
+    print(json.dumps(dict(case="C4 M=%d N=%d with n_lin=8" % (M4, N4), wall_s=t, its=len(data["hist"]), resid=data["hist"][-1]["resid"],
+                          obj=data["hist"][-1]["obj"], t_aff_solve_mean=float(np.mean(data["t_aff_solve"])),
+                          row_violation=float((val - h).max()), active_rows=int(np.sum(val >= h - 1e-7)),
+                          dyn=float(np.abs(f - X[:, 1:]).max()), consensus=bool(np.all(U[:, :1] == U[:1, :1])),
+                          umax=float(np.abs(U).max()))), flush=True)

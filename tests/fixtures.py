@@ -98,8 +98,25 @@ def config_ltv(seed, M, N, n, m, Nc, xbox=True):
     return d, A, Bm
 
 
-def config_c4(M=64, N=100):
-    return config_ltv(3, M, N, 12, 4, 1, xbox=True)
+def config_c4(M=64, N=100, n_lin=0):
+    """C4 (seed 3): 12-state / 4-input LTV, slew, control and state boxes, Nc = 1; with ``n_lin`` > 0 also SURVEY 8(d)'s
+    ``n_lin`` random linear rows g_k'[u; x] <= h_k per (particle, stage) (BASELINE: "box/linear constraints"), returned in
+    ``solver_settings["lin_cstrs"] = (Gu, Gx, h)``.  h_k = 0.5 + |g_k'[0; x~]| with x~ the uncontrolled response, so the
+    rows hold with margin at u = 0 (the problem is feasible) and bind once the optimal controls push against them."""
+    d, A, Bm = config_ltv(3, M, N, 12, 4, 1, xbox=True)
+    if n_lin > 0:
+        rng = np.random.default_rng(33)
+        n, m = 12, 4
+        Gu = rng.standard_normal((M, N, n_lin, m)) / np.sqrt(n + m)
+        Gx = rng.standard_normal((M, N, n_lin, n)) / np.sqrt(n + m)
+        xt = np.empty((M, N, n))
+        x = d["x0"].copy()
+        for j in range(N):
+            x = np.einsum("mrt,mt->mr", A[:, j], x)
+            xt[:, j] = x
+        h = 0.5 + np.abs(np.einsum("mjkr,mjr->mjk", Gx, xt))
+        d["solver_settings"] = dict(d["solver_settings"], lin_cstrs=(Gu, Gx, h))
+    return d, A, Bm
 
 
 def config_c5(M=1024, N=200):

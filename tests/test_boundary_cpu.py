@@ -257,3 +257,38 @@ def test_remote_shim_keeps_the_client_surface():
     seen = {}
     remote.solve_problem(dict(f_fx_fu_fn="f", Q="Q", R="R", x0="x0", max_it=3), solve_fn=lambda *a, **k: seen.update(a=a, k=k))
     assert seen["a"] == ("f", "Q", "R", "x0") and seen["k"] == dict(max_it=3, verbose=True)
+
+
+def test_linear_rows_as_extra_states_equal_direct_rows():
+    """pmpc_b200/lin_cstrs.py (host logic, no GPU): the reference's `extra_cstrs` tuples are parsed into stage-local rows,
+    and the sub-problem augmented with the row values as extra states (whose box is the constraint) has the same minimiser
+    as the QP with the rows taken directly into G — both solved by the CPU oracle."""
+    from fixtures import rand_problem
+    from oracle import lqp
+    from pmpc_b200 import lin_cstrs
+
+    rng = np.random.default_rng(30)
+    M, N, n, m, L = 3, 6, 4, 2, 2
+    args, kw = rand_problem(rng, M, N, n, m, True, 0.5, per_particle_slew=False)
+    x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur = args
+    Xf, Uf, _ = lqp.lqp_solve(*args, Nc=1, **kw)
+    Gu, Gx = rng.standard_normal((M, N, L, m)), rng.standard_normal((M, N, L, n))
+    val = np.einsum("ijka,ija->ijk", Gu, Uf) + np.einsum("ijkr,ijr->ijk", Gx, Xf)
+    h = np.where(rng.random(val.shape) < 0.15, val - 0.1 * np.abs(val), val + 1.0)
+    Xd, Ud, info = lqp.lqp_solve(*args, Nc=1, lin_rows=(Gu, Gx, h), **kw)
+    assert np.sum(np.abs(np.einsum("ijka,ija->ijk", Gu, Ud) + np.einsum("ijkr,ijr->ijk", Gx, Xd) - h) < 1e-8) >= 3
+    fa, fxa, fua, x0a, Xpa, Qa, Xra, xla, xua = lin_cstrs.augment((Gu, Gx, h), f, fx, fu, x0, Xp, Up, Q, R, Xr, kw["reg_x"], None, None)
+    Xa, Ua, _ = lqp.lqp_solve(x0a, fa, fxa, fua, Xpa, Up, Qa, R, Xra, Ur, Nc=1, **dict(kw, lx=xla, ux=xua))
+    assert np.abs(Xa[..., :n] - Xd).max() < 1e-10 and np.abs(Ua - Ud).max() < 1e-10 and np.abs(Xd - Xf).max() > 1e-2
+    # reference tuple format, one particle: z = [u_1 .. u_N ; x_1 .. x_N] (README.md:232-235)
+    N1, nz = 5, 5 * m + 5 * n
+    G = np.zeros((2, nz))
+    G[0, 2 * m:3 * m], G[0, N1 * m + 2 * n:N1 * m + 3 * n] = [1.0, -2.0], [0.5, 0.0, 0.0, 3.0]   # stage 2
+    G[1, N1 * m + 4 * n + 1] = 7.0                                                                 # stage 4, state only
+    Gu1, Gx1, h1 = lin_cstrs.from_extra_cstrs([(2, [], 0, G, np.zeros((2, 0)), np.array([0.3, 0.9]), np.zeros(nz), np.zeros(0))],
+                                              1, N1, n, m, -1)
+    assert Gu1.shape == (1, N1, 1, m) and np.array_equal(Gu1[0, 2, 0], [1.0, -2.0]) and Gx1[0, 2, 0, 3] == 3.0
+    assert Gx1[0, 4, 0, 1] == 7.0 and h1[0, 2, 0] == 0.3 and h1[0, 4, 0] == 0.9 and np.isinf(h1[0, 0, 0])
+    G[1, 0] = 1.0  # now row 1 couples stage 0's control with stage 4's state
+    with pytest.raises(NotImplementedError, match="stage-local"):
+        lin_cstrs.from_extra_cstrs([(2, [], 0, G, np.zeros((2, 0)), np.zeros(2), np.zeros(nz), np.zeros(0))], 1, N1, n, m, -1)
