@@ -244,3 +244,34 @@ def test_c_oracle_batch_threads_equal_serial():
         X, U, h = cport.scp_dubins(p[b], d["Q"][b], d["R"][b], d["x0"][b], d["X_ref"][b], d["U_ref"][b], d["X_prev"][b],
                                    d["U_prev"][b], d["u_l"][b], d["u_u"][b], max_it=30, res_tol=1e-6, Nc=1, osqp_settings=st)
         assert its[b] == len(h) and np.array_equal(X, Xb[b]) and np.array_equal(U, Ub[b])
+
+
+def test_exact_qp_oracle_against_scipy_trust_constr():
+    """The exact QP oracle (own primal-dual active-set solve + KKT certificate) cross-checked by an INDEPENDENT third-party
+    solver on the same assembled matrices: SciPy's trust-constr interior-point method on  min 1/2 z'Pz + q'z,  A z = b,
+    l <= G z <= u  (consensus, slew, u_{-1} term, control and state boxes, general linear rows).  Not the reference's
+    solver stack (Julia / OSQP cannot run here), but a solver this repository did not write."""
+    from scipy.optimize import Bounds, LinearConstraint, minimize
+
+    from fixtures import rand_problem
+
+    rng = np.random.default_rng(70)
+    M, N, n, m, Nc = 2, 5, 3, 2, 1
+    args, kw = rand_problem(rng, M, N, n, m, True, 0.6, per_particle_slew=False)
+    Xf, Uf, _ = lqp.lqp_solve(*args, Nc=Nc, **kw)
+    xb = 0.9 * np.abs(Xf[:, N - 2:]).max()
+    lx, ux = -1e3 * np.ones((M, N, n)), 1e3 * np.ones((M, N, n))
+    lx[:, N - 2:], ux[:, N - 2:] = -xb, xb
+    Gu, Gx = rng.standard_normal((M, N, 1, m)), rng.standard_normal((M, N, 1, n))
+    val = np.einsum("ijka,ija->ijk", Gu, Uf) + np.einsum("ijkr,ijr->ijk", Gx, Xf)
+    h = val + np.where(rng.random(val.shape) < 0.3, -0.05 * (0.2 + np.abs(val)), 1.0)
+    X, U, info = lqp.lqp_solve(*args, Nc=Nc, lx=lx, ux=ux, lin_rows=(Gu, Gx, h), **kw)
+    prob = info["prob"]
+    P, q, A, b, G = prob.P.toarray(), prob.q, prob.A.toarray(), prob.b, prob.G.toarray()
+    cons = [LinearConstraint(A, b, b), LinearConstraint(G, prob.l, prob.u)]
+    res = minimize(lambda z: 0.5 * z @ P @ z + q @ z, np.zeros(prob.nz), jac=lambda z: P @ z + q, hess=lambda z: P,
+                   constraints=cons, method="trust-constr", options=dict(gtol=1e-12, xtol=1e-14, barrier_tol=1e-12, maxiter=3000))
+    assert np.abs(A @ res.x - b).max() < 1e-8
+    assert abs(res.fun - info["cert"].objective) <= 1e-7 * max(1.0, abs(info["cert"].objective))
+    assert np.abs(res.x - info["z"]).max() <= 1e-5 * max(1.0, np.abs(info["z"]).max())
+    assert np.sum(np.abs(prob.G @ info["z"] - prob.u) < 1e-9) + np.sum(np.abs(prob.G @ info["z"] - prob.l) < 1e-9) >= 3  # active rows
