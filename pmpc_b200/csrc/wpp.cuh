@@ -68,13 +68,17 @@ struct Wpp {
   static constexpr int O_V = O_Q + NQ;                // vectors: c, wv (pc), x, a / dx              (4 x NX)
   static constexpr int O_M = O_V + 4 * NX;            // H, E, Z (Zc)                                (3 x NU x NU)
   static constexpr int O_U = O_M + 3 * NU * NU;       // h0, h, kv, ufix, z (zc) | u, up, du         (5 x NU)
-  static constexpr int O_BAR = O_U + 6 * NU;          // mbarriers: A, Q, B (bsweep) / slot 0, slot 1, Q (fsweep)
-  static constexpr int SLAB = O_BAR + 6;
+  static constexpr int O_BAR = O_U + 6 * NU;          // mbarriers: A, Q, B, A' (bsweep) / slot 0, slot 1, Q (fsweep)
+  // small shapes: a second A buffer, so that A of stage j - 1 is requested a whole stage ahead (the stage of an n = 12
+  // problem is shorter than an HBM round trip; at n = 32 the first half of the stage covers it and the slab has no room)
+  static constexpr bool A2 = (NX <= 16);
+  static constexpr int O_A2 = O_BAR + 8;
+  static constexpr int SLAB = O_A2 + (A2 ? NX * NX : 0);
   static_assert(NX % 2 == 0 && NQ % 2 == 0 && NR % 2 == 0 && NH % 2 == 0 && SLAB % 2 == 0, "16-byte alignment of the sub-buffers");
   static constexpr int V_C = 0, V_WV = NX, V_X = 2 * NX, V_AD = 3 * NX, V_DX = 3 * NX;
   static constexpr int MM_H = 0, MM_E = NU * NU, MM_Z = 2 * NU * NU;
   static constexpr int U_H0 = 0, U_H = NU, U_KV = 2 * NU, U_UF = 3 * NU, U_Z = 4 * NU, U_U = 0, U_UP = NU, U_DU = 2 * NU;
-  enum { BAR_A = 0, BAR_Q = 1, BAR_B = 2, BAR_S0 = 3, BAR_S1 = 4, BAR_FQ = 5 };
+  enum { BAR_A = 0, BAR_Q = 1, BAR_B = 2, BAR_S0 = 3, BAR_S1 = 4, BAR_FQ = 5, BAR_A2 = 6, NBAR = 7 };
   static constexpr int DMAX = 64;  // largest shared block (Nc * NU) this kernel takes; beyond it the old kernel runs
 
   // ------------------------------------------------------------------------------------------------------------
@@ -265,7 +269,7 @@ struct Wpp {
   // ------------------------------------------------------------------------------------------------------------
   // bulk-async staging (tma.cuh): lane 0 arms the warp's mbarrier with the byte count and issues the copies; every
   // lane waits on the barrier's phase.  ph[b] counts the completed uses of barrier b (uniform over the warp).
-  unsigned phA, phQ, phB, phS0, phS1, phFQ;
+  unsigned phA, phQ, phB, phS0, phS1, phFQ, phA2;
   __device__ __forceinline__ uint64_t* bar(int b) const { return reinterpret_cast<uint64_t*>(slab() + O_BAR) + b; }
   __device__ __forceinline__ void bar_wait(int b, unsigned& ph) {
     mbar_wait(bar(b), ph & 1u);
@@ -273,10 +277,10 @@ struct Wpp {
   }
   __device__ __forceinline__ void stage_init() {
     if (lane == 0) {
-      for (int b = 0; b < 6; ++b) mbar_init(bar(b), 1);
+      for (int b = 0; b < NBAR; ++b) mbar_init(bar(b), 1);
       fence_mbar_init();
     }
-    phA = phQ = phB = phS0 = phS1 = phFQ = 0;
+    phA = phQ = phB = phS0 = phS1 = phFQ = phA2 = 0;
     __syncwarp();
   }
 
@@ -286,8 +290,17 @@ struct Wpp {
   // the slab: Pc in O_S, Wc in O_W, Zc in MM_Z, pc in V_WV, zc in U_Z.
   __device__ __forceinline__ void bsweep(size_t g) {
     double* sl = slab();
-    double *Sm = sl + O_S, *Am = sl + O_A, *Bm = sl + O_B, *SBWm = sl + O_SBW, *Wm = sl + O_W, *Gm = sl + O_G, *Qb = sl + O_Q;
+    double *Sm = sl + O_S, *Bm = sl + O_B, *SBWm = sl + O_SBW, *Wm = sl + O_W, *Gm = sl + O_G, *Qb = sl + O_Q;
     double *cv = sl + O_V + V_C, *wvv = sl + O_V + V_WV;
+    // pairs (a, b), a <= b, of the packed m x m matrices this lane assembles / stores (constant over the sweep)
+    int pa[(NR + 31) / 32], pbb[(NR + 31) / 32];
+#pragma unroll
+    for (int kk = 0; kk < (NR + 31) / 32; ++kk) {
+      int a = 0, rem = lane + 32 * kk;
+      while (a < NU - 1 && rem >= NU - a) { rem -= NU - a; ++a; }
+      pa[kk] = a;
+      pbb[kk] = (a + rem < NU) ? a + rem : NU - 1;
+    }
     double *Hm = sl + O_M + MM_H, *Em = sl + O_M + MM_E, *Zm = sl + O_M + MM_Z;
     double *h0m = sl + O_U + U_H0, *hm = sl + O_U + U_H, *kvm = sl + O_U + U_KV, *ufm = sl + O_U + U_UF, *zm = sl + O_U + U_Z;
     const int l = lane;
@@ -341,18 +354,28 @@ struct Wpp {
     };
     fence_proxy_async();  // plain stores of the previous phase into buffers the bulk copies are about to overwrite
     __syncwarp();
+    // A of stage j goes to buffer (j & 1) when there are two (A2), tracked by its own barrier
+    auto issue_a = [&](int j) {
+      const bool odd = A2 && (j & 1);
+      uint64_t* b = bar(odd ? BAR_A2 : BAR_A);
+      mbar_expect_tx(b, NX * NX * 8);
+      bulk_g2s(sl + (odd ? O_A2 : O_A), pb.A + gix(g, N, j, NX * NX), NX * NX * 8, b);
+    };
     if (l == 0) {
       issue_q(N - 1);
       issue_b(N - 1);
+      if (A2 && N - 1 >= 1) issue_a(N - 1);
     }
     Vec vn = load_vec(N - 1);
     for (int j = N - 1; j >= Nc; --j) {
       const Vec vc = vn;
       if (j - 1 >= Nc) vn = load_vec(j - 1);
-      // ---- P0: A of this stage is needed in the second half only: start its copy now
-      if (l == 0 && j >= 1) {
-        mbar_expect_tx(bar(BAR_A), NX * NX * 8);
-        bulk_g2s(Am, pb.A + gix(g, N, j, NX * NX), NX * NX * 8, bar(BAR_A));
+      const double* Am = sl + ((A2 && (j & 1)) ? O_A2 : O_A);
+      // ---- P0: A is needed in the second half of the stage only.  One buffer: start the copy of this stage's A now;
+      // two buffers: this stage's A was requested a stage ago, request the next one's
+      if (l == 0) {
+        if (!A2 && j >= 1) issue_a(j);
+        if (A2 && j - 1 >= Nc && j - 1 >= 1) issue_a(j - 1);
       }
       bar_wait(BAR_Q, phQ);
       double Rp[(NR + 31) / 32];
@@ -397,9 +420,7 @@ struct Wpp {
       for (int kk = 0; kk < (NR + 31) / 32; ++kk) {
         const int pi = l + 32 * kk;
         if (pi < NR) {
-          int a = 0, rem = pi;
-          while (rem >= NU - a) { rem -= NU - a; ++a; }
-          const int b = a + rem;
+          const int a = pa[kk], b = pbb[kk];
           double acc = Rp[kk];
           if (SLEW) {
             acc += Zm[a * NU + b];
@@ -426,11 +447,8 @@ struct Wpp {
       for (int kk = 0; kk < (NR + 31) / 32; ++kk) {
         const int pi = l + 32 * kk;
         if (pi < NR) {
-          int a = 0, rem = pi;
-          while (rem >= NU - a) { rem -= NU - a; ++a; }
-          const int b = a + rem;
-          Hm[a * NU + b] = Rp[kk];
-          Hm[b * NU + a] = Rp[kk];
+          Hm[pa[kk] * NU + pbb[kk]] = Rp[kk];
+          Hm[pbb[kk] * NU + pa[kk]] = Rp[kk];
         }
       }
       if (l < NU) h0m[l] = h0;
@@ -455,7 +473,8 @@ struct Wpp {
 #pragma unroll
       for (int a = 0; a < NU; ++a) { Kc[a] = 0.0; Gc[a] = 0.0; }
       if (j >= 1) {
-        bar_wait(BAR_A, phA);
+        if (A2 && (j & 1)) bar_wait(BAR_A2, phA2);
+        else bar_wait(BAR_A, phA);
         // ---- P4: column l of G = (S B + W)' A, K = -E G, p' = A' wv + G' k, S A
         double pn = 0.0;
         double SAc[NX];
@@ -526,20 +545,13 @@ struct Wpp {
           for (int a = 0; a < NU; ++a) hg[H_K + a * NX + l] = ((fmask >> a) & 1u) ? Gc[a] : Kc[a];
         }
         if (l < NU) hg[H_KF + l] = ((fmask >> l) & 1u) ? hm[l] : kvm[l];
-        if (pb.has_ubox) {
-          for (int pi = l; pi < NHO; pi += 32) {
-            int a = 0, rem = pi;
-            while (rem >= NU - 1 - a) { rem -= NU - 1 - a; ++a; }
-            const int b = a + 1 + rem;
-            hg[H_H + pi] = Hm[a * NU + b];
-          }
-        }
-        if (SLEW) {
-          double* Eg = F.E + gix(g, N, j, NR);
-          for (int pi = l; pi < NR; pi += 32) {
-            int a = 0, rem = pi;
-            while (rem >= NU - a) { rem -= NU - a; ++a; }
-            Eg[pi] = Em[a * NU + a + rem];
+#pragma unroll
+        for (int kk = 0; kk < (NR + 31) / 32; ++kk) {
+          const int pi = l + 32 * kk;
+          if (pi < NR) {
+            const int a = pa[kk], b = pbb[kk];
+            if (pb.has_ubox && a < b) hg[H_H + pko(a, b)] = Hm[a * NU + b];
+            if (SLEW) F.E[gix(g, N, j, NR) + pi] = Em[a * NU + b];
           }
         }
       }

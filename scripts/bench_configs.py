@@ -23,9 +23,7 @@ if "c1" in which:
     d, p = config_c1()
     kw = {k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in d.items()}
     car = DubinsCar(p[0])
-    X, U, data = pmpc_b200.solve(car, **kw)
-    kw["solver_settings"] = dict(kw["solver_settings"], _device_solver=data["device_solver"])
-    t, (X, U, data) = timed(lambda: pmpc_b200.solve(car, **kw), 50)
+    t, (X, U, data) = timed(lambda: pmpc_b200.solve(car, **kw), 50)  # plain calls: handles are cached inside solve
     print(json.dumps(dict(config="C1 Dubins N=20 M=1, 10 SCP iterations", p50_ms=1e3 * t, kernel_ms=data["device"]["kernel_ms"],
                           scp_iters=len(data["hist"]), solves_per_s=1.0 / t)), flush=True)
 
@@ -48,20 +46,31 @@ if "c3" in which:
                           scp_iters=[int(info["scp_iters"].min()), float(info["scp_iters"].mean()), int(info["scp_iters"].max())],
                           status_ok=bool((info["status"] == 0).all()), consensus=bool(np.all(U[:, :, 0] == U[:, :1, 0])))), flush=True)
 
+def fp64_peak():
+    import ctypes as C
+    from pmpc_b200 import _lib
+    r = C.c_double()
+    return r.value if _lib.load().pmpc_microbench(0, 1, C.byref(r)) == 0 else float("nan")
+
+
 for name, cfg, label in (("c4", config_c4, "C4 LTV n=12 m=4 N=100 M=64 Nc=1, slew, u and x boxes"),
                          ("c5", config_c5, "C5 LTV n=32 m=8 N=200 M=1024 Nc=5, slew, u box (one GPU)")):
     if name not in which:
         continue
     d, A, Bm = cfg()
     fn = LTV(A, Bm)
-    X, U, data = pmpc_b200.solve(fn, **d)
-    d["solver_settings"] = dict(d["solver_settings"], _device_solver=data["device_solver"])
-    t, (X, U, data) = timed(lambda: pmpc_b200.solve(fn, **d), 3 if name == "c4" else 1)
+    t, (X, U, data) = timed(lambda: pmpc_b200.solve(fn, **d), 3 if name == "c4" else 2)
     dev = data["device"]
     M, N = U.shape[:2]
+    n, m = A.shape[-1], Bm.shape[-1]
     Nc = d["solver_settings"]["Nc"]
     f = np.einsum("mjrt,mjt->mjr", A, X[:, :-1]) + np.einsum("mjrt,mjt->mjr", Bm, U)
+    # flops = M N [F (4n^3 + 6n^2 m + 4n m^2 + m^3/3) + I (6n^2 + 8nm + 2m^2)], F = I = active-set passes here
+    flops = M * N * dev["polish_passes"] * ((4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0) + (6 * n * n + 8 * n * m + 2 * m * m))
+    peak = fp64_peak()
     print(json.dumps(dict(config=label, p50_s=t, kernel_ms=dev["kernel_ms"], scp_iters=len(data["hist"]), resid=data["hist"][-1]["resid"],
                           status=dev["status"], admm_iters=dev["admm_iters"], factorizations=dev["factorizations"], polish=dev["polish_passes"],
                           dyn_violation=float(np.abs(f - X[:, 1:]).max()), consensus=bool(np.all(U[:, :Nc] == U[:1, :Nc])),
-                          u_in_box=bool(np.abs(U).max() <= 1 + 1e-9), kkt=max(sd["kkt"] for sd in data["solver_data"]))), flush=True)
+                          u_in_box=bool(np.abs(U).max() <= 1 + 1e-9), kkt=max(sd["kkt"] for sd in data["solver_data"]),
+                          roofline=dict(bound="fp64", flops_survey_8d=flops, achieved_tflops=flops / (dev["kernel_ms"] * 1e-3) / 1e12,
+                                        peak_tflops_measured_here=peak, frac=flops / (dev["kernel_ms"] * 1e-3) / 1e12 / peak))), flush=True)
