@@ -261,7 +261,7 @@ def main():
                     help="independent C2 problems per GPU per step (0 = --waves full waves: SMs x resident CTAs per SM x waves)")
     ap.add_argument("--waves", type=int, default=8)
     ap.add_argument("--latency-solves", type=int, default=200)
-    ap.add_argument("--e2e-chunks", type=int, default=16, help="sub-batches of the pipelined end-to-end leg (1 = no pipelining; default = half a wave each: kernels of consecutive sub-batches co-reside)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="sub-batches of the pipelined end-to-end leg (1 = no pipelining; 0 = one sub-batch per full wave of the solve kernel, at most 16: each costs a handle's worth of host work)")
     ap.add_argument("--cpu-sample-its", type=int, default=16)
     ap.add_argument("--ref-sample-its", type=int, default=16,
                     help="SCP iterations every host thread runs per step in the reference arm (62 = whole solves; early iterations "
@@ -384,6 +384,8 @@ def main():
 
     # ---- end to end through the public API with host buffers ---------------------------------------
     ua = {k: pmpc_b200.pinned_copy(v) for k, v in untiled(arrs).items()}
+    if args.e2e_chunks <= 0:
+        args.e2e_chunks = int(max(1, min(16, B // max(1, occ[0] * occ[1]))))
 
     def e2e_step(solver):
         return pmpc_b200.solve_batch(p, ua["Q"], ua["R"], ua["x0"], ua["X_ref"], ua["U_ref"], ua["X_prev"],
