@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -425,7 +426,9 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   pb.Nc = (M == 1) ? 0 : (int)Nc;  // one particle: consensus is vacuous (the Nc==0 quirk is applied at pack time)
   pb.D = pb.Nc * sh.NU;
   pb.tile = (sh.NX >= 8) ? 1 : 32;  // == Solver<NX, NU>::TILE
-  pb.Mpad = (M == 1 || pb.tile == 1) ? (int)M : (int)(((M + 31) / 32) * 32);
+  // 2 <= M <= 16 particles: two problems share a 32-slot tile (the two-problems-per-warp kernel, kind 3; the
+  // one-problem-per-warp kernels read the same layout: their mirror lanes stay inside the problem's own 16 slots)
+  pb.Mpad = (M == 1 || pb.tile == 1) ? (int)M : ((M <= 16) ? 16 : (int)(((M + 31) / 32) * 32));
   pb.P = (int)((((size_t)B * pb.Mpad + 31) / 32) * 32);
   pb.hist_len = 128;
   pb.rank = 0; pb.world = 1; pb.M_total = (int)M; pb.comm_cap = 0; pb.seq0 = 0;
@@ -799,12 +802,19 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
   int var = 0;
   if (NX == 4 && NU == 2 && pb.dyn_kind == DYN_DUBINS) var |= 1;
   if (NX <= 4 && !pb.has_slew) var |= 2;
-  launch_fn fn = nullptr;
-  for (const VariantEntry& v : kVariants)
+  launch_fn fn = nullptr, fn_half = nullptr;
+  for (const VariantEntry& v : kVariants) {
     if (v.nx == NX && v.nu == NU && v.kind == kind && v.var == var) fn = v.fn;
+    if (v.nx == NX && v.nu == NU && v.kind == 3 && v.var == var) fn_half = v.fn;
+  }
   if (!fn) return fail(PMPC_ERR_UNSUPPORTED, "no kernel for this shape");
+  // two problems per warp: M <= 16 particles in the 16-slot layout, fused active-set passes only (no state box, one
+  // GPU); what it cannot finish is continued by the one-problem-per-warp kernel launched behind it in resume mode
+  const bool half = fn_half && pb.M >= 2 && pb.M <= 16 && pb.Mpad == 16 && pb.fused && pb.polish && !pb.has_xbox &&
+                    pb.world <= 1 && !getenv("PMPC_NO_HALF");
   if (occ_out) {
-    cudaError_t e = fn(pb, blocks, threads, h->stream, occ_out);
+    cudaError_t e = half ? fn_half(pb, (pb.B + 1) / 2, 32, h->stream, occ_out) : fn(pb, blocks, threads, h->stream, occ_out);
+    if (half) *occ_out *= 2;  // problems per SM
     return e == cudaSuccess ? PMPC_OK : fail(PMPC_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
   }
   if (pb.world > 1 && kind == 0) return fail(PMPC_ERR_UNSUPPORTED, "particle sharding needs at least 2 particles per rank");
@@ -858,6 +868,12 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
     next_window();
     e = we->launch(h->pb, pl, h->stream);
     if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("warp-per-particle kernel launch: ") + cudaGetErrorString(e));
+    ++g_launches;
+    h->pb.resume = 1;
+  }
+  if (half) {
+    cudaError_t e = fn_half(h->pb, (pb.B + 1) / 2, 32, h->stream, nullptr);
+    if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch (two problems per warp): ") + cudaGetErrorString(e));
     ++g_launches;
     h->pb.resume = 1;
   }

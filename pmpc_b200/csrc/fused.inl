@@ -56,7 +56,7 @@
   __device__ __forceinline__ Sm smem_view(const DevProb& pb, unsigned char* smem) const {
     double* base = reinterpret_cast<double*>(smem);
     Sm v;
-    v.tab = has_tab ? base : nullptr;
+    v.tab = has_tab ? base + ((PPW == 2) ? (tid >> 4) * (pb.tab_doubles / 2) : 0) : nullptr;
     v.ring = pb.ring ? base + pb.tab_doubles + (size_t)wid * DEPTH * SLOT : nullptr;
     v.bars = pb.ring ? reinterpret_cast<uint64_t*>(base + pb.tab_doubles + (size_t)(T >> 5) * DEPTH * SLOT) + wid * DEPTH : nullptr;
     return v;
@@ -97,10 +97,11 @@
         fence_mbar_init();
       }
     }
+    if (PPW == 2) tb = base + (tid >> 4) * (pb.tab_doubles / 2);  // one table per half-warp problem
     if (GROUPED && pb.tab_doubles > 0 && pb.uniform[prob]) {
       // particle 0 of the problem speaks for all (checked on the device by uniform_check_kernel)
       const size_t g0 = (size_t)prob * pb.Mpad;
-      for (int idx = tid; idx < N * TW; idx += T) {
+      for (int idx = (PPW == 2 ? hl : tid); idx < N * TW; idx += (PPW == 2 ? 16 : T)) {
         const int j = idx / TW, k = idx % TW;
         double v;
         if (k < T_RS) v = pb.Qs[ixg(j, NQ, k - T_QS, g0)];
@@ -1191,7 +1192,7 @@
       for (int k = 0; k < Dn; ++k) act[k] = nact[k];
       if (ch == 0.0) break;
     }
-    if (tid == 0) {  // every thread holds the same values; the forward sweep and later passes read them from HBM
+    if (hl == 0 && pvalid && (PPW == 1 || wr_en)) {  // every thread holds the same values; the forward sweep and later passes read them from HBM
       for (int a = 0; a < Dn; ++a) {
         pb.uc[(size_t)prob * Dn + a] = ucv[a];
         pb.gc[(size_t)prob * Dn + a] = gcv[a];
@@ -1385,6 +1386,59 @@
         tries = 0;  // (the loop increment makes the next pass a "not first" one: same linearisation point)
       }
     }
+  }
+
+  // ---- two problems per warp (PPW == 2) -------------------------------------------------------------------
+  // The two half-warps execute every sweep in lockstep (one ring, one instruction stream); what differs per problem is
+  // DATA: the statistics are reduced per half-warp, and a problem that is finished — sub-problem accepted, SCP loop
+  // converged, failed, or handed over — is frozen: its lanes keep computing but store nothing (`valid`, `wr_en`).
+  // A warp's time is the longer of its two problems either way, so lockstep costs nothing over divergence.
+  // Returns this half's status: 0 accepted, 1 NaN, 8 hand the problem to the one-problem-per-warp kernel (a state
+  // bound wants to be active, or the active-set iteration stalls: interior point / ADMM live there).
+  bool wr_en = true;  // this half's shared-block results may be written (shared_small)
+  template <bool SLEW, bool UBOX, bool DUB>
+  __device__ __forceinline__ int fused_qp_half(const DevProb& pb, unsigned char* smem, double* st, long long* cnt, bool active) {
+    double pc[NX], zc[NU], keep[ST_COUNT];
+    const bool constrained = pb.has_ubox || pb.has_xbox;
+    for (int k = 0; k < ST_COUNT; ++k) keep[k] = st[k] = 0.0;
+    keep[ST_GSCALE] = keep[ST_ZSCALE] = 1.0;
+    const bool base_valid = this->valid;
+    bool done = !active, first = true;
+    int status = 0;
+    for (int tries = 0;; ++tries) {
+      this->valid = base_valid && !done;
+      wr_en = !done;
+      bsweep<SLEW, UBOX, DUB>(pb, smem, first, pc, zc);
+      first = false;
+      double kk_c = 0.0, uv_c = 0.0, ch_c = 0.0;
+      if (Nc >= 1) ch_c = shared_small<UBOX>(pc, zc, &kk_c, &uv_c);
+      fsweep<SLEW, UBOX, DUB>(pb, smem, st);
+      reduce_stats(st);
+      if (!done) {
+        cnt[2] += 1; cnt[3] += 1; cnt[7] += 2;
+        st[ST_KKT] = fmax(st[ST_KKT], kk_c);
+        st[ST_UVIOL] = fmax(st[ST_UVIOL], uv_c);
+        st[ST_CHANGED] += ch_c;
+        const double tol_g = pb.kkt_tol * st[ST_GSCALE], tol_z = pb.kkt_tol * st[ST_ZSCALE];
+        if (st[ST_NAN] > 0.0) {
+          status = 1;
+          done = true;
+        } else if (!constrained || (st[ST_KKT] <= tol_g && st[ST_UVIOL] <= tol_z && st[ST_XVIOL] <= tol_z)) {
+          cnt[5] += 1;
+          done = true;
+        } else if (st[ST_XVIOL] > tol_z || st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) {
+          status = 8;
+          done = true;
+        }
+        if (done)
+          for (int k = 0; k < ST_COUNT; ++k) keep[k] = st[k];
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+    this->valid = base_valid;
+    wr_en = true;
+    for (int k = 0; k < ST_COUNT; ++k) st[k] = keep[k];
+    return status;
   }
 
   // One convex sub-problem on the fused path.  Returns status bits (as solve_qp), or -1 when the

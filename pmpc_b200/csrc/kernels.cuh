@@ -18,6 +18,37 @@ __global__ void __launch_bounds__(BLK, (BLK <= 128 ? PMPC_MINB : 1)) scp_kernel(
   S.template run<VAR>(pb, dyn_smem);
 }
 
+// Two problems of at most 16 particles per warp (Solver PPW = 2): one warp per CTA.
+template <int NX, int NU, int VAR>
+__global__ void __launch_bounds__(32, 8) scp_kernel_half(const __grid_constant__ DevProb pb) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ double red[ST_COUNT];
+  __shared__ double red2[RCAP];
+  Solver<NX, NU, true, 2> S(pb, red, red2);
+  S.template run_half<VAR>(pb, dyn_smem);
+}
+
+template <int NX, int NU, int VAR>
+cudaError_t launch_half(DevProb pb, int blocks, int threads, cudaStream_t stream, int* occ_out) {
+  using S = Solver<NX, NU, true, 2>;
+  (void)threads;
+  const size_t max_smem = 200 * 1024;
+  const int one = (S::table_doubles(pb.N) + 15) / 16 * 16;  // one uniform cost table per half-warp problem
+  pb.tab_doubles = ((size_t)2 * one * 8 <= 64 * 1024) ? 2 * one : 0;
+  size_t ring_bytes = (size_t)S::ring_doubles(1) * 8 + (size_t)S::DEPTH * 8;
+  pb.ring = (S::RING_SHAPE && pb.ring && (size_t)pb.tab_doubles * 8 + ring_bytes <= max_smem) ? 1 : 0;
+  if (!pb.ring) ring_bytes = 0;
+  const size_t smem = (size_t)pb.tab_doubles * 8 + ring_bytes;
+  auto kern = scp_kernel_half<NX, NU, VAR>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (occ_out != nullptr) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, 32, smem);
+  kern<<<blocks, 32, smem, stream>>>(pb);
+  return cudaGetLastError();
+}
+
 template <int NX, int NU, bool GROUPED, int BLK, int VAR>
 cudaError_t launch_variant(DevProb pb, int blocks, int threads, cudaStream_t stream, int* occ_out) {
   using S = Solver<NX, NU, GROUPED>;

@@ -159,7 +159,10 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NX, int NU, bool GROUPED>
+// PPW: problems per warp.  2 = two problems of at most 16 particles share a warp (and its 32-slot layout tile): half
+// the lanes of an M = 16 problem would otherwise mirror a neighbour (BASELINE config 3).  Only the fused active-set
+// passes run in that mode (run_half / fused_qp_half); everything else is handed to the PPW = 1 kernel of the same shape.
+template <int NX, int NU, bool GROUPED, int PPW = 1>
 struct Solver {
   static constexpr int NQ = NX * (NX + 1) / 2;
   static constexpr int NR = NU * (NU + 1) / 2;
@@ -177,6 +180,8 @@ struct Solver {
   const int N, Nc, D, T, tid;
   int prob, g;
   bool valid;
+  int hl;       // PPW = 2: lane within the half-warp that owns the problem (PPW = 1: == tid)
+  bool pvalid;  // PPW = 2: this half-warp has a problem (the last warp of an odd batch has one empty half)
   double s;  // slew weight of this particle
   double* red;  // shared: ST_COUNT doubles (+ D handled in global)
   double* red2; // shared: RCAP doubles per warp
@@ -201,7 +206,17 @@ struct Solver {
         tid(threadIdx.x), red(red_), red2(red2_), Xc(pb_.X), Uc(pb_.U), Xpv(pb_.Xp), Upv(pb_.Up), xseq(pb_.seq0), xdead(false) {
     // lanes without a particle mirror the last valid lane of their own warp (same warp tile)
     dead = false;
-    if (GROUPED) {
+    hl = tid;
+    pvalid = true;
+    if (GROUPED && PPW == 2) {
+      // two problems per warp: lanes 0-15 own problem 2 b, lanes 16-31 problem 2 b + 1 (Mpad == 16: both in one tile)
+      hl = tid & 15;
+      const int pr = (int)blockIdx.x * 2 + (tid >> 4);
+      pvalid = pr < pb.B;
+      prob = pvalid ? pr : pb.B - 1;  // an empty half mirrors the last problem and never stores
+      valid = pvalid && hl < pb.M;
+      g = prob * pb.Mpad + min(hl, pb.M - 1);
+    } else if (GROUPED) {
       prob = blockIdx.x;
       valid = tid < pb.M;
       g = prob * pb.Mpad + min(tid, min(pb.M - 1, tid | 31));
@@ -272,6 +287,21 @@ struct Solver {
   // stall samples).
   __device__ __forceinline__ void cta_reduce(double* v, int cnt, unsigned sum_mask) {
     if (!GROUPED) return;
+    if (PPW == 2) {
+      // the problem is a half-warp: butterfly over 16 lanes.  Same association as the one-problem-per-warp kernel,
+      // whose first step only adds the zeros of the mirror lanes: results are bit-identical between the two.
+      for (int k = 0; k < cnt; ++k) {
+        const bool is_sum = (sum_mask >> k) & 1u;
+        double r = v[k];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          const double t = __shfl_xor_sync(0xffffffffu, r, o);
+          r = is_sum ? r + t : fmax(r, t);
+        }
+        v[k] = r;
+      }
+      return;
+    }
     const int ln = tid & 31, w = tid >> 5, nw = T >> 5;
     for (int k = 0; k < cnt; ++k) {
       const bool is_sum = (sum_mask >> k) & 1u;
@@ -1548,6 +1578,91 @@ struct Solver {
     cnt[0] = it;
     if (writer) {
       for (int k = 0; k < 8; ++k) pb.info[(size_t)k * pb.B + prob] = cnt[k];
+    }
+  }
+
+  // ---- the SCP loop with two problems per warp (PPW == 2; see fused_qp_half) --------------------------------
+  template <int VAR>
+  __device__ __forceinline__ void run_half(const DevProb& kp, unsigned char* smem) {
+    constexpr bool DUB = (VAR & 1) && NX == 4 && NU == 2;
+    constexpr bool LEAN = (VAR & 2) != 0;
+    fused_init(smem);
+    flip = false;
+    double st[ST_COUNT];
+    for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
+    long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool writer = pvalid && hl == 0;
+    bool active = pvalid, handed = false;
+    int its = 0;
+    const double *solX = Xc, *solU = Uc, *linX = Xpv, *linU = Upv;
+    for (int it = 0; it < pb.max_it; ++it) {
+      const int status = fused_qp_half<!LEAN, true, DUB>(kp, smem, st, cnt, active);
+      if (active) {
+        if (status & 8) {  // continued by the one-problem-per-warp kernel from this iteration's linearisation point
+          handed = true;
+          active = false;
+          linX = Xpv;
+          linU = Upv;
+        } else {
+          solX = Xc;
+          solU = Uc;
+          its = it + 1;
+          if (status & 1) {
+            cnt[4] |= 1;
+            if (valid) {  // reference convention: NaN output on failure (osqp_solver.jl:69-71)
+              for (int j = 0; j < N; ++j) {
+#pragma unroll
+                for (int r = 0; r < NX; ++r) at(Xc, j, NX, r) = NAN;
+#pragma unroll
+                for (int t = 0; t < NU; ++t) at(Uc, j, NU, t) = NAN;
+              }
+            }
+            active = false;
+          } else {
+            const double max_res = fmax(st[ST_DX], st[ST_DU]);
+            const int hrow = it + pb.hist_off;
+            if (writer && hrow < pb.hist_len) {
+              const size_t Bn = (size_t)pb.B;
+              pb.hist[((size_t)0 * pb.hist_len + hrow) * Bn + prob] = st[ST_OBJ] / ((double)N * (double)pb.M);
+              pb.hist[((size_t)1 * pb.hist_len + hrow) * Bn + prob] = max_res;
+              pb.hist[((size_t)2 * pb.hist_len + hrow) * Bn + prob] = 0.0;
+              pb.hist[((size_t)3 * pb.hist_len + hrow) * Bn + prob] = st[ST_KKT] / fmax(st[ST_GSCALE], 1.0);
+            }
+            if (max_res < pb.res_tol) active = false;
+          }
+        }
+      }
+      if (!pb.keep_prev) {  // X_prev <- X is a buffer swap, in lockstep for both problems (a frozen one stores nothing)
+        double* t0 = Xc; Xc = Xpv; Xpv = t0;
+        double* t1 = Uc; Uc = Upv; Upv = t1;
+        flip = !flip;
+      }
+      if (!__any_sync(0xffffffffu, active)) break;
+    }
+    // leave the solution in pb.X / pb.U (and pb.Xp / pb.Up unless keep_prev); a handed-over problem only needs its
+    // linearisation point in pb.Xp / pb.Up
+    if (valid) {
+      const double* sx = handed ? linX : solX;
+      const double* su = handed ? linU : solU;
+      for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+          const double v = sx[ix(j, NX, r)];
+          if (!handed && sx != pb.X) at(pb.X, j, NX, r) = v;
+          if ((handed || !pb.keep_prev) && sx != pb.Xp) at(pb.Xp, j, NX, r) = v;
+        }
+#pragma unroll
+        for (int t = 0; t < NU; ++t) {
+          const double v = su[ix(j, NU, t)];
+          if (!handed && su != pb.U) at(pb.U, j, NU, t) = v;
+          if ((handed || !pb.keep_prev) && su != pb.Up) at(pb.Up, j, NU, t) = v;
+        }
+      }
+    }
+    cnt[0] = its;
+    if (writer) {
+      for (int k = 0; k < 8; ++k) pb.info[(size_t)k * pb.B + prob] = cnt[k];
+      pb.fb[prob] = handed ? 1 : 0;
     }
   }
 };
