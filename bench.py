@@ -200,20 +200,35 @@ def survey_streaming_bytes(info, n=NX, m=NU, nparam=3):
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_sample(cores: int, its: int, seed: int = 0):
-    """CPU leg: `cores` C2 problems, one per host thread, each the first `its` SCP iterations (res_tol = -1 forces
-    exactly `its`), with the reference's algorithm restated in C (oracle/c/pmpc_oracle.c: lqp_utils.jl assembly +
-    OSQP 0.6.2 at its defaults + Dubins + the SCP loop).  Returns wall seconds."""
+def cpu_sample(cores: int, its: int, seed: int = 0, whole: bool = False):
+    """CPU leg: `cores` problems of the workload, one per host thread, each the first `its` SCP iterations (res_tol = -1
+    forces exactly `its`) — or, with `whole`, each solved to the workload's stop rule — with the reference's algorithm
+    restated in C (oracle/c/pmpc_oracle.c: lqp_utils.jl assembly + OSQP 0.6.2 at its defaults + Dubins + the SCP loop).
+    Returns wall seconds (and the iteration counts with `whole`)."""
     from oracle import cport
 
     arrs, p, d0 = make_batch(cores, seed)
     t = time.perf_counter()
     X, U, iters = cport.scp_dubins_batch(cores, p, arrs["Q"], arrs["R"], arrs["x0"], arrs["X_ref"], arrs["U_ref"], arrs["X_prev"],
                                          arrs["U_prev"], arrs["u_l"], arrs["u_u"], reg_x=d0["reg_x"], reg_u=d0["reg_u"],
-                                         max_it=its, res_tol=-1.0, Nc=NC)
+                                         max_it=MAX_IT if whole else its, res_tol=RES_TOL if whole else -1.0, Nc=NC)
     sec = time.perf_counter() - t
-    assert np.isfinite(X).all() and (iters == its).all()
-    return sec
+    assert np.isfinite(X).all() and (whole or (iters == its).all())
+    return (sec, np.asarray(iters)) if whole else sec
+
+
+def cpu_whole_solves(cores: int, rounds: int, seed: int = 0):
+    """`rounds` x `cores` whole solves (C3: a problem is 480 particle-stages, a few seconds per core).  Returns
+    (solves/s, sample description)."""
+    sec, its = 0.0, []
+    for r in range(rounds):
+        s, i = cpu_sample(cores, 0, seed=seed + 100 * r, whole=True)
+        sec += s
+        its.append(i)
+    its = np.concatenate(its)
+    return cores * rounds / sec, (f"{cores} host threads x {rounds} WHOLE solves each of problems of this workload (res_tol {RES_TOL:g}, "
+                                  f"max_it {MAX_IT}; {its.mean():.1f} SCP iterations on average) with the reference's solver restated "
+                                  f"in C (oracle/c/pmpc_oracle.c, OSQP 0.6.2 defaults), {sec:.1f} s wall")
 
 
 def reference_arm(args):
@@ -226,15 +241,20 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    full_its = c2_iters_fixture()["c_port_scp_iters"]
-    sample_its = args.ref_sample_its
     for _ in range(args.warmup):
         cpu_sample(cores, 1)  # warm-up: caches and thread pool only; one SCP iteration each
-    times = [cpu_sample(cores, sample_its, seed=k) for k in range(args.steps)]
-    step = float(np.mean(times))
-    value = cores * (sample_its / full_its) / step
-    sample = (f"{cores} host threads, each the first {sample_its} of {full_its} SCP iterations of its own C2 problem "
-              f"(plain-C restatement: OSQP 0.6.2 at the reference's defaults eps=1e-3), scaled to full solves")
+    if args.workload == "c3":  # small problems: every step is one whole solve per host thread
+        t0 = time.perf_counter()
+        value, sample = cpu_whole_solves(cores, args.steps, seed=1)
+        step = (time.perf_counter() - t0) / args.steps
+    else:
+        full_its = c2_iters_fixture()["c_port_scp_iters"]
+        sample_its = args.ref_sample_its
+        times = [cpu_sample(cores, sample_its, seed=k) for k in range(args.steps)]
+        step = float(np.mean(times))
+        value = cores * (sample_its / full_its) / step
+        sample = (f"{cores} host threads, each the first {sample_its} of {full_its} SCP iterations of its own C2 problem "
+                  f"(plain-C restatement: OSQP 0.6.2 at the reference's defaults eps=1e-3), scaled to full solves")
     import shutil
 
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
@@ -348,7 +368,9 @@ def main():
     X, U = X.copy(), U.copy()
     hist = ds.hist(int(info["scp_iters"].max()))
     last_res = np.array([hist["resid"][info["scp_iters"][b] - 1, b] for b in range(B)])
-    ok = bool((info["status"] == 0).all() and (last_res < RES_TOL).all() and np.isfinite(X).all()
+    # (a problem that is still above res_tol after max_it iterations stops there, as in the reference: scp_mpc.py:424-428)
+    at_max = info["scp_iters"] >= MAX_IT
+    ok = bool((info["status"] == 0).all() and ((last_res < RES_TOL) | at_max).all() and np.isfinite(X).all()
               and np.abs(U).max() <= 1 + 1e-9 and np.all(U[:, :, 0] == U[:, :1, 0]))
     kernel_ms = ds.last_kernel_ms()  # the last step's SCP kernel alone
     occ = ds.occupancy()
@@ -358,7 +380,8 @@ def main():
     peak, peak_src = hbm_peak()
     abytes, aflops = alg_bytes_flops(info)
     roofline = {"bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "scp_kernel<4,2,grouped>",
+                "frac": abytes / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                "kernel": ("scp_kernel_half<4,2> (two problems per warp) + resume launch" if args.workload == "c3" else "scp_kernel<4,2,grouped>"),
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,
                 "model": "fused two-sweep pass: 486 B per (particle, stage, pass) = X_prev,U_prev,act in; K,k,H01,sparse stage "
                          "out+in; X,U,act out (DESIGN.md 5)",
@@ -373,6 +396,10 @@ def main():
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
             tr = json.load(fh)
+        tr = tr.get(args.workload, tr if args.workload == "c2" else None)
+    else:
+        tr = None
+    if tr:
         # ncu (--set full) DRAM read + write bytes of the same kernel, per problem, scaled to this launch
         roofline["traffic"] = tr["dram_bytes_per_problem"] * B
         roofline["traffic_source"] = tr.get("source")
@@ -430,8 +457,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fx = c2_iters_fixture()
         its, cores = args.cpu_sample_its, os.cpu_count() or 1
-        sec = cpu_sample(cores, its)
-        cpu = {"value": cores / (sec * fx["c_port_scp_iters"] / its), "unit": "solves/s", "cores": cores, "kind": "port",
+        if args.workload == "c3":
+            v, sample = cpu_whole_solves(cores, 3)
+            cpu = {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample}
+        else:
+            sec = cpu_sample(cores, its)
+        if cpu is None:
+            cpu = {"value": cores / (sec * fx["c_port_scp_iters"] / its), "unit": "solves/s", "cores": cores, "kind": "port",
                "sample": f"{cores} host threads, each the first {its} of {fx['c_port_scp_iters']} SCP iterations of its own C2 "
                          f"problem with the reference's solver restated in C (oracle/c/pmpc_oracle.c, OSQP 0.6.2 defaults), "
                          f"{sec:.1f} s wall, scaled to full solves"}
@@ -447,8 +479,9 @@ def main():
                             "julia_on_this_box": __import__("shutil").which("julia")},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu, "parity_ok": ok,
-                "scp_iters": {"min": int(info["scp_iters"].min()), "max": int(info["scp_iters"].max()),
-                              "problem0": int(info["scp_iters"][0]), "reference_port": c2_iters_fixture()},
+                "scp_iters": {"min": int(info["scp_iters"].min()), "max": int(info["scp_iters"].max()), "mean": float(info["scp_iters"].mean()),
+                              "stopped_at_max_it": int(at_max.sum()),
+                              "problem0": int(info["scp_iters"][0]), "reference_port": (c2_iters_fixture() if args.workload == "c2" else None)},
                 "qp_passes_per_solve": {"factorizations": float(info["factorizations"].mean()),
                                         "polish": float(info["polish_passes"].mean()), "admm": float(info["admm_iters"].mean())},
                 "latency_ms": ({"p50": 1e3 * float(np.median(lat)), "min": 1e3 * float(min(lat)), "n": len(lat),

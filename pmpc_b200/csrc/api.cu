@@ -85,7 +85,7 @@ static bool pick_shape(int n, int m, Shape* out) {
 struct pmpc_userdyn_s;  // userdyn.inl
 
 struct pmpc_handle_s {
-  int device = 0;
+  int device = 0, num_sms = 1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;  // pmpc_timer_start / pmpc_timer_stop
@@ -411,6 +411,7 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   } else {
     CU(cudaGetDevice(&h->device));
   }
+  CU(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
@@ -810,8 +811,12 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
   if (!fn) return fail(PMPC_ERR_UNSUPPORTED, "no kernel for this shape");
   // two problems per warp: M <= 16 particles in the 16-slot layout, fused active-set passes only (no state box, one
   // GPU); what it cannot finish is continued by the one-problem-per-warp kernel launched behind it in resume mode
+  // It pays once the one-problem-per-warp kernel needs more than one wave (8 warps per SM): below that it only doubles
+  // the latency of a warp.  PMPC_HALF=0 / 1 overrides the batch-size rule (tests, A/B timing).
+  const char* half_env = getenv("PMPC_HALF");
+  const bool half_wanted = half_env ? atoi(half_env) != 0 : pb.B > 8 * h->num_sms;
   const bool half = fn_half && pb.M >= 2 && pb.M <= 16 && pb.Mpad == 16 && pb.fused && pb.polish && !pb.has_xbox &&
-                    pb.world <= 1 && !getenv("PMPC_NO_HALF");
+                    pb.D <= DSMALL && pb.world <= 1 && half_wanted;  // (D <= DSMALL: shared block solved in registers)
   if (occ_out) {
     cudaError_t e = half ? fn_half(pb, (pb.B + 1) / 2, 32, h->stream, occ_out) : fn(pb, blocks, threads, h->stream, occ_out);
     if (half) *occ_out *= 2;  // problems per SM
@@ -872,6 +877,8 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
     h->pb.resume = 1;
   }
   if (half) {
+    const char* hi = getenv("PMPC_HALF_IPM");
+    h->pb.half_ipm = hi ? atoi(hi) : 1;
     cudaError_t e = fn_half(h->pb, (pb.B + 1) / 2, 32, h->stream, nullptr);
     if (e != cudaSuccess) return fail(PMPC_ERR_CUDA, std::string("kernel launch (two problems per warp): ") + cudaGetErrorString(e));
     ++g_launches;

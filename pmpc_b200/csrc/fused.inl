@@ -56,7 +56,7 @@
   __device__ __forceinline__ Sm smem_view(const DevProb& pb, unsigned char* smem) const {
     double* base = reinterpret_cast<double*>(smem);
     Sm v;
-    v.tab = has_tab ? base + ((PPW == 2) ? (tid >> 4) * (pb.tab_doubles / 2) : 0) : nullptr;
+    v.tab = has_tab ? base + ((PPW == 2) ? (tid >> 4) * (pb.tab_doubles / (2 * (T >> 5))) : 0) : nullptr;
     v.ring = pb.ring ? base + pb.tab_doubles + (size_t)wid * DEPTH * SLOT : nullptr;
     v.bars = pb.ring ? reinterpret_cast<uint64_t*>(base + pb.tab_doubles + (size_t)(T >> 5) * DEPTH * SLOT) + wid * DEPTH : nullptr;
     return v;
@@ -97,7 +97,7 @@
         fence_mbar_init();
       }
     }
-    if (PPW == 2) tb = base + (tid >> 4) * (pb.tab_doubles / 2);  // one table per half-warp problem
+    if (PPW == 2) tb = base + (tid >> 4) * (pb.tab_doubles / (2 * (T >> 5)));  // one table per half-warp problem
     if (GROUPED && pb.tab_doubles > 0 && pb.uniform[prob]) {
       // particle 0 of the problem speaks for all (checked on the device by uniform_check_kernel)
       const size_t g0 = (size_t)prob * pb.Mpad;
@@ -1200,7 +1200,7 @@
         for (int b = 0; b < Dn; ++b) F.Hc[(size_t)prob * Dn * Dn + (size_t)a * Dn + b] = H[a * DSMALL + b];
       }
     }
-    __syncthreads();
+    if (PPW == 2) { __threadfence_block(); __syncwarp(); } else __syncthreads();  // (PPW 2: a problem lives in a half-warp)
     return ch;
   }
 
@@ -1233,7 +1233,7 @@
     if (!GROUPED || Nc < 1) return;
     const double* ucn = pb.uc + (size_t)prob * D;
     const size_t g0 = (size_t)prob * pb.Mpad;
-    for (int k = tid; k < D; k += T) {
+    for (int k = (PPW == 2 ? hl : tid); k < D; k += (PPW == 2 ? 16 : T)) {
       const size_t o = ixg(k / NU, NU, k % NU, g0);
       ipm_ratios(ip, pb.wu[o], ucn[k], pb.lu[o], pb.uu[o], pb.yu[o], pb.wx[o], acc);
     }
@@ -1255,15 +1255,15 @@
     if (GROUPED && Nc >= 1) {
       const double* ucn = pb.uc + (size_t)prob * D;
       const size_t g0 = (size_t)prob * pb.Mpad;
-      __syncthreads();
-      for (int k = tid; k < D; k += T) {
+      if (PPW == 2) __syncwarp(); else __syncthreads();  // (PPW 2: the problem is a half-warp; CTA barriers are phase barriers there)
+      for (int k = (PPW == 2 ? hl : tid); k < D; k += (PPW == 2 ? 16 : T)) {
         const size_t o = ixg(k / NU, NU, k % NU, g0);
         const double lo = pb.lu[o], hi = pb.uu[o];
         double u = 0.0, lh = pb.yu[o], ll = pb.wx[o];
         ipm_point(ip, pb.wu[o], ucn[k], lo, hi, 0.0, u, lh, ll);
-        pb.actc[(size_t)prob * D + k] = (hi - u < lh) ? 1 : ((u - lo < ll) ? -1 : 0);
+        if (PPW == 1 || (wr_en && pvalid)) pb.actc[(size_t)prob * D + k] = (hi - u < lh) ? 1 : ((u - lo < ll) ? -1 : 0);
       }
-      __syncthreads();
+      if (PPW == 2) { __threadfence_block(); __syncwarp(); } else __syncthreads();
     }
   }
 
@@ -1395,7 +1395,134 @@
   // A warp's time is the longer of its two problems either way, so lockstep costs nothing over divergence.
   // Returns this half's status: 0 accepted, 1 NaN, 8 hand the problem to the one-problem-per-warp kernel (a state
   // bound wants to be active, or the active-set iteration stalls: interior point / ADMM live there).
-  bool wr_en = true;  // this half's shared-block results may be written (shared_small)
+  bool wr_en = true;  // this half's shared-block results may be written (shared_small, interior-point state)
+
+  // Shared block of an interior-point iteration in registers (the half-warp counterpart of assemble_shared + grad_shared
+  // + ipm_shared_pre + factor_shared + apply_shared for D <= DSMALL): sum_i H_i, sum_i g_i by one half-warp reduction, the
+  // lazily updated iterate and the barrier terms of the shared controls, an unmasked Cholesky solve, replicated per lane.
+  template <bool UBOX>
+  __device__ __noinline__ void shared_small_ipm(const Ipm ip, const double* pc, const double* zc) {
+    const FactorSet& F = pb.fs[MODE_POLISH];
+    const int Dn = D;
+    double hv[DSMALL * DSMALL + DSMALL];
+    for (int k = 0; k < Dn; ++k) shared_grad(MODE_POLISH, true, k, nullptr, 0.0, 0.0, nullptr, nullptr, 0, &hv[k * Dn]);
+    shared_grad(MODE_POLISH, false, -1, nullptr, 0.0, 0.0, pc, zc, 0, &hv[Dn * Dn]);
+    cta_reduce(hv, Dn * Dn + Dn, 0xffffffffu);
+    double H[DSMALL * DSMALL], gcv[DSMALL], un[DSMALL], lhn[DSMALL], lln[DSMALL];
+    const size_t g0 = (size_t)prob * pb.Mpad;
+    const double* Up0 = flip ? pb.U : pb.Up;
+    for (int a = 0; a < Dn; ++a) {
+      for (int b = 0; b < Dn; ++b) H[a * DSMALL + b] = 0.5 * (hv[b * Dn + a] + hv[a * Dn + b]);
+      gcv[a] = hv[Dn * Dn + a];
+      const size_t o = ixg(a / NU, NU, a % NU, g0);
+      const double lo = pb.lu[o], hi = pb.uu[o];
+      double u = 0.0, lh = 0.0, ll = 0.0, u0 = 0.0;
+      if (!ip.init) {
+        u0 = pb.wu[o]; lh = pb.yu[o]; ll = pb.wx[o];
+      }
+      ipm_point(ip, u0, pb.uc[(size_t)prob * Dn + a], lo, hi, Up0[o], u, lh, ll);
+      un[a] = u; lhn[a] = lh; lln[a] = ll;
+      const double sh = hi - u, sl = u - lo, sg = lh / sh + ll / sl;
+      H[a * DSMALL + a] += sg;
+      gcv[a] += -sg * u + ip.mu / sh - ip.mu / sl;
+    }
+    double L[DSMALL * DSMALL], y[DSMALL];
+    for (int k = 0; k < Dn; ++k) {  // Cholesky (lower)
+      double dk = H[k * DSMALL + k];
+      for (int l = 0; l < k; ++l) dk -= L[k * DSMALL + l] * L[k * DSMALL + l];
+      dk = sqrt(dk);
+      L[k * DSMALL + k] = dk;
+      for (int i = k + 1; i < Dn; ++i) {
+        double v = H[i * DSMALL + k];
+        for (int l = 0; l < k; ++l) v -= L[i * DSMALL + l] * L[k * DSMALL + l];
+        L[i * DSMALL + k] = v / dk;
+      }
+    }
+    for (int i = 0; i < Dn; ++i) {
+      double v = -gcv[i];
+      for (int l = 0; l < i; ++l) v -= L[i * DSMALL + l] * y[l];
+      y[i] = v / L[i * DSMALL + i];
+    }
+    for (int i = Dn - 1; i >= 0; --i) {
+      double v = y[i];
+      for (int l = i + 1; l < Dn; ++l) v -= L[l * DSMALL + i] * y[l];
+      y[i] = v / L[i * DSMALL + i];
+    }
+    __syncwarp();  // every lane has read the interior-point state of the shared controls
+    if (hl == 0 && pvalid && wr_en) {
+      for (int a = 0; a < Dn; ++a) {
+        const size_t o = ixg(a / NU, NU, a % NU, g0);
+        pb.wu[o] = un[a]; pb.yu[o] = lhn[a]; pb.wx[o] = lln[a];
+        pb.uc[(size_t)prob * Dn + a] = y[a];
+        pb.gc[(size_t)prob * Dn + a] = gcv[a];
+        for (int b = 0; b < Dn; ++b) F.Hc[(size_t)prob * Dn * Dn + (size_t)a * Dn + b] = H[a * DSMALL + b];
+      }
+    }
+    if (PPW == 2) { __threadfence_block(); __syncwarp(); } else __syncthreads();
+  }
+
+  // Interior-point solve (ipm_solve) for the halves with want == true, the other half frozen.  rc per half: 0 converged,
+  // 1 NaN, -1 no convergence (the polish passes that follow decide).
+  template <bool SLEW, bool UBOX, bool DUB>
+  __device__ __noinline__ int ipm_solve_half(const DevProb& pb, unsigned char* smem, double* st, long long* cnt, double scale,
+                                              bool want, bool base_valid) {
+    double pc[NX], zc[NU];
+    Ipm ip;
+    ip.mu_prev = scale;
+    ip.mu = 0.2 * scale;
+    ip.ap = ip.ad = 0.0;
+    ip.init = 1;
+    const double tol_c = 1e-9 * scale;
+    int rc = -1;
+    bool fin = !want;
+    for (int it = 0; it < 80; ++it) {
+      this->valid = base_valid && want && !fin;
+      wr_en = want && !fin;
+      half_phase(1);
+      bsweep<SLEW, UBOX, DUB, 1>(pb, smem, false, pc, zc, ip);
+      if (Nc >= 1) shared_small_ipm<UBOX>(ip, pc, zc);
+      double acc[7] = {INFINITY, INFINITY, 0.0, 0.0, 0.0, 0.0, 0.0};
+      __syncthreads();
+      fsweep<SLEW, UBOX, DUB, 1>(pb, smem, st, ip, acc);
+      double v8[8];
+      if (!this->valid) {
+        acc[0] = acc[1] = INFINITY;
+        acc[2] = acc[3] = acc[4] = acc[5] = acc[6] = 0.0;
+      }
+      if (want && !fin) ipm_shared_post(pb, ip, acc);
+      v8[0] = -acc[0]; v8[1] = -acc[1];
+      for (int k = 2; k < 7; ++k) v8[k] = acc[k];
+      v8[7] = this->valid ? st[ST_NAN] : 0.0;
+      cta_reduce(v8, 8, 0x7cu);
+      if (!fin) {
+        cnt[1] += 1; cnt[2] += 1; cnt[3] += 1; cnt[7] += 2;
+        const double a0 = -v8[0], a1 = -v8[1];
+        const double ap = fmin(1.0, 0.995 * a0), ad = fmin(1.0, 0.995 * a1);
+        const double comp = (v8[2] + ad * v8[3] + ap * v8[4] + ap * ad * v8[5]) / fmax(v8[6], 1.0);
+        if (v8[7] > 0.0 || !(comp == comp)) {
+          rc = 1;
+          fin = true;
+        } else {
+          ip.mu_prev = ip.mu;
+          ip.ap = ap;
+          ip.ad = ad;
+          ip.init = 0;
+          if (comp <= tol_c && ap >= 0.9) {
+            rc = 0;
+            fin = true;
+          } else {
+            ip.mu = fmax(0.2 * comp, 1e-3 * tol_c);
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, fin)) break;
+    }
+    this->valid = base_valid && want && rc != 1;
+    wr_en = want && rc != 1;
+    ipm_finish(pb, ip);
+    return rc;
+  }
+
   template <bool SLEW, bool UBOX, bool DUB>
   __device__ __forceinline__ int fused_qp_half(const DevProb& pb, unsigned char* smem, double* st, long long* cnt, bool active) {
     double pc[NX], zc[NU], keep[ST_COUNT];
@@ -1403,18 +1530,22 @@
     for (int k = 0; k < ST_COUNT; ++k) keep[k] = st[k] = 0.0;
     keep[ST_GSCALE] = keep[ST_ZSCALE] = 1.0;
     const bool base_valid = this->valid;
-    bool done = !active, first = true;
-    int status = 0;
-    for (int tries = 0;; ++tries) {
-      this->valid = base_valid && !done;
-      wr_en = !done;
+    enum { RUN = 0, WANT_IPM = 1, DONE = 2 };
+    int state = active ? RUN : DONE, status = 0, tries = 0;
+    bool first = true, ipm_used = false;
+    double scale = 1.0;
+    for (;;) {
+      this->valid = base_valid && state == RUN;
+      wr_en = state == RUN;
+      half_phase(1);
       bsweep<SLEW, UBOX, DUB>(pb, smem, first, pc, zc);
       first = false;
       double kk_c = 0.0, uv_c = 0.0, ch_c = 0.0;
       if (Nc >= 1) ch_c = shared_small<UBOX>(pc, zc, &kk_c, &uv_c);
+      __syncthreads();
       fsweep<SLEW, UBOX, DUB>(pb, smem, st);
       reduce_stats(st);
-      if (!done) {
+      if (state == RUN) {
         cnt[2] += 1; cnt[3] += 1; cnt[7] += 2;
         st[ST_KKT] = fmax(st[ST_KKT], kk_c);
         st[ST_UVIOL] = fmax(st[ST_UVIOL], uv_c);
@@ -1422,18 +1553,43 @@
         const double tol_g = pb.kkt_tol * st[ST_GSCALE], tol_z = pb.kkt_tol * st[ST_ZSCALE];
         if (st[ST_NAN] > 0.0) {
           status = 1;
-          done = true;
+          state = DONE;
         } else if (!constrained || (st[ST_KKT] <= tol_g && st[ST_UVIOL] <= tol_z && st[ST_XVIOL] <= tol_z)) {
           cnt[5] += 1;
-          done = true;
-        } else if (st[ST_XVIOL] > tol_z || st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) {
-          status = 8;
-          done = true;
+          state = DONE;
+        } else if (st[ST_XVIOL] > tol_z) {
+          status = 8;  // a state bound wants to be active: ADMM lives in the one-problem-per-warp kernel
+          state = DONE;
+        } else if (st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) {
+          // the active-set iteration stalls or cycles: one interior-point solve, then polish from its estimate
+          if (ipm_used || !pb.has_ubox || !pb.half_ipm) {
+            status = 8;
+            state = DONE;
+          } else {
+            state = WANT_IPM;
+            scale = fmax(st[ST_GSCALE], 1.0);
+          }
         }
-        if (done)
+        ++tries;
+        if (state == DONE)
           for (int k = 0; k < ST_COUNT; ++k) keep[k] = st[k];
       }
-      if (__all_sync(0xffffffffu, done)) break;
+      if (__any_sync(0xffffffffu, state == WANT_IPM)) {
+        const int rc = ipm_solve_half<SLEW, UBOX, DUB>(pb, smem, st, cnt, scale, state == WANT_IPM, base_valid);
+        if (state == WANT_IPM) {
+          if (rc == 1) {
+            status = 1;
+            state = DONE;
+            for (int k = 0; k < ST_COUNT; ++k) keep[k] = 0.0;
+            keep[ST_NAN] = 1.0;
+          } else {
+            state = RUN;
+            ipm_used = true;
+            tries = 0;
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, state == DONE)) break;
     }
     this->valid = base_valid;
     wr_en = true;

@@ -18,9 +18,10 @@ __global__ void __launch_bounds__(BLK, (BLK <= 128 ? PMPC_MINB : 1)) scp_kernel(
   S.template run<VAR>(pb, dyn_smem);
 }
 
-// Two problems of at most 16 particles per warp (Solver PPW = 2): one warp per CTA.
+// Two problems of at most 16 particles per warp (Solver PPW = 2), HW warps per CTA whose sweeps are phase-aligned
+// (Solver::half_phase).
 template <int NX, int NU, int VAR>
-__global__ void __launch_bounds__(32, 8) scp_kernel_half(const __grid_constant__ DevProb pb) {
+__global__ void __launch_bounds__(128, 2) scp_kernel_half(const __grid_constant__ DevProb pb) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ double red[ST_COUNT];
   __shared__ double red2[RCAP];
@@ -31,21 +32,30 @@ __global__ void __launch_bounds__(32, 8) scp_kernel_half(const __grid_constant__
 template <int NX, int NU, int VAR>
 cudaError_t launch_half(DevProb pb, int blocks, int threads, cudaStream_t stream, int* occ_out) {
   using S = Solver<NX, NU, true, 2>;
-  (void)threads;
-  const size_t max_smem = 200 * 1024;
-  const int one = (S::table_doubles(pb.N) + 15) / 16 * 16;  // one uniform cost table per half-warp problem
-  pb.tab_doubles = ((size_t)2 * one * 8 <= 64 * 1024) ? 2 * one : 0;
-  size_t ring_bytes = (size_t)S::ring_doubles(1) * 8 + (size_t)S::DEPTH * 8;
-  pb.ring = (S::RING_SHAPE && pb.ring && (size_t)pb.tab_doubles * 8 + ring_bytes <= max_smem) ? 1 : 0;
-  if (!pb.ring) ring_bytes = 0;
-  const size_t smem = (size_t)pb.tab_doubles * 8 + ring_bytes;
+  (void)blocks; (void)threads;
   auto kern = scp_kernel_half<NX, NU, VAR>;
-  if (smem > 48 * 1024) {
+  const int one = (S::table_doubles(pb.N) + 15) / 16 * 16;  // one uniform cost table per half-warp problem
+  const int want_ring = pb.ring;
+  // warps per CTA: as many as keep 8 warps resident per SM (the register file's limit) — 4 (two CTAs per SM), else 2, 1
+  int W = 4, occ = 0;
+  size_t smem = 0;
+  for (;; W >>= 1) {
+    pb.tab_doubles = ((size_t)2 * W * one * 8 <= 100 * 1024 / (4 / W)) ? 2 * W * one : 0;
+    size_t ring_bytes = (size_t)S::ring_doubles(W) * 8 + (size_t)W * S::DEPTH * 8;
+    pb.ring = (S::RING_SHAPE && want_ring) ? 1 : 0;
+    if (!pb.ring) ring_bytes = 0;
+    smem = (size_t)pb.tab_doubles * 8 + ring_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem)) != cudaSuccess) return e;
+    if (occ * W >= 8 || W == 1) break;
   }
-  if (occ_out != nullptr) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, 32, smem);
-  kern<<<blocks, 32, smem, stream>>>(pb);
+  if (occ_out != nullptr) {
+    *occ_out = occ * W;  // warps (= pairs of problems) per SM
+    return cudaSuccess;
+  }
+  const int nblk = (pb.B + 2 * W - 1) / (2 * W);
+  kern<<<nblk, 32 * W, smem, stream>>>(pb);
   return cudaGetLastError();
 }
 

@@ -90,6 +90,7 @@ struct DevProb {
   double* wscr;
   int* fb;
   int resume;
+  int half_ipm;               // two-problems-per-warp kernel: interior-point fallback inside the kernel (1) or hand the problem over (0)
   int* xerr;                            // device flag: an exchange timed out (read back by pmpc_sync)
 };
 
@@ -211,7 +212,7 @@ struct Solver {
     if (GROUPED && PPW == 2) {
       // two problems per warp: lanes 0-15 own problem 2 b, lanes 16-31 problem 2 b + 1 (Mpad == 16: both in one tile)
       hl = tid & 15;
-      const int pr = (int)blockIdx.x * 2 + (tid >> 4);
+      const int pr = ((int)blockIdx.x * (int)(blockDim.x >> 5)) * 2 + (tid >> 4);  // (tid >> 4) = 2 * warp + half
       pvalid = pr < pb.B;
       prob = pvalid ? pr : pb.B - 1;  // an empty half mirrors the last problem and never stores
       valid = pvalid && hl < pb.M;
@@ -1596,6 +1597,7 @@ struct Solver {
     int its = 0;
     const double *solX = Xc, *solU = Uc, *linX = Xpv, *linU = Upv;
     for (int it = 0; it < pb.max_it; ++it) {
+      if (!__any_sync(0xffffffffu, active)) break;  // (an empty warp of the last CTA)
       const int status = fused_qp_half<!LEAN, true, DUB>(kp, smem, st, cnt, active);
       if (active) {
         if (status & 8) {  // continued by the one-problem-per-warp kernel from this iteration's linearisation point
@@ -1664,7 +1666,18 @@ struct Solver {
       for (int k = 0; k < 8; ++k) pb.info[(size_t)k * pb.B + prob] = cnt[k];
       pb.fb[prob] = handed ? 1 : 0;
     }
+    // this warp is finished: keep answering the phase barriers of the CTA's other warps (half_phase) until all are
+    while (half_phase(0)) __syncthreads();
   }
+
+  // Phase alignment of the warps of a CTA in the two-problems-per-warp kernel.  Every warp solves its own pair of problems
+  // independently, but all of them start a backward sweep — and a forward sweep — together: the resident warps of an SM
+  // then execute the same loop body, so that one instruction fetch serves them all.  (With eight independent one-warp
+  // CTAs per SM at eight different places of a 330 KB kernel the instruction cache — 32 KB — misses all the time:
+  // ncu `no_instruction` 2.5 stall cycles per issued instruction.)  All passes have the same length, so nobody waits
+  // for long.  Two CTA barriers per pass: start of bsweep (returns whether any warp of the CTA still works) and start of
+  // fsweep; everything else in this mode synchronises at warp level.
+  __device__ __forceinline__ int half_phase(int working) { return __syncthreads_or(working); }
 };
 
 }  // namespace pmpc
