@@ -837,6 +837,10 @@ static int launch(pmpc_handle_t h, int* occ_out = nullptr) {
       if (w.nx == NX && w.nu == NU && w.slew == (pb.has_slew ? 1 : 0)) we = &w;
   CU(cudaEventRecord(h->ev0, h->stream));
   h->pb.resume = 0;
+  {
+    const char* mu = getenv("PMPC_AL_MU");  // multiplier method for active state bounds (wpp.cuh): starting penalty; 0 = ADMM hand-over
+    h->pb.al_mu = mu ? atof(mu) : 30.0;
+  }
   if (we) {
     WppPlan pl;
     cudaError_t e = we->plan(pb, &pl);

@@ -90,6 +90,7 @@ struct DevProb {
   double* wscr;
   int* fb;
   int resume;
+  double al_mu;               // warp-per-particle kernel: starting penalty of the multiplier method that carries active state bounds (0 = hand over)
   int half_ipm;               // two-problems-per-warp kernel: interior-point fallback inside the kernel (1) or hand the problem over (0)
   int* xerr;                            // device flag: an exchange timed out (read back by pmpc_sync)
 };

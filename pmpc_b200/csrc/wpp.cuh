@@ -21,6 +21,9 @@
 //
 // Data layout: TILE = 1 (solver.cuh): element e of stage j of particle slot g is arr[(g * N + j) * E + e].
 #pragma once
+#ifdef PMPC_WPP_DEBUG
+#include <cstdio>
+#endif
 #include <cooperative_groups.h>
 
 #include "solver.cuh"
@@ -102,6 +105,7 @@ struct Wpp {
   double *Xc, *Uc;             // iterate being written
   const double *Xpv, *Upv;     // linearisation point
   bool flip;
+  double amu = 0.0;            // current penalty of the multiplier method for state bounds (xbox_terms; 0 = off)
   Team tm;
   double* cred;                // CTA exchange area in shared memory behind the slabs (cred_doubles)
   __host__ __device__ static constexpr int cred_doubles(int W_) { return 16 + (W_ + 1) * ST_COUNT; }
@@ -288,6 +292,25 @@ struct Wpp {
   // Backward sweep of particle slot g over the free stages j = N-1 .. Nc (fused.inl bsweep, generic branch): masked
   // Riccati matrix + vector step; writes the hand-off block.  On return (Nc >= 1) the boundary value function sits in
   // the slab: Pc in O_S, Wc in O_W, Zc in MM_Z, pc in V_WV, zc in U_Z.
+  // Active state bounds ride on the active-set passes by the method of multipliers: a state component whose
+  // multiplier y (pb.yx, y > 0 upper, y < 0 lower bound) is non-zero carries the term (mu/2) (x - b + y/mu)^2, i.e. mu on
+  // the diagonal of the stage cost and y - mu b in its linear term (qx).  The forward sweep then sets
+  // y+ = mu (x + y/mu - clip(x + y/mu, lx, ux)): stationarity holds exactly with y+, the bound violation of an
+  // held component is |y+ - y| / mu (its distance to the bound, on either side) and contracts by about (curvature / mu) per pass; a component whose sign of y
+  // changes counts as an active-set change.  Converged: no change, violation below tolerance (qp()).
+  __device__ __forceinline__ bool xbox_terms(size_t g, int j, double& qx) const {
+    qx = 0.0;
+    if (amu > 0.0) {
+      const double y = pb.yx[gix(g, N, j, NX) + lc];
+      if (y != 0.0) {
+        const double b = (y > 0.0) ? pb.ux[gix(g, N, j, NX) + lc] : pb.lx[gix(g, N, j, NX) + lc];
+        qx = y - amu * b;
+        return true;
+      }
+    }
+    return false;
+  }
+
   __device__ __forceinline__ void bsweep(size_t g) {
     double* sl = slab();
     double *Sm = sl + O_S, *Bm = sl + O_B, *SBWm = sl + O_SBW, *Wm = sl + O_W, *Gm = sl + O_G, *Qb = sl + O_Q;
@@ -323,12 +346,13 @@ struct Wpp {
       return;
     }
     // per-lane stage vectors travel through registers, loaded one stage ahead
-    struct Vec { double c, qref, xp, ub, rref, lo, hi, Rp[(NR + 31) / 32]; signed char act; };
+    struct Vec { double c, qref, xp, ub, rref, lo, hi, Rp[(NR + 31) / 32], qx; signed char act; bool ax; };
     auto load_vec = [&](int j) -> Vec {
       Vec v;
       v.c = pb.c[gix(g, N, j, NX) + lc];
       v.qref = pb.qref[gix(g, N, j, NX) + lc];
       v.xp = Xpv[gix(g, N, j, NX) + lc];
+      v.ax = xbox_terms(g, j, v.qx);
       const int la = l < NU ? l : NU - 1;
       v.ub = Upv[gix(g, N, j, NU) + la];
       v.rref = pb.rref[gix(g, N, j, NU) + la];
@@ -383,10 +407,10 @@ struct Wpp {
       for (int k = 0; k < (NR + 31) / 32; ++k) Rp[k] = vc.Rp[k];
 #pragma unroll
       for (int r = 0; r < NX; ++r) {
-        const double v = qs_at(Qb, r, lc) + Pcol[r];
+        const double v = qs_at(Qb, r, lc) + Pcol[r] + ((r == lc && vc.ax) ? amu : 0.0);
         if (lact) Sm[r * NX + l] = v;
       }
-      const double q_l = -vc.qref - pb.reg_x * vc.xp;
+      const double q_l = -vc.qref - pb.reg_x * vc.xp + vc.qx;
       const double r_l = -vc.rref - pb.reg_u * vc.ub;
       if (lact) cv[l] = vc.c;
       const bool fixed_l = (l < NU) && vc.act != 0;
@@ -646,8 +670,10 @@ struct Wpp {
       }
       __syncwarp();
       double an[VB], gu[VB];
+      double qxj;
+      const double mxj = xbox_terms(g, j, qxj) ? amu : 0.0;
       {
-        const double q0 = -pb.qref[gix(g, N, j, NX) + lc] - pb.reg_x * Xpv[gix(g, N, j, NX) + lc];
+        const double q0 = -pb.qref[gix(g, N, j, NX) + lc] - pb.reg_x * Xpv[gix(g, N, j, NX) + lc] + qxj;
         const int la = l < NU ? l : NU - 1;
         const double r0 = -pb.rref[gix(g, N, j, NU) + la] - pb.reg_u * Upv[gix(g, N, j, NU) + la];
 #pragma unroll
@@ -662,6 +688,8 @@ struct Wpp {
 #pragma unroll
         for (int vb = 0; vb < VB; ++vb) an[vb] = fma(qv, xv[vb * NX + t], an[vb]);
       }
+#pragma unroll
+      for (int vb = 0; vb < VB; ++vb) an[vb] = fma(mxj, xv[vb * NX + lc], an[vb]);
       if (l < NU) {
         for (int t = 0; t < NU; ++t) {
           const double rv = rs_at(Rg, l, t);
@@ -758,7 +786,7 @@ struct Wpp {
     const double* uc = (Nc >= 1) ? pb.uc + (size_t)prob * D : nullptr;  // written by the team leader: read through L2
     const double rdiag = pb.rdiag0[g];
     double dxm = 0.0, dum = 0.0, obj = 0.0, nanf = 0.0, kkt_v = 0.0, uviol = 0.0, xviol = 0.0, changed = 0.0, gscale = 1.0,
-           zscale = 1.0;
+           zscale = 1.0, nact = 0.0;
     struct Vec { double c, xp, xref, qref, lx, ux, ub, uref, rref, lo, hi, kf; signed char act; };
     auto load_vec = [&](int j) -> Vec {
       Vec v;
@@ -864,6 +892,7 @@ struct Wpp {
           uviol = fmax(uviol, fmax(u - hi, lo - u));
           if (u - hi > 0.0 && hi < INFINITY) na = 1;
           else if (u - lo < 0.0 && lo > -INFINITY) na = -1;
+          if (na != 0) nact += 1.0;
         }
         if (na != act) {
           changed += 1.0;
@@ -891,7 +920,26 @@ struct Wpp {
         if (!(xn == xn)) nanf = 1.0;
         zscale = fmax(zscale, fabs(xn));
         gscale = fmax(gscale, fabs(vc.qref + pb.reg_x * vc.xp));
-        if (pb.has_xbox) xviol = fmax(xviol, fmax(xn - vc.ux, vc.lx - xn));
+        if (pb.has_xbox) {
+          xviol = fmax(xviol, fmax(xn - vc.ux, vc.lx - xn));
+          if (amu > 0.0) {  // multiplier update (xbox_terms)
+            const double yo = pb.yx[gix(g, N, j, NX) + l];
+            const double t = xn + yo / amu;
+            double yn = amu * (t - fmin(fmax(t, vc.lx), vc.ux));
+            if ((yn > 0.0) != (yo > 0.0) || (yn < 0.0) != (yo < 0.0)) {
+              changed += 1.0;
+              if (yo == 0.0) {
+                nact += 1.0;
+              } else {
+                // a component that was held and comes off its bound: the pass was stationary with the multiplier
+                // y + mu (x - b) of the wrong sign, not with y+ = 0
+                kkt_v = fmax(kkt_v, fabs(amu * (t - (yo > 0.0 ? vc.ux : vc.lx)) - yn));
+              }
+            }
+            if (yn != 0.0) xviol = fmax(xviol, fabs(yn - yo) / amu);  // held component: distance to its bound, either side
+            if (yn != yo) pb.yx[gix(g, N, j, NX) + l] = yn;
+          }
+        }
       }
       double e2 = 0.0, du = 0.0;
       if (l < NU) {
@@ -945,6 +993,7 @@ struct Wpp {
     st[ST_CHANGED] = warp_max(changed);
     st[ST_GSCALE] = warp_max(gscale);
     st[ST_ZSCALE] = warp_max(zscale);
+    st[ST_XACT] = warp_max(nact);  // (here: components newly put on a bound by this sweep)
   }
 
   // ------------------------------------------------------------------------------------------------------------
@@ -959,6 +1008,10 @@ struct Wpp {
     const int HG = D * D + D;  // consensus payload: columns of sum_i H_i, then sum_i g_i
     double* wacc = (Nc >= 1) ? pb.wscr + ((size_t)blockIdx.x * W + wid) * (size_t)tm.cap : nullptr;
     double* cacc = (Nc >= 1) ? pb.wscr + ((size_t)gridDim.x * W + blockIdx.x) * (size_t)tm.cap : nullptr;
+    int unsettled = 0, settled = 0;
+    amu = (pb.has_xbox && pb.al_mu > 0.0) ? pb.al_mu : 0.0;
+    double base = amu;
+    int need = 2;
     for (int tries = 0;; ++tries) {
       // ---- backward sweeps + consensus terms of this warp's particles
       for (int q = 0; q < ppw; ++q) {
@@ -1066,6 +1119,11 @@ struct Wpp {
       st[ST_KKT] = fmax(st[ST_KKT], kk_c);
       st[ST_UVIOL] = fmax(st[ST_UVIOL], uv_c);
       st[ST_CHANGED] += ch_c;
+#ifdef PMPC_WPP_DEBUG
+      if (prob == 0 && tm.idx == 0 && tid == 0)
+        printf("wpp qp try %d: kkt %.3e uviol %.3e xviol %.3e changed %.0f nact %.0f mu %.0e\n", tries, st[ST_KKT],
+               st[ST_UVIOL], st[ST_XVIOL], st[ST_CHANGED], st[ST_XACT], amu);
+#endif
       if (st[ST_NAN] > 0.0) return 1;
       if (!constrained) {
         cnt[5] += 1;
@@ -1076,8 +1134,40 @@ struct Wpp {
         cnt[5] += 1;
         return 0;
       }
-      if (st[ST_XVIOL] > tol_z) return -1;  // a state bound wants to be active: ADMM (thread-per-particle kernel)
-      if (st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters) return -1;  // stalls or cycles: interior point there
+      if (st[ST_XVIOL] > tol_z) {
+        // a state bound is active.  Multiplier method (xbox_terms): sweep on.  The penalty starts small, where the
+        // undamped active-set iteration over controls and state bounds together is stable, and goes up a notch after
+        // two passes without a change of the set (the violation contracts by about curvature / mu per pass); when the
+        // set starts moving again it goes back down and waits longer before the next raise.  Without the method
+        // (al_mu = 0), or when it does not get there: ADMM in the thread-per-particle kernel
+        if (!(pb.al_mu > 0.0) || tries + 1 >= pb.polish_iters + 150) {
+#ifdef PMPC_WPP_DEBUG
+          if (prob == 0 && tm.idx == 0 && tid == 0) printf("wpp qp: hands over (state bounds) after try %d\n", tries);
+#endif
+          return -1;
+        }
+        if (st[ST_CHANGED] <= 0.0) {
+          unsettled = 0;
+          if (++settled >= need && amu < 3e5) {  // quiet passes at this penalty: one notch up
+            amu *= 10.0;
+            settled = 0;
+          }
+        } else {
+          settled = 0;
+          ++unsettled;
+          if (unsettled >= 2 && amu > base) {  // the set moves again: back down, and more patience before the next raise
+            amu = fmax(amu * 0.1, base);
+            need = min(2 * need, 16);
+            unsettled = 0;
+          } else if (unsettled >= 24 && base > 1.0) {  // cycling at the starting penalty itself: a softer start
+            base = fmax(base / 3.0, 1.0);
+            amu = base;
+            unsettled = 0;
+          }
+        }
+        continue;
+      }
+      if (st[ST_CHANGED] <= 0.0 || tries + 1 >= pb.polish_iters + (amu > 0.0 ? 150 : 0)) return -1;  // stalls or cycles: interior point there
     }
   }
   // ------------------------------------------------------------------------------------------------------------

@@ -68,6 +68,8 @@ if "c4lin" in which:
     M4, N4 = int(os.environ.get("C4_M", 64)), int(os.environ.get("C4_N", 100))
     d, A, Bm = config_c4(M=M4, N=N4, n_lin=8)
     fn = LTV(A, Bm)
+    if "C4_IT" in os.environ:
+        d["max_it"] = int(os.environ["C4_IT"])
     t = time.perf_counter()
     X, U, data = pmpc_b200.solve(fn, **d)
     t = time.perf_counter() - t
@@ -79,3 +81,26 @@ if "c4lin" in which:
                           row_violation=float((val - h).max()), active_rows=int(np.sum(val >= h - 1e-7)),
                           dyn=float(np.abs(f - X[:, 1:]).max()), consensus=bool(np.all(U[:, :1] == U[:1, :1])),
                           umax=float(np.abs(U).max()))), flush=True)
+
+if "c4box" in which:
+    # config 4 at full size with a state box that binds on the second half of the horizon (tests: test_active_state_box_at_c4_shape)
+    d, A, Bm = config_c4(M=64, N=100)
+    d["x0"] = 2.0 * d["x0"]
+    fn = LTV(A, Bm)
+    free = dict(d); free.pop("x_l"); free.pop("x_u")
+    Xf, _, _ = pmpc_b200.solve(fn, **free)
+    half = 50
+    xb = 0.7 * np.abs(Xf[:, 1 + half:]).max()
+    d["x_l"], d["x_u"] = -1e3 * np.ones_like(d["x_l"]), 1e3 * np.ones_like(d["x_u"])
+    d["x_l"][:, half:], d["x_u"][:, half:] = -xb, xb
+    for mu in ("30", "0"):
+        os.environ["PMPC_AL_MU"] = mu
+        for rep in range(2):
+            t = time.perf_counter()
+            X, U, data = pmpc_b200.solve(fn, **d)
+            t = time.perf_counter() - t
+        dev = data["device"]
+        print(json.dumps(dict(case="C4 full size, active state box, PMPC_AL_MU=" + mu, wall_s=t, kernel_ms=dev.get("kernel_ms"), its=len(data["hist"]),
+                              active=int(np.sum(np.abs(X[:, 1 + half:]) >= xb - 1e-8)), xmax_over_box=float(np.abs(X[:, 1 + half:]).max() / xb),
+                              polish=int(np.sum(dev.get("polish_passes", 0))), admm=int(np.sum(dev.get("admm_iters", 0))), status=int(np.max(dev["status"])))), flush=True)
+    os.environ.pop("PMPC_AL_MU")
