@@ -787,17 +787,18 @@ struct Wpp {
     const double rdiag = pb.rdiag0[g];
     double dxm = 0.0, dum = 0.0, obj = 0.0, nanf = 0.0, kkt_v = 0.0, uviol = 0.0, xviol = 0.0, changed = 0.0, gscale = 1.0,
            zscale = 1.0, nact = 0.0;
-    struct Vec { double c, xp, xref, qref, lx, ux, ub, uref, rref, lo, hi, kf; signed char act; };
+    struct Vec { double c, xp, xref, qref, lx, ux, yx, ub, uref, rref, lo, hi, kf; signed char act; };
     auto load_vec = [&](int j) -> Vec {
       Vec v;
       v.c = pb.c[gix(g, N, j, NX) + lc];
       v.xp = Xpv[gix(g, N, j, NX) + lc];
       v.xref = pb.xref[gix(g, N, j, NX) + lc];
       v.qref = pb.qref[gix(g, N, j, NX) + lc];
-      v.lx = -INFINITY; v.ux = INFINITY;
+      v.lx = -INFINITY; v.ux = INFINITY; v.yx = 0.0;
       if (pb.has_xbox) {
         v.lx = pb.lx[gix(g, N, j, NX) + lc];
         v.ux = pb.ux[gix(g, N, j, NX) + lc];
+        if (amu > 0.0) v.yx = pb.yx[gix(g, N, j, NX) + lc];
       }
       const int la = l < NU ? l : NU - 1;
       v.ub = Upv[gix(g, N, j, NU) + la];
@@ -923,7 +924,7 @@ struct Wpp {
         if (pb.has_xbox) {
           xviol = fmax(xviol, fmax(xn - vc.ux, vc.lx - xn));
           if (amu > 0.0) {  // multiplier update (xbox_terms)
-            const double yo = pb.yx[gix(g, N, j, NX) + l];
+            const double yo = vc.yx;
             const double t = xn + yo / amu;
             double yn = amu * (t - fmin(fmax(t, vc.lx), vc.ux));
             if ((yn > 0.0) != (yo > 0.0) || (yn < 0.0) != (yo < 0.0)) {

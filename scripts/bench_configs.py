@@ -1,6 +1,6 @@
 """Times every BASELINE.json config at full size on one GPU through the public API (host arrays in, host
 arrays out) and prints one JSON line per config.  bench.py stays the contract benchmark (C2); this is the
-side table DESIGN.md quotes for C1, C3, C4, C5.     usage: python scripts/bench_configs.py [c1 c3 c4 c5]"""
+side table DESIGN.md quotes for C1, C3, C4, C5.     usage: python scripts/bench_configs.py [c1 c3 c4 c4lin c5]"""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..")); sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
@@ -8,7 +8,7 @@ import pmpc_b200
 from pmpc_b200 import DubinsCar, LTV
 from fixtures import config_c1, config_c3, config_c4, config_c5
 
-which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
+which = sys.argv[1:] or ["c1", "c3", "c4", "c4lin", "c5"]
 
 
 def timed(fn, reps):
@@ -36,13 +36,13 @@ if "c3" in which:
     st = {}
     def run():
         X, U, info, ds = pmpc_b200.solve_batch(p, Q, R, d["x0"], solver=st.get("ds"), reuse_buffers=True,
-                                               chunks=int(os.environ.get("C3_CHUNKS", 16)), **args)
+                                               chunks=int(os.environ.get("C3_CHUNKS", 6)), **args)
         st["ds"] = ds
         return X, U, info, ds
     t, (X, U, info, ds) = timed(run, 3)
     print(json.dumps(dict(config="C3 %d independent Dubins problems N=30 M=16 Nc=1" % B, e2e_s=t, solves_per_s=B / t,
                           kernel_ms=ds.last_kernel_ms(), device_solves_per_s=B / (ds.last_kernel_ms() * 1e-3),
-                          chunks=int(os.environ.get("C3_CHUNKS", 16)),
+                          chunks=int(os.environ.get("C3_CHUNKS", 6)),
                           scp_iters=[int(info["scp_iters"].min()), float(info["scp_iters"].mean()), int(info["scp_iters"].max())],
                           status_ok=bool((info["status"] == 0).all()), consensus=bool(np.all(U[:, :, 0] == U[:, :1, 0])))), flush=True)
 
@@ -74,3 +74,21 @@ for name, cfg, label in (("c4", config_c4, "C4 LTV n=12 m=4 N=100 M=64 Nc=1, sle
                           u_in_box=bool(np.abs(U).max() <= 1 + 1e-9), kkt=max(sd["kkt"] for sd in data["solver_data"]),
                           roofline=dict(bound="fp64", flops_survey_8d=flops, achieved_tflops=flops / (dev["kernel_ms"] * 1e-3) / 1e12,
                                         peak_tflops_measured_here=peak, frac=flops / (dev["kernel_ms"] * 1e-3) / 1e12 / peak))), flush=True)
+
+
+if "c4lin" in which:
+    # BASELINE config 4 exactly as specified: the state box AND n_lin = 8 random linear rows g'[u; x] <= h per (particle, stage).
+    # The rows travel as 8 extra states whose upper bound is h (pmpc_b200/lin_cstrs.py, host SCP loop: one device QP per
+    # iteration, 20-state shape); the device solver carries the active ones by the multiplier method inside the
+    # warp-per-particle kernel (wpp.cuh xbox_terms).
+    d, A, Bm = config_c4(n_lin=8)
+    fn = LTV(A, Bm)
+    t, (X, U, data) = timed(lambda: pmpc_b200.solve(fn, **d), 3)
+    Gu, Gx, h = d["solver_settings"]["lin_cstrs"]
+    val = np.einsum("ijka,ija->ijk", Gu, U) + np.einsum("ijkr,ijr->ijk", Gx, X[:, 1:])
+    f = np.einsum("mjrt,mjt->mjr", A, X[:, :-1]) + np.einsum("mjrt,mjt->mjr", Bm, U)
+    print(json.dumps(dict(config="C4 LTV n=12 m=4 N=100 M=64 Nc=1, slew, u and x boxes, n_lin: 8", n_lin=8, p50_s=t, scp_iters=len(data["hist"]),
+                          resid=data["hist"][-1]["resid"], device_qp_s_mean=float(np.mean(data["t_aff_solve"])),
+                          row_violation=float((val - h).max()), active_rows=int(np.sum(val >= h - 1e-7)), rows=int(h.size),
+                          dyn_violation=float(np.abs(f - X[:, 1:]).max()), consensus=bool(np.all(U[:, :1] == U[:1, :1])),
+                          u_in_box=bool(np.abs(U).max() <= 1 + 1e-9))), flush=True)
