@@ -14,6 +14,7 @@ from .handle import DeviceSolver  # noqa: F401
 from .batch import solve_batch  # noqa: F401
 from ._lib import PmpcError, pinned_copy, pinned_empty  # noqa: F401
 from .problem_struct import Problem  # noqa: F401
+from .lqp_matrices import lqp_generate_problem_matrices  # noqa: F401
 
 """Keyword-compatible arguments in the solver scp solve call (reference pmpc/__init__.py:4-33)."""
 SOLVE_KWS = {

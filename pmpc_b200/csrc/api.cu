@@ -499,9 +499,10 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaMemsetAsync(h->xerr, 0, sizeof(int), h->stream));
   pb.xerr = h->xerr;
   pb.xtimeout_ns = 30ull * 1000000000ull;
-  CU(cudaMalloc(&h->fb, B * sizeof(int)));
-  CU(cudaMemsetAsync(h->fb, 0, B * sizeof(int), h->stream));
+  CU(cudaMalloc(&h->fb, (B + 1) * sizeof(int)));  // (+ the pair queue of the two-problems-per-warp kernel)
+  CU(cudaMemsetAsync(h->fb, 0, (B + 1) * sizeof(int), h->stream));
   pb.fb = h->fb;
+  pb.queue = h->fb + B;
   pb.resume = 0;
   pb.tm = nullptr; pb.wscr = nullptr; pb.tm_cap = 0; pb.tseq0 = 0;
   fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);

@@ -77,19 +77,22 @@
   }
 
   // dynamic shared memory: [table][ring of every warp][mbarriers of every warp]
-  __device__ __forceinline__ void fused_init(unsigned char* smem) {
+  // first: false when a warp of the two-problems-per-warp kernel takes its next pair (the ring and its barriers carry on)
+  __device__ __forceinline__ void fused_init(unsigned char* smem, bool first = true) {
     lane = tid & 31;
     wid = tid >> 5;
     col = g % TILE;
-    rcount = 0;
-    ring = nullptr;
-    bars = nullptr;
     tab = nullptr;
     has_tab = false;
     double* base = reinterpret_cast<double*>(smem);
     const int nw = T >> 5;
     double* tb = base;
-    if (pb.ring) {
+    if (first) {
+      rcount = 0;
+      ring = nullptr;
+      bars = nullptr;
+    }
+    if (first && pb.ring) {
       ring = base + pb.tab_doubles + (size_t)wid * DEPTH * SLOT;
       bars = reinterpret_cast<uint64_t*>(base + pb.tab_doubles + (size_t)nw * DEPTH * SLOT) + wid * DEPTH;
       if (lane == 0) {
@@ -117,7 +120,7 @@
       tab = tb;
       has_tab = true;
     }
-    __syncthreads();
+    if (PPW == 2) __syncwarp(); else __syncthreads();  // (PPW 2: tables, ring and barriers are per half-warp / per warp)
   }
 
   // one field (E doubles at table offset `off`) of the stage's cost / reference / bound data

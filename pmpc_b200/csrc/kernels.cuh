@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(BLK, (BLK <= 128 ? PMPC_MINB : 1)) scp_kernel(
   S.template run<VAR>(pb, dyn_smem);
 }
 
+static __global__ void queue_init_kernel(int* q, int v) { *q = v; }
+
 // Two problems of at most 16 particles per warp (Solver PPW = 2), HW warps per CTA whose sweeps are phase-aligned
 // (Solver::half_phase).
 template <int NX, int NU, int VAR>
@@ -26,7 +28,16 @@ __global__ void __launch_bounds__(128, 2) scp_kernel_half(const __grid_constant_
   __shared__ double red[ST_COUNT];
   __shared__ double red2[RCAP];
   Solver<NX, NU, true, 2> S(pb, red, red2);
-  S.template run_half<VAR>(pb, dyn_smem);
+  // persistent CTAs: the first pair of a warp is its own index, further pairs come from the queue (starts at grid x warps)
+  const int W = (int)(blockDim.x >> 5), npairs = (pb.B + 1) / 2;
+  int pair = (int)blockIdx.x * W + (int)(threadIdx.x >> 5);
+  for (bool first = true; pair < npairs; first = false) {
+    if (!first) S.assign_pair(pair);
+    S.template run_half<VAR>(pb, dyn_smem, first);
+    pair = ((threadIdx.x & 31) == 0) ? atomicAdd(pb.queue, 1) : 0;
+    pair = __shfl_sync(0xffffffffu, pair, 0);
+  }
+  S.half_idle();
 }
 
 template <int NX, int NU, int VAR>
@@ -54,7 +65,11 @@ cudaError_t launch_half(DevProb pb, int blocks, int threads, cudaStream_t stream
     *occ_out = occ * W;  // warps (= pairs of problems) per SM
     return cudaSuccess;
   }
-  const int nblk = (pb.B + 2 * W - 1) / (2 * W);
+  int dev = 0, sms = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nblk = min((pb.B + 2 * W - 1) / (2 * W), occ * sms);  // one wave of resident CTAs; the rest comes through the queue
+  queue_init_kernel<<<1, 1, 0, stream>>>(pb.queue, nblk * W);
   kern<<<nblk, 32 * W, smem, stream>>>(pb);
   return cudaGetLastError();
 }

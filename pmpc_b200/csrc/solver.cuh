@@ -89,6 +89,7 @@ struct DevProb {
   unsigned long long tseq0;
   double* wscr;
   int* fb;
+  int* queue;                 // two-problems-per-warp kernel: next pair of problems to hand out (persistent CTAs)
   int resume;
   double al_mu;               // warp-per-particle kernel: starting penalty of the multiplier method that carries active state bounds (0 = hand over)
   int half_ipm;               // two-problems-per-warp kernel: interior-point fallback inside the kernel (1) or hand the problem over (0)
@@ -212,12 +213,8 @@ struct Solver {
     pvalid = true;
     if (GROUPED && PPW == 2) {
       // two problems per warp: lanes 0-15 own problem 2 b, lanes 16-31 problem 2 b + 1 (Mpad == 16: both in one tile)
-      hl = tid & 15;
-      const int pr = ((int)blockIdx.x * (int)(blockDim.x >> 5)) * 2 + (tid >> 4);  // (tid >> 4) = 2 * warp + half
-      pvalid = pr < pb.B;
-      prob = pvalid ? pr : pb.B - 1;  // an empty half mirrors the last problem and never stores
-      valid = pvalid && hl < pb.M;
-      g = prob * pb.Mpad + min(hl, pb.M - 1);
+      assign_pair((int)blockIdx.x * (int)(blockDim.x >> 5) + (tid >> 5));
+      return;
     } else if (GROUPED) {
       prob = blockIdx.x;
       valid = tid < pb.M;
@@ -230,6 +227,19 @@ struct Solver {
       prob = g;  // M == 1
     }
     s = pb.has_slew ? pb.slew[g] : 0.0;
+  }
+
+  // PPW = 2: this warp takes the pair of problems (2 pair, 2 pair + 1); lanes 0-15 own the first, lanes 16-31 the second
+  // (Mpad == 16: both in one tile).  Resets everything the constructor derives from the problem index.
+  __device__ __forceinline__ void assign_pair(int pair) {
+    hl = tid & 15;
+    const int pr = pair * 2 + ((tid >> 4) & 1);
+    pvalid = pr < pb.B;
+    prob = pvalid ? pr : pb.B - 1;  // an empty half mirrors the last problem and never stores
+    valid = pvalid && hl < pb.M;
+    g = prob * pb.Mpad + min(hl, pb.M - 1);
+    s = pb.has_slew ? pb.slew[g] : 0.0;
+    Xc = pb.X; Uc = pb.U; Xpv = pb.Xp; Upv = pb.Up;
   }
 
   // Helper instance for the warp-per-particle kernel (wpp.cuh): only the CTA-cooperative shared-block routines and the
@@ -1585,10 +1595,10 @@ struct Solver {
 
   // ---- the SCP loop with two problems per warp (PPW == 2; see fused_qp_half) --------------------------------
   template <int VAR>
-  __device__ __forceinline__ void run_half(const DevProb& kp, unsigned char* smem) {
+  __device__ __forceinline__ void run_half(const DevProb& kp, unsigned char* smem, bool first) {
     constexpr bool DUB = (VAR & 1) && NX == 4 && NU == 2;
     constexpr bool LEAN = (VAR & 2) != 0;
-    fused_init(smem);
+    fused_init(smem, first);
     flip = false;
     double st[ST_COUNT];
     for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
@@ -1667,7 +1677,10 @@ struct Solver {
       for (int k = 0; k < 8; ++k) pb.info[(size_t)k * pb.B + prob] = cnt[k];
       pb.fb[prob] = handed ? 1 : 0;
     }
-    // this warp is finished: keep answering the phase barriers of the CTA's other warps (half_phase) until all are
+  }
+
+  // A warp without further work keeps answering the phase barriers of the CTA's other warps (half_phase) until all are done
+  __device__ __forceinline__ void half_idle() {
     while (half_phase(0)) __syncthreads();
   }
 
@@ -1677,7 +1690,8 @@ struct Solver {
   // CTAs per SM at eight different places of a 330 KB kernel the instruction cache — 32 KB — misses all the time:
   // ncu `no_instruction` 2.5 stall cycles per issued instruction.)  All passes have the same length, so nobody waits
   // for long.  Two CTA barriers per pass: start of bsweep (returns whether any warp of the CTA still works) and start of
-  // fsweep; everything else in this mode synchronises at warp level.
+  // fsweep; everything else in this mode synchronises at warp level.  A warp whose pair is finished takes the next pair
+  // from a queue (DevProb::queue, scp_kernel_half) and idles at the barriers only once the queue is empty.
   __device__ __forceinline__ int half_phase(int working) { return __syncthreads_or(working); }
 };
 

@@ -776,6 +776,7 @@ struct Wpp {
   // Rows of A (and of K) are read with a rotated column index, (t + row) mod NX, which keeps lanes that read
   // different rows of an unpadded matrix on different banks.
   __device__ __forceinline__ void fsweep(size_t g, double* st) {
+    const double iamu = amu > 0.0 ? 1.0 / amu : 0.0;
     double* sl = slab();
     double* Qb = sl + O_Q;
     double *xv = sl + O_V + V_X, *dxv = sl + O_V + V_DX;
@@ -925,7 +926,7 @@ struct Wpp {
           xviol = fmax(xviol, fmax(xn - vc.ux, vc.lx - xn));
           if (amu > 0.0) {  // multiplier update (xbox_terms)
             const double yo = vc.yx;
-            const double t = xn + yo / amu;
+            const double t = fma(yo, iamu, xn);
             double yn = amu * (t - fmin(fmax(t, vc.lx), vc.ux));
             if ((yn > 0.0) != (yo > 0.0) || (yn < 0.0) != (yo < 0.0)) {
               changed += 1.0;
@@ -937,7 +938,7 @@ struct Wpp {
                 kkt_v = fmax(kkt_v, fabs(amu * (t - (yo > 0.0 ? vc.ux : vc.lx)) - yn));
               }
             }
-            if (yn != 0.0) xviol = fmax(xviol, fabs(yn - yo) / amu);  // held component: distance to its bound, either side
+            if (yn != 0.0) xviol = fmax(xviol, fabs(yn - yo) * iamu);  // held component: distance to its bound, either side
             if (yn != yo) pb.yx[gix(g, N, j, NX) + l] = yn;
           }
         }

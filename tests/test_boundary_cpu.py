@@ -292,3 +292,40 @@ def test_linear_rows_as_extra_states_equal_direct_rows():
     G[1, 0] = 1.0  # now row 1 couples stage 0's control with stage 4's state
     with pytest.raises(NotImplementedError, match="stage-local"):
         lin_cstrs.from_extra_cstrs([(2, [], 0, G, np.zeros((2, 0)), np.zeros(2), np.zeros(nz), np.zeros(0))], 1, N1, n, m, -1)
+
+
+def test_lqp_generate_problem_matrices_equals_oracle_assembly():
+    """The host-side debugging export (pmpc/scp_mpc.py:66-75 -> main.jl:374-409: P, q, A, b, G, l, u of one sub-problem)
+    against the oracle's independent assembly of the same matrices: every consensus case, slew with and without the
+    u_{-1} term, control and state boxes, absent bounds."""
+    import scipy.sparse as sp
+    from oracle.lqp import build_lqp
+    from pmpc_b200 import lqp_generate_problem_matrices
+
+    rng = np.random.default_rng(5)
+    for (M, N, n, m, Nc, slew, um1, ubox, xbox) in [(3, 5, 4, 2, 2, 0.7, True, True, True), (2, 4, 3, 2, 0, 0.3, True, True, False),
+                                                   (1, 6, 4, 2, 0, 0.0, False, False, True), (4, 3, 2, 1, -1, 0.5, False, True, True),
+                                                   (2, 1, 3, 2, 1, 0.4, True, False, False)]:
+        sym = lambda a: a @ np.swapaxes(a, -1, -2) + np.eye(a.shape[-1])
+        Q, R = sym(rng.standard_normal((M, N, n, n))), sym(rng.standard_normal((M, N, m, m)))
+        f, fx, fu = rng.standard_normal((M, N, n)), rng.standard_normal((M, N, n, n)), rng.standard_normal((M, N, n, m))
+        Xp, Up, Xr, Ur = (rng.standard_normal((M, N, d)) for d in (n, m, n, m))
+        x0 = rng.standard_normal((M, n))
+        kw = dict(reg_x=rng.uniform(0.5, 1.5, M), reg_u=rng.uniform(0.01, 0.1, M), Nc=Nc)
+        if slew:
+            kw["slew_reg"] = np.full(M, slew)
+        if um1:
+            kw.update(slew_reg0=rng.uniform(0.1, 0.5, M), slew_um1=rng.standard_normal((M, m)))
+        if ubox:
+            kw.update(lu=-rng.uniform(0.5, 1, (M, N, m)), uu=rng.uniform(0.5, 1, (M, N, m)))
+        if xbox:
+            kw.update(lx=-rng.uniform(2, 3, (M, N, n)), ux=rng.uniform(2, 3, (M, N, n)))
+        o = build_lqp(x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur, **kw)
+        P, q, A, b, G, l, u = lqp_generate_problem_matrices(x0, f, fx, fu, Xp, Up, Q, R, Xr, Ur, **kw)
+        for mine, ref in ((P, o.P), (A, o.A), (G, o.G)):
+            assert mine.shape == ref.shape and abs(sp.csc_matrix(mine) - ref).max() < 1e-13 if mine.shape[0] else mine.shape == ref.shape
+        assert np.abs(q - o.q).max() < 1e-13 and np.abs(b - o.b).max() < 1e-13
+        assert np.array_equal(l, o.l) and np.array_equal(u, o.u)
+    # the reference wrapper's call shape: no settings, a single particle without the leading axis
+    P, q, A, b, G, l, u = lqp_generate_problem_matrices(x0[0], f[0], fx[0], fu[0], Xp[0], Up[0], Q[0], R[0], Xr[0], Ur[0])
+    assert P.shape == (N * (n + m), N * (n + m)) and A.shape == (N * n, N * (n + m)) and G.shape[0] == 0
