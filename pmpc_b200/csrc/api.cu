@@ -499,10 +499,12 @@ int pmpc_create(pmpc_handle_t* out, int device, size_t B, size_t M, size_t N, si
   CU(cudaMemsetAsync(h->xerr, 0, sizeof(int), h->stream));
   pb.xerr = h->xerr;
   pb.xtimeout_ns = 30ull * 1000000000ull;
-  CU(cudaMalloc(&h->fb, (B + 1) * sizeof(int)));  // (+ the pair queue of the two-problems-per-warp kernel)
-  CU(cudaMemsetAsync(h->fb, 0, (B + 1) * sizeof(int), h->stream));
+  // (+ the pair queue of the two-problems-per-warp kernel, + one byte per particle: any state multiplier non-zero)
+  CU(cudaMalloc(&h->fb, (B + 1) * sizeof(int) + P));
+  CU(cudaMemsetAsync(h->fb, 0, (B + 1) * sizeof(int) + P, h->stream));
   pb.fb = h->fb;
   pb.queue = h->fb + B;
+  pb.xany = reinterpret_cast<unsigned char*>(h->fb + B + 1);
   pb.resume = 0;
   pb.tm = nullptr; pb.wscr = nullptr; pb.tm_cap = 0; pb.tseq0 = 0;
   fill_kernel<<<nblk(B), 256, 0, h->stream>>>(pb.rho, B, pb.rho0);
@@ -692,6 +694,7 @@ int pmpc_set_warm_start(pmpc_handle_t h, const double* X_prev, const double* U_p
   CU(cudaMemsetAsync(pb.yu, 0, N * NU * P * sizeof(double), h->stream));
   CU(cudaMemsetAsync(pb.wx, 0, N * NX * P * sizeof(double), h->stream));
   CU(cudaMemsetAsync(pb.yx, 0, N * NX * P * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(pb.xany, 0, P, h->stream));
   CU(cudaMemsetAsync(pb.act, 0, N * NU * P, h->stream));
   CU(cudaMemsetAsync(pb.actn, 0, N * NU * P, h->stream));
   CU(cudaMemsetAsync(pb.actc, 0, (size_t)pb.B * pb.D + 32, h->stream));

@@ -90,6 +90,7 @@ struct DevProb {
   double* wscr;
   int* fb;
   int* queue;                 // two-problems-per-warp kernel: next pair of problems to hand out (persistent CTAs)
+  unsigned char* xany;        // warp-per-particle kernel: per particle, some state multiplier (yx) is non-zero
   int resume;
   double al_mu;               // warp-per-particle kernel: starting penalty of the multiplier method that carries active state bounds (0 = hand over)
   int half_ipm;               // two-problems-per-warp kernel: interior-point fallback inside the kernel (1) or hand the problem over (0)

@@ -298,9 +298,9 @@ struct Wpp {
   // y+ = mu (x + y/mu - clip(x + y/mu, lx, ux)): stationarity holds exactly with y+, the bound violation of an
   // held component is |y+ - y| / mu (its distance to the bound, on either side) and contracts by about (curvature / mu) per pass; a component whose sign of y
   // changes counts as an active-set change.  Converged: no change, violation below tolerance (qp()).
-  __device__ __forceinline__ bool xbox_terms(size_t g, int j, double& qx) const {
+  __device__ __forceinline__ bool xbox_terms(size_t g, int j, double& qx, bool xa) const {
     qx = 0.0;
-    if (amu > 0.0) {
+    if (xa) {
       const double y = pb.yx[gix(g, N, j, NX) + lc];
       if (y != 0.0) {
         const double b = (y > 0.0) ? pb.ux[gix(g, N, j, NX) + lc] : pb.lx[gix(g, N, j, NX) + lc];
@@ -345,6 +345,7 @@ struct Wpp {
       __syncwarp();
       return;
     }
+    const bool xa = amu > 0.0 && pb.xany[g] != 0;  // some state multiplier of this particle is non-zero (xbox_terms)
     // per-lane stage vectors travel through registers, loaded one stage ahead
     struct Vec { double c, qref, xp, ub, rref, lo, hi, Rp[(NR + 31) / 32], qx; signed char act; bool ax; };
     auto load_vec = [&](int j) -> Vec {
@@ -352,7 +353,7 @@ struct Wpp {
       v.c = pb.c[gix(g, N, j, NX) + lc];
       v.qref = pb.qref[gix(g, N, j, NX) + lc];
       v.xp = Xpv[gix(g, N, j, NX) + lc];
-      v.ax = xbox_terms(g, j, v.qx);
+      v.ax = xbox_terms(g, j, v.qx, xa);
       const int la = l < NU ? l : NU - 1;
       v.ub = Upv[gix(g, N, j, NU) + la];
       v.rref = pb.rref[gix(g, N, j, NU) + la];
@@ -617,6 +618,7 @@ struct Wpp {
     double* xs = pb.fs[MODE_ADMM].K + gix(g, N, 0, NU * NX);  // [Nc][VB][NX]
     const int l = lane;
     const double s = SLEW ? pb.slew[g] : 0.0;
+    const bool xa = amu > 0.0 && pb.xany[g] != 0;
     // u_{j,t} of direction vb: unit vector for v < D, zero for the inhomogeneous direction (and beyond it)
     auto uval = [&](int vb, int j, int t) -> double { return (v0 + vb < D && j >= 0 && j < Nc && j * NU + t == v0 + vb) ? 1.0 : 0.0; };
     auto inhom = [&](int vb) -> bool { return v0 + vb == D; };
@@ -671,7 +673,7 @@ struct Wpp {
       __syncwarp();
       double an[VB], gu[VB];
       double qxj;
-      const double mxj = xbox_terms(g, j, qxj) ? amu : 0.0;
+      const double mxj = xbox_terms(g, j, qxj, xa) ? amu : 0.0;
       {
         const double q0 = -pb.qref[gix(g, N, j, NX) + lc] - pb.reg_x * Xpv[gix(g, N, j, NX) + lc] + qxj;
         const int la = l < NU ? l : NU - 1;
@@ -777,6 +779,8 @@ struct Wpp {
   // different rows of an unpadded matrix on different banks.
   __device__ __forceinline__ void fsweep(size_t g, double* st) {
     const double iamu = amu > 0.0 ? 1.0 / amu : 0.0;
+    const bool xa = amu > 0.0 && pb.xany[g] != 0;
+    bool xnew = false;
     double* sl = slab();
     double* Qb = sl + O_Q;
     double *xv = sl + O_V + V_X, *dxv = sl + O_V + V_DX;
@@ -799,7 +803,7 @@ struct Wpp {
       if (pb.has_xbox) {
         v.lx = pb.lx[gix(g, N, j, NX) + lc];
         v.ux = pb.ux[gix(g, N, j, NX) + lc];
-        if (amu > 0.0) v.yx = pb.yx[gix(g, N, j, NX) + lc];
+        if (xa) v.yx = pb.yx[gix(g, N, j, NX) + lc];
       }
       const int la = l < NU ? l : NU - 1;
       v.ub = Upv[gix(g, N, j, NU) + la];
@@ -924,7 +928,8 @@ struct Wpp {
         gscale = fmax(gscale, fabs(vc.qref + pb.reg_x * vc.xp));
         if (pb.has_xbox) {
           xviol = fmax(xviol, fmax(xn - vc.ux, vc.lx - xn));
-          if (amu > 0.0) {  // multiplier update (xbox_terms)
+          if (amu > 0.0 && (xa || xn > vc.ux || xn < vc.lx)) {  // multiplier update (xbox_terms); nothing to do while no
+                                                                  // multiplier of the particle is set and x is inside
             const double yo = vc.yx;
             const double t = fma(yo, iamu, xn);
             double yn = amu * (t - fmin(fmax(t, vc.lx), vc.ux));
@@ -939,7 +944,10 @@ struct Wpp {
               }
             }
             if (yn != 0.0) xviol = fmax(xviol, fabs(yn - yo) * iamu);  // held component: distance to its bound, either side
-            if (yn != yo) pb.yx[gix(g, N, j, NX) + l] = yn;
+            if (yn != yo) {
+              pb.yx[gix(g, N, j, NX) + l] = yn;
+              xnew = true;
+            }
           }
         }
       }
@@ -985,6 +993,7 @@ struct Wpp {
       }
       __syncwarp();  // Qb / Rs staging free for the next stage
     }
+    if (!xa && __any_sync(0xffffffffu, xnew) && lane == 0) pb.xany[g] = 1;
     st[ST_DX] = sqrt(dxm);
     st[ST_DU] = sqrt(dum);
     st[ST_OBJ] = warp_sum(obj);
