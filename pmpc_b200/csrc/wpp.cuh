@@ -408,9 +408,10 @@ struct Wpp {
       for (int k = 0; k < (NR + 31) / 32; ++k) Rp[k] = vc.Rp[k];
 #pragma unroll
       for (int r = 0; r < NX; ++r) {
-        const double v = qs_at(Qb, r, lc) + Pcol[r] + ((r == lc && vc.ax) ? amu : 0.0);
+        const double v = qs_at(Qb, r, lc) + Pcol[r];
         if (lact) Sm[r * NX + l] = v;
       }
+      if (vc.ax && lact) Sm[lc * NX + l] += amu;  // (rare: a held state component of this stage, xbox_terms)
       const double q_l = -vc.qref - pb.reg_x * vc.xp + vc.qx;
       const double r_l = -vc.rref - pb.reg_u * vc.ub;
       if (lact) cv[l] = vc.c;
