@@ -5,6 +5,7 @@
 #ifndef PMPC_MINB
 #define PMPC_MINB 2
 #endif
+#include <cstdlib>
 namespace pmpc {
 
 // One CTA per problem, one thread per particle (GROUPED) or one thread per single-particle
@@ -23,7 +24,7 @@ static __global__ void queue_init_kernel(int* q, int v) { *q = v; }
 // Two problems of at most 16 particles per warp (Solver PPW = 2), HW warps per CTA whose sweeps are phase-aligned
 // (Solver::half_phase).
 template <int NX, int NU, int VAR>
-__global__ void __launch_bounds__(128, 2) scp_kernel_half(const __grid_constant__ DevProb pb) {
+__global__ void __launch_bounds__(256, 1) scp_kernel_half(const __grid_constant__ DevProb pb) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ double red[ST_COUNT];
   __shared__ double red2[RCAP];
@@ -47,14 +48,18 @@ cudaError_t launch_half(DevProb pb, int blocks, int threads, cudaStream_t stream
   auto kern = scp_kernel_half<NX, NU, VAR>;
   const int one = (S::table_doubles(pb.N) + 15) / 16 * 16;  // one uniform cost table per half-warp problem
   const int want_ring = pb.ring;
-  // warps per CTA: as many as keep 8 warps resident per SM (the register file's limit) — 4 (two CTAs per SM), else 2, 1
-  int W = 4, occ = 0;
+  // warps per CTA: as many as keep 8 warps resident per SM (the register file's limit) — 4 (two CTAs per SM), else 2, 1;
+  // the cost tables are dropped (global reads instead) when they do not fit beside the ring at that occupancy
+  const char* we = getenv("PMPC_HALF_W");
+  int W = we ? atoi(we) : 4, occ = 0;
+  if (W != 8 && W != 4 && W != 2 && W != 1) W = 4;
   size_t smem = 0;
   for (;; W >>= 1) {
-    pb.tab_doubles = ((size_t)2 * W * one * 8 <= 100 * 1024 / (4 / W)) ? 2 * W * one : 0;
+    const size_t cap = (227 * 1024 - 2048) / (size_t)max(1, 8 / W) - 1024;
     size_t ring_bytes = (size_t)S::ring_doubles(W) * 8 + (size_t)W * S::DEPTH * 8;
     pb.ring = (S::RING_SHAPE && want_ring) ? 1 : 0;
     if (!pb.ring) ring_bytes = 0;
+    pb.tab_doubles = ((size_t)2 * W * one * 8 + ring_bytes <= cap) ? 2 * W * one : 0;
     smem = (size_t)pb.tab_doubles * 8 + ring_bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
