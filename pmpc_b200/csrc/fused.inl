@@ -1528,10 +1528,10 @@
 
   template <bool SLEW, bool UBOX, bool DUB>
   __device__ __forceinline__ int fused_qp_half(const DevProb& pb, unsigned char* smem, double* st, long long* cnt, bool active) {
-    double pc[NX], zc[NU], keep[ST_COUNT];
+    double pc[NX], zc[NU];
+    double k_dx = 0.0, k_du = 0.0, k_obj = 0.0, k_kkt = 0.0, k_gs = 1.0, k_nan = 0.0;  // what the SCP loop reads of the accepted pass
     const bool constrained = pb.has_ubox || pb.has_xbox;
-    for (int k = 0; k < ST_COUNT; ++k) keep[k] = st[k] = 0.0;
-    keep[ST_GSCALE] = keep[ST_ZSCALE] = 1.0;
+    for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
     const bool base_valid = this->valid;
     enum { RUN = 0, WANT_IPM = 1, DONE = 2 };
     int state = active ? RUN : DONE, status = 0, tries = 0;
@@ -1575,7 +1575,7 @@
         }
         ++tries;
         if (state == DONE)
-          for (int k = 0; k < ST_COUNT; ++k) keep[k] = st[k];
+          k_dx = st[ST_DX], k_du = st[ST_DU], k_obj = st[ST_OBJ], k_kkt = st[ST_KKT], k_gs = st[ST_GSCALE], k_nan = st[ST_NAN];
       }
       if (__any_sync(0xffffffffu, state == WANT_IPM)) {
         const int rc = ipm_solve_half<SLEW, UBOX, DUB>(pb, smem, st, cnt, scale, state == WANT_IPM, base_valid);
@@ -1583,8 +1583,9 @@
           if (rc == 1) {
             status = 1;
             state = DONE;
-            for (int k = 0; k < ST_COUNT; ++k) keep[k] = 0.0;
-            keep[ST_NAN] = 1.0;
+            k_dx = k_du = k_obj = k_kkt = 0.0;
+            k_gs = 1.0;
+            k_nan = 1.0;
           } else {
             state = RUN;
             ipm_used = true;
@@ -1596,7 +1597,9 @@
     }
     this->valid = base_valid;
     wr_en = true;
-    for (int k = 0; k < ST_COUNT; ++k) st[k] = keep[k];
+    for (int k = 0; k < ST_COUNT; ++k) st[k] = 0.0;
+    st[ST_DX] = k_dx, st[ST_DU] = k_du, st[ST_OBJ] = k_obj, st[ST_KKT] = k_kkt, st[ST_GSCALE] = k_gs, st[ST_NAN] = k_nan;
+    st[ST_ZSCALE] = 1.0;
     return status;
   }
 
