@@ -329,3 +329,71 @@ def test_lqp_generate_problem_matrices_equals_oracle_assembly():
     # the reference wrapper's call shape: no settings, a single particle without the leading axis
     P, q, A, b, G, l, u = lqp_generate_problem_matrices(x0[0], f[0], fx[0], fu[0], Xp[0], Up[0], Q[0], R[0], Xr[0], Ur[0])
     assert P.shape == (N * (n + m), N * (n + m)) and A.shape == (N * n, N * (n + m)) and G.shape[0] == 0
+
+
+def test_batch_grouping_signature_separates_what_must_not_share_a_launch():
+    """`solve_problems` groups problem dictionaries by `batch._sig`; everything the group's single launch decides once has
+    to be part of it (an LTV model with and one without an affine term, device-solver settings, cone / smoothing requests,
+    shapes, stop rule), and whatever `solve` itself routes to its host loop must not be grouped at all (-> None)."""
+    from pmpc_b200 import LTV, DubinsCar
+    from pmpc_b200.batch import _sig
+
+    M, N, n, m = 2, 5, 4, 2
+    A, Bm, c = np.tile(np.eye(n), (M, N, 1, 1)), np.zeros((M, N, n, m)), np.ones((M, N, n))
+    base = dict(Q=np.tile(np.eye(n), (M, N, 1, 1)), R=np.tile(np.eye(m), (M, N, 1, 1)), x0=np.ones((M, n)),
+                u_l=-np.ones((M, N, m)), u_u=np.ones((M, N, m)), solver_settings=dict(solver="osqp", Nc=1))
+    lin, aff = dict(base, f_fx_fu_fn=LTV(A, Bm)), dict(base, f_fx_fu_fn=LTV(A, Bm, c))
+    assert _sig(lin) is not None and _sig(lin) == _sig(dict(base, f_fx_fu_fn=LTV(2 * A, Bm)))  # same structure, other numbers
+    assert _sig(lin) != _sig(aff)
+    assert _sig(lin) != _sig(dict(lin, solver_settings=dict(solver="osqp", Nc=1, b200=dict(fused=0))))
+    assert _sig(lin) != _sig(dict(lin, solver_settings=dict(solver="ecos", Nc=1)))
+    assert _sig(lin) != _sig(dict(lin, solver_settings=dict(solver="osqp", Nc=1, smooth_alpha=10.0)))
+    assert _sig(lin) != _sig(dict(lin, solver_settings=dict(solver="osqp", Nc=2)))
+    assert _sig(lin) != _sig(dict(lin, max_it=7)) and _sig(lin) != _sig(dict(lin, res_tol=1e-3))
+    assert _sig(lin) != _sig(dict(lin, x_l=-np.ones((M, N, n)), x_u=np.ones((M, N, n))))
+    assert _sig(lin) != _sig(dict(lin, reg_x=2.0)) and _sig(lin) != _sig(dict(lin, slew_rate=0.5))
+    car = dict(base, f_fx_fu_fn=DubinsCar(np.array([[1.0, 1.0, 0.3]] * M)))
+    assert _sig(car) is not None and _sig(car) != _sig(lin)
+    for host_only in (dict(solver_settings=dict(solver="osqp", Nc=1, host_loop=True)), dict(debug=True), dict(return_min_viol=True),
+                      dict(time_limit=5.0), dict(filter_method="AA"), dict(lin_cost_fn=lambda X, U, problems: (0 * X, 0 * U)),
+                      dict(extra_cstrs_fns=[lambda X, U, problems: []]), dict(f_fx_fu_fn=lambda X, U: (X, None, None))):
+        assert _sig(dict(lin, **host_only)) is None, host_only
+
+
+def test_extra_cstrs_tuples_are_mapped_to_stage_rows_or_refused_by_name():
+    """`lin_cstrs.from_extra_cstrs` reads the reference's 8-tuples `(l, q, e, G_left, G_right, h, c_left, c_right)`
+    (README.md:219-239 of the reference, variable vector z = [controls; states]): stage-local linear rows become
+    (Gu, Gx, h) per (particle, stage); cones, new variables, cost augmentation and rows that couple stages are refused."""
+    from pmpc_b200.lin_cstrs import from_extra_cstrs
+
+    M, N, n, m, Nc = 2, 3, 2, 1, 1
+    Nf = N - Nc
+    nu_tot = Nc * m + M * Nf * m
+    nz = nu_tot + M * N * n
+    ucol = lambda i, j: j * m if j < Nc else Nc * m + i * Nf * m + (j - Nc) * m
+    xcol = lambda i, j: nu_tot + i * N * n + j * n
+    G = np.zeros((2, nz))
+    G[0, ucol(1, 2)], G[0, xcol(1, 2) + 1] = 0.5, -2.0   # particle 1, stage 2: 0.5 u - 2 x_1 <= 3
+    G[1, xcol(0, 0)] = 1.0                               # particle 0, stage 0: x_0 <= 4
+    tup = (2, [], 0, G, np.zeros((2, 0)), np.array([3.0, 4.0]), np.zeros(nz), np.zeros(0))
+    Gu, Gx, h = from_extra_cstrs([tup], M, N, n, m, Nc)
+    assert Gu.shape == (M, N, 1, m) and Gx.shape == (M, N, 1, n) and h.shape == (M, N, 1)
+    assert Gu[1, 2, 0, 0] == 0.5 and Gx[1, 2, 0, 1] == -2.0 and h[1, 2, 0] == 3.0
+    assert Gx[0, 0, 0, 0] == 1.0 and h[0, 0, 0] == 4.0
+    assert np.isinf(h).sum() == M * N - 2 and np.count_nonzero(Gu) == 1 and np.count_nonzero(Gx) == 2
+    bad = {
+        "cone": (0, [3], 0, np.zeros((3, nz)), np.zeros((3, 0)), np.zeros(3), np.zeros(nz), np.zeros(0)),
+        "new variables": (1, [], 0, G[:1], np.ones((1, 2)), np.ones(1), np.zeros(nz), np.zeros(0)),
+        "cost augmentation": (1, [], 0, G[:1], np.zeros((1, 0)), np.ones(1), np.ones(nz), np.zeros(0)),
+    }
+    for what, t in bad.items():
+        with pytest.raises(NotImplementedError, match=what.split()[0]):
+            from_extra_cstrs([t], M, N, n, m, Nc)
+    G2 = np.zeros((1, nz))
+    G2[0, xcol(0, 0)], G2[0, xcol(0, 1)] = 1.0, 1.0  # couples two stages
+    with pytest.raises(NotImplementedError, match="stage"):
+        from_extra_cstrs([(1, [], 0, G2, np.zeros((1, 0)), np.ones(1), np.zeros(nz), np.zeros(0))], M, N, n, m, Nc)
+    G3 = np.zeros((1, nz))
+    G3[0, ucol(0, 0)] = 1.0  # a row on the shared control of a multi-particle problem
+    with pytest.raises(NotImplementedError, match="shared"):
+        from_extra_cstrs([(1, [], 0, G3, np.zeros((1, 0)), np.ones(1), np.zeros(nz), np.zeros(0))], M, N, n, m, Nc)
