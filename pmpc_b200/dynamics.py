@@ -12,6 +12,14 @@ import numpy as np
 class BuiltinDynamics:
     kind = "affine"
 
+    def __getstate__(self):
+        """A model is its description: the device handle a call may have cached stays behind when it is pickled
+        (problems travel to ``pmpc_b200.remote`` workers as pickles)."""
+        state = dict(self.__dict__)
+        if "_solver" in state:
+            state["_solver"] = None
+        return state
+
 
 class DubinsCar(BuiltinDynamics):
     """Unicycle car of reference ``tests/dubins_car.py:48-90``; ``p = (v_scale, w_scale, T)`` of

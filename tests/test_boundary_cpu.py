@@ -243,22 +243,6 @@ def test_user_dynamics_wrapper_compiles_for_sm100a_without_a_gpu():
     assert rc != 0 and "user_dynamics.cu" in log and "undeclared_symbol" in log
 
 
-def test_remote_shim_keeps_the_client_surface():
-    """pmpc_b200.remote: the functions a client of the reference's task farm calls (pmpc/remote.py:100-130, 324-343,
-    391-398) exist with the same parameters; server management is a no-op; None problems map to None results."""
-    from pmpc_b200 import remote
-
-    assert list(inspect.signature(remote.solve_problems).parameters) == [
-        "problems", "verbose", "randomize_assignment", "rescan", "max_solve_time", "redis_config"]
-    assert list(inspect.signature(remote.solve_problem).parameters) == ["problem", "solve_fn"]
-    assert list(inspect.signature(remote.start_server).parameters) == ["port", "verbose", "redis_config"]
-    assert remote.solve.blocking is True and remote.start_server() is None
-    assert remote.solve_problems([None, None]) == [None, None]
-    seen = {}
-    remote.solve_problem(dict(f_fx_fu_fn="f", Q="Q", R="R", x0="x0", max_it=3), solve_fn=lambda *a, **k: seen.update(a=a, k=k))
-    assert seen["a"] == ("f", "Q", "R", "x0") and seen["k"] == dict(max_it=3, verbose=True)
-
-
 def test_linear_rows_as_extra_states_equal_direct_rows():
     """pmpc_b200/lin_cstrs.py (host logic, no GPU): the reference's `extra_cstrs` tuples are parsed into stage-local rows,
     and the sub-problem augmented with the row values as extra states (whose box is the constraint) has the same minimiser
