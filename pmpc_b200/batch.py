@@ -15,6 +15,9 @@ from .dynamics import BuiltinDynamics, DubinsCar, LTV, UserDynamics
 from .handle import DeviceSolver
 
 
+_CACHED_BATCH_MAX_UNITS = 1 << 18  # particle-stages (B*M*N); beyond it a batch handle is released after the call
+
+
 def _sig(p: Dict[str, Any]):
     dyn = p.get("f_fx_fu_fn")
     if not isinstance(dyn, (DubinsCar, LTV, UserDynamics)):
@@ -221,7 +224,18 @@ def solve_batched(problems: List[Dict[str, Any]], verbose: bool = False, device:
             for i in idxs:
                 results[i] = solve(**dict(problems[i], verbose=verbose))
             continue
-        res, _ = solve_same_shape([problems[i] for i in idxs], device=device)
+        # a control loop re-solves the same batch every step (and a farm worker sees the same batch size again and
+        # again): moderate batches keep their handle (device slab, streams, pinned buffers) in solve's cache
+        group = [problems[i] for i in idxs]
+        Q0 = np.asarray(group[0]["Q"])
+        M = 1 if np.asarray(group[0]["x0"]).ndim == 1 else Q0.shape[0]
+        N, n, m = Q0.shape[-3], Q0.shape[-1], np.asarray(group[0]["R"]).shape[-1]
+        cached = None
+        if 1 < len(group) * M * N <= _CACHED_BATCH_MAX_UNITS:
+            from .scp_mpc import _cached_solver
+
+            cached = _cached_solver(M, N, n, m, (group[0].get("solver_settings") or {}).get("Nc", -1), device, B=len(group))
+        res, _ = solve_same_shape(group, device=device, solver=cached)
         for i, r in zip(idxs, res):
             results[i] = r
     return results

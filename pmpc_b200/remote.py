@@ -365,6 +365,14 @@ def _as_problem(args: tuple, kwargs: dict) -> Dict[str, Any]:
     return dict(bound, **extra)
 
 
+def _portable(ret):
+    """A result leaves the process: the device handle ``solve`` parks in ``data["device_solver"]`` (for callers that
+    keep solving the same problem in place) is process-local and stays behind."""
+    if isinstance(ret, tuple) and len(ret) == 3 and isinstance(ret[2], dict) and "device_solver" in ret[2]:
+        return ret[0], ret[1], {k: v for k, v in ret[2].items() if k != "device_solver"}
+    return ret
+
+
 def _server_info(worker: "Worker") -> Dict[str, Any]:
     return dict(hostname=HOSTNAME, pid=os.getpid(), ports=list(worker.ports), device=os.getenv("CUDA_VISIBLE_DEVICES"),
                 requests=worker.requests, cycles=worker.cycles, coalesced_calls=worker.coalesced_calls,
@@ -469,7 +477,7 @@ class Worker:
             replies[i] = self._run(method, args, kwargs)
         for fr, ret in zip(frames, replies):
             try:
-                payload = pack_reply(ret)
+                payload = pack_reply(_portable(ret))
             except Exception:
                 payload = pack_reply(traceback.format_exc())
             self.sock.send_multipart(fr[:-1] + [payload])

@@ -141,12 +141,12 @@ _HANDLE_CACHE_MAX = 8
 _HANDLE_LOCK = threading.Lock()
 
 
-def _cached_solver(M, N, xdim, udim, Nc, device=-1):
-    key = (int(device), M, N, xdim, udim, Nc)
+def _cached_solver(M, N, xdim, udim, Nc, device=-1, B=1):
+    key = (int(device), M, N, xdim, udim, Nc) + ((int(B),) if B != 1 else ())
     with _HANDLE_LOCK:
         ds = _HANDLE_CACHE.pop(key, None)
         if ds is None or not ds._h.value:
-            ds = DeviceSolver(M, N, xdim, udim, Nc, device=device)
+            ds = DeviceSolver(M, N, xdim, udim, Nc, B=B, device=device)
         _HANDLE_CACHE[key] = ds
         while len(_HANDLE_CACHE) > _HANDLE_CACHE_MAX:
             _, old = _HANDLE_CACHE.popitem(last=False)

@@ -208,6 +208,18 @@ def test_worker_answers_calls_errors_and_garbage():
         assert remote.call("echo", HOST, h.port, True, "still alive") == (("still alive",), {})
 
 
+def test_results_leave_the_worker_without_process_local_handles():
+    """`solve` parks its device handle in data["device_solver"]; that key stays on the worker.  A result that cannot be
+    pickled at all is answered with the pickling traceback."""
+    methods = dict(solve=lambda *a, **k: (np.ones(2), np.zeros(1), dict(hist=[1], device_solver=threading.Lock())),
+                   tune_scp=lambda *a, **k: threading.Lock())
+    with Hosted(methods=methods).start() as h:
+        X, U, data = remote.call("solve", HOST, h.port, True)
+        assert np.array_equal(X, np.ones(2)) and data == dict(hist=[1])
+        err = remote.call("tune_scp", HOST, h.port, True)
+        assert isinstance(err, str) and "Traceback" in err and "pickle" in err.lower()
+
+
 def test_waiting_solve_requests_become_one_batch_call():
     """K solve requests that are waiting when the worker looks (K ports of one ROUTER socket) reach `batch_solve` as ONE
     list, in the keyword form solve_problems takes; other methods in the same drain are served individually; replies go
@@ -417,6 +429,11 @@ def test_reference_client_unmodified_talks_to_this_worker(tmp_path):
 
 
 # -- GPU -------------------------------------------------------------------------------------------
+def solved(ret):
+    assert not isinstance(ret, str), "the worker answered with an error:\n" + ret
+    return ret
+
+
 def _dubins_problems(K, rng, N=12, M=4):
     from pmpc_b200 import DubinsCar
 
@@ -451,12 +468,13 @@ def test_gpu_worker_serves_solves_bit_identical_to_in_process_calls(gpu, worker_
         remote.solve.hostname, remote.solve.port = HOST, port
         try:
             fn = dubins.make_f_fx_fu_fn(p)
-            Xw, Uw, dw = remote.solve(fn, Q, R, x0, **kw)
+            Xw, Uw, dw = solved(remote.solve(fn, Q, R, x0, **kw))
             Xl, Ul, dl = pmpc_b200.solve(fn, Q, R, x0, **kw)
             assert np.array_equal(Xw, Xl) and np.array_equal(Uw, Ul)
             assert [h["obj"] for h in dw["hist"]] == [h["obj"] for h in dl["hist"]]
             car = pmpc_b200.DubinsCar(p=p, eps=1e-6)
-            Xw, Uw, dw = remote.solve(car, Q, R, x0, **kw)
+            Xw, Uw, dw = solved(remote.solve(car, Q, R, x0, **kw))
+            assert "device_solver" not in dw and dw["hist"]
             Xl, Ul, dl = pmpc_b200.solve(car, Q, R, x0, **kw)
             assert np.array_equal(Xw, Xl) and np.array_equal(Uw, Ul)
         finally:
@@ -467,7 +485,7 @@ def test_gpu_worker_serves_solves_bit_identical_to_in_process_calls(gpu, worker_
         local = pmpc_b200.solve_problems(probs[:-1])
         assert out[-1] is None
         exact = 0
-        for (Xw, Uw, dw), (Xl, Ul, dl) in zip(out[:-1], local):
+        for (Xw, Uw, dw), (Xl, Ul, dl) in zip(map(solved, out[:-1]), local):
             # the worker's launches group the problems differently from the one local batch: same iterates (the
             # kernels are batch-composition independent, test_batched_equals_individual), compared to 1e-12 here
             assert np.abs(Xw - Xl).max() <= 1e-12 and np.abs(Uw - Ul).max() <= 1e-12
@@ -479,3 +497,31 @@ def test_gpu_worker_serves_solves_bit_identical_to_in_process_calls(gpu, worker_
         assert info["coalesced_calls"] >= 1 and info["largest_batch"] >= 2, info
     finally:
         srv.stop()
+
+
+@pytest.mark.gpu
+def test_repeated_batches_reuse_one_handle_without_carrying_state(gpu):
+    """solve_problems keeps the handle of a moderate batch in solve's cache (a control loop, or a farm worker, sends the
+    same batch shape again and again).  A second batch of the same shape but other data, no control bounds and a slew
+    penalty, solved on the re-used handle, equals the same batch solved on a fresh handle bit for bit."""
+    import pmpc_b200
+    from pmpc_b200 import scp_mpc
+
+    A = _dubins_problems(6, np.random.default_rng(11))
+    B = _dubins_problems(6, np.random.default_rng(12))
+    for p in B:
+        del p["u_l"], p["u_u"]
+        p.update(slew_rate=0.3, X_prev=0.05 * np.ones_like(p["X_ref"]))
+    scp_mpc.clear_handle_cache()
+    pmpc_b200.solve_problems(A)
+    keys = [k for k in scp_mpc._HANDLE_CACHE if len(k) == 7 and k[-1] == 6]
+    assert len(keys) == 1, list(scp_mpc._HANDLE_CACHE)
+    handle = scp_mpc._HANDLE_CACHE[keys[0]]
+    reused = pmpc_b200.solve_problems(B)
+    assert scp_mpc._HANDLE_CACHE[keys[0]] is handle
+    scp_mpc.clear_handle_cache()
+    fresh = pmpc_b200.solve_problems(B)
+    for (Xr, Ur, dr), (Xf, Uf, df) in zip(reused, fresh):
+        assert np.array_equal(Xr, Xf) and np.array_equal(Ur, Uf) and len(dr["hist"]) == len(df["hist"])
+    single = pmpc_b200.solve(**B[2])
+    assert np.array_equal(single[0], fresh[2][0]) and np.array_equal(single[1], fresh[2][1])
