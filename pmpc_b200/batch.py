@@ -6,6 +6,7 @@ problem per CPU worker, B problems of identical shape become B CTAs of the same 
 """
 from __future__ import annotations
 
+import gc
 import time
 from typing import Any, Dict, List, Optional
 
@@ -99,18 +100,30 @@ def solve_same_shape(problems: List[Dict[str, Any]], device: int = -1, solver: O
     its_max = int(info["scp_iters"].max())
     h = ds.hist(max(its_max, 1))
     x0s = stack("x0", (M, n))
+    # result records in the reference's format (one dict per SCP iteration, scp_mpc.py:409-417).  Built from Python lists:
+    # indexing NumPy scalars one by one costs more host time per problem than the solve kernel does at C3's batch size
+    obj, resid, admm = h["obj"].T.tolist(), h["resid"].T.tolist(), h["admm_iters"].T.tolist()
+    status, iters = info["status"].tolist(), info["scp_iters"].tolist()
+    dev_keys, dev_cols = list(info), [v.tolist() for v in info.values()]
+    reg_x, reg_u = float(p0.get("reg_x", 1.0)), float(p0.get("reg_u", 1e-2))
+    Xfull = np.concatenate([x0s[:, :, None, :], X], -2)
     out = []
-    for b in range(B):
-        if int(info["status"][b]) & 1:
-            out.append((None, None, None))
-            continue
-        its = int(info["scp_iters"][b])
-        hist = [dict(it=i + 1, elaps=wall * (i + 1) / its, obj=float(h["obj"][i, b]), resid=float(h["resid"][i, b]),
-                     reg_x=float(p0.get("reg_x", 1.0)), reg_u=float(p0.get("reg_u", 1e-2))) for i in range(its)]
-        data = dict(hist=hist, solver_data=[dict(admm_iters=int(h["admm_iters"][i, b])) for i in range(its)],
-                    t_aff_solve=[wall / its] * its, device={k: int(v[b]) for k, v in info.items()})
-        Xb = np.concatenate([x0s[b][:, None, :], X[b]], -2)
-        out.append((Xb[0], U[b][0], data) if single else (Xb, U[b], data))
+    collecting = gc.isenabled()
+    gc.disable()  # ~120 small acyclic dicts per problem: the cycle collector's passes over them were a third of this loop
+    try:
+        for b in range(B):
+            if int(status[b]) & 1:
+                out.append((None, None, None))
+                continue
+            its = int(iters[b])
+            hist = [{"it": i, "elaps": wall * i / its, "obj": o, "resid": r, "reg_x": reg_x, "reg_u": reg_u}
+                    for i, o, r in zip(range(1, its + 1), obj[b], resid[b])]
+            data = dict(hist=hist, solver_data=[{"admm_iters": int(a)} for a in admm[b][:its]],
+                        t_aff_solve=[wall / its] * its, device={k: int(c[b]) for k, c in zip(dev_keys, dev_cols)})
+            out.append((Xfull[b, 0], U[b, 0], data) if single else (Xfull[b], U[b], data))
+    finally:
+        if collecting:
+            gc.enable()
     return out, ds
 
 

@@ -36,6 +36,7 @@ import ctypes.util
 import gc
 import inspect
 import os
+import pickle
 import random
 import signal
 import sys
@@ -158,7 +159,13 @@ def unpack_request(msg: bytes) -> Tuple[str, tuple, dict]:
 
 
 def pack_reply(ret: Any) -> bytes:
-    return COMPRESSION_MODULE.compress(serializer.dumps(ret))
+    """``zstd(pickle(result))``.  Results are plain data (arrays, dicts of numbers, strings): the C pickler writes the
+    same stream cloudpickle would, several times faster; cloudpickle is the fallback for anything it refuses."""
+    try:
+        blob = pickle.dumps(ret, protocol=serializer.DEFAULT_PROTOCOL)
+    except Exception:
+        blob = serializer.dumps(ret)
+    return COMPRESSION_MODULE.compress(blob)
 
 
 def unpack_reply(msg: bytes) -> Any:
@@ -192,20 +199,25 @@ class _SocketOwner:
     term = destroy
 
 
-def call(method: str, hostname: Optional[str] = None, port: Optional[int] = None, blocking: bool = True, *args,
-         **kwargs) -> Union[Any, Callable]:
-    """Call one of the worker's methods (``remote.py:59-97``).  ``blocking``: returns the result.  Otherwise returns a
-    poll function that yields ``"NOT_ARRIVED_YET"`` until the reply is there; ``fn.sock`` / ``fn.ctx`` as in the
-    reference, for callers that give up on a worker."""
+def _request_socket(hostname, port, blocking: bool):
+    """A REQ socket to one worker address (``remote.py:76-87``: two-second send / receive limits on non-blocking calls)."""
     _need_wire()
-    hostname = hostname if hostname is not None else DEFAULT_HOSTNAME
-    port = port if port is not None else DEFAULT_PORT
     sock = zmq.Context.instance().socket(zmq.REQ)
     sock.setsockopt(zmq.LINGER, 0)
     if not blocking:
         sock.setsockopt(zmq.RCVTIMEO, 2000)
         sock.setsockopt(zmq.SNDTIMEO, 2000)
-    sock.connect("tcp://%s:%s" % (hostname, port))
+    sock.connect("tcp://%s:%s" % (hostname if hostname is not None else DEFAULT_HOSTNAME,
+                                  port if port is not None else DEFAULT_PORT))
+    return sock
+
+
+def call(method: str, hostname: Optional[str] = None, port: Optional[int] = None, blocking: bool = True, *args,
+         **kwargs) -> Union[Any, Callable]:
+    """Call one of the worker's methods (``remote.py:59-97``).  ``blocking``: returns the result.  Otherwise returns a
+    poll function that yields ``"NOT_ARRIVED_YET"`` until the reply is there; ``fn.sock`` / ``fn.ctx`` as in the
+    reference, for callers that give up on a worker."""
+    sock = _request_socket(hostname, port, blocking)
     sock.send(pack_request(method, args, kwargs))
     if blocking:
         try:
@@ -254,6 +266,13 @@ def solve_problem_remote(args: Tuple[Dict[str, Any], str, int, bool]):
     return solve_problem(problem, solve_fn=lambda *a, **k: call("solve", hostname, port, blocking, *a, **k))
 
 
+def _solve_request(problem: Dict[str, Any]) -> bytes:
+    """The bytes ``solve_problem_remote`` sends for this problem."""
+    sent = dict()
+    solve_problem(problem, solve_fn=lambda *a, **k: sent.update(args=a, kwargs=k))
+    return pack_request("solve", sent["args"], sent["kwargs"])
+
+
 WORKER_ADDRS: List[Tuple[str, Any]] = []
 LAST_WORKER_SCAN = time.time() - 60.0
 
@@ -300,7 +319,9 @@ def solve_problems(problems: List[Optional[Dict[str, Any]]], verbose: bool = Fal
                    rescan: bool = True, max_solve_time: float = 20.0, redis_config: Optional[Dict[str, Any]] = None):
     """``pmpc.remote.solve_problems`` (``remote.py:391-452``): solutions in the order of ``problems``, ``None`` for a
     ``None`` entry.  One job at a time per worker address; a worker that holds a job longer than ``max_solve_time`` is
-    dropped and its job goes back to the queue; when every worker is gone the registry is scanned again.
+    dropped and its job goes back to the queue; when every worker is gone the registry is scanned again.  Same requests
+    on the wire as the reference's scheduler; the sockets are kept per address for the duration of the call (a REQ socket
+    costs more to create than a problem costs to pack) and replies are awaited with a poller instead of a sleep loop.
 
     With no worker address at all (``WORKER_ADDRS`` empty and nothing in redis) the reference waits forever; here the
     problems are solved by THIS process's GPU as one batch (``pmpc_b200.solve_problems``)."""
@@ -312,55 +333,71 @@ def solve_problems(problems: List[Optional[Dict[str, Any]]], verbose: bool = Fal
     results: Dict[int, Any] = {i: None for i, p in enumerate(problems) if p is None}
     queue = collections.deque(i for i, p in enumerate(problems) if p is not None)
     idle: List[Tuple[str, Any]] = list(WORKER_ADDRS)
-    busy: Dict[Tuple[str, Any], Tuple[int, Callable, float]] = dict()
+    socks: Dict[Tuple[str, Any], Any] = dict()  # one REQ socket per worker address, kept for the whole call
+    busy: Dict[Any, Tuple[Tuple[str, Any], int, float]] = dict()  # socket -> (address, problem index, send time)
+    poller = zmq.Poller()
     bar = None
     if verbose:
         from tqdm import tqdm
 
         bar = tqdm(total=len(problems), initial=len(results))
     lonely_since = None
-    while len(results) < len(problems):
-        progressed = False
-        for addr, (idx, poll, t0) in list(busy.items()):
-            ret = poll()
-            if isinstance(ret, str) and ret == NOT_ARRIVED_YET:
-                if time.time() - t0 > max_solve_time:
-                    print("PMPC Worker %s is broken, we will use another worker." % (addr,))
-                    poll.ctx.destroy()
-                    del busy[addr]
+    try:
+        while len(results) < len(problems):
+            if randomize_assignment:
+                random.shuffle(idle)
+            while idle and queue:
+                addr, idx = idle.pop(), queue.pop()
+                sock = socks.get(addr)
+                if sock is None:
+                    sock = socks[addr] = _request_socket(addr[0], addr[1], blocking=False)
+                    poller.register(sock, zmq.POLLIN)
+                try:
+                    sock.send(_solve_request(problems[idx]))
+                except zmq.Again:  # the send queue of a worker that is not there is full
                     queue.append(idx)
-                continue
-            results[idx] = ret
-            del busy[addr]
-            idle.append(addr)
-            progressed = True
-            if bar is not None:
-                bar.update(1)
-        if randomize_assignment:
-            random.shuffle(idle)
-        while idle and queue:
-            addr, idx = idle.pop(), queue.pop()
-            busy[addr] = (idx, solve_problem_remote((problems[idx], addr[0], addr[1], False)), time.time())
-            progressed = True
-        if not busy and not idle and queue:  # every worker was dropped
-            lonely_since = lonely_since or time.time()
-            if time.time() - lonely_since > max(max_solve_time, 1.0):
-                raise RuntimeError("pmpc_b200.remote.solve_problems: no PMPC worker answers (%d problems left)" % len(queue))
-            print("All PMPC workers deemed dead, rescanning all PMPC workers.")
-            rescan_workers(force=True, redis_config=redis_config)
-            idle = list(WORKER_ADDRS) if redis is not None else []
-            time.sleep(0.2)
-        elif not progressed:
-            time.sleep(2e-4)
-    if bar is not None:
-        bar.close()
+                    poller.unregister(sock)
+                    socks.pop(addr).close(0)
+                    continue
+                busy[sock] = (addr, idx, time.time())
+            for sock, _ in poller.poll(5 if busy else 0):
+                if sock in busy:
+                    addr, idx, _ = busy.pop(sock)
+                    results[idx] = unpack_reply(sock.recv())
+                    idle.append(addr)
+                    if bar is not None:
+                        bar.update(1)
+            now = time.time()
+            for sock, (addr, idx, t0) in list(busy.items()):
+                if now - t0 > max_solve_time:
+                    print("PMPC Worker %s is broken, we will use another worker." % (addr,))
+                    del busy[sock]
+                    poller.unregister(sock)
+                    socks.pop(addr).close(0)
+                    queue.append(idx)
+            if not busy and not idle and queue:  # every worker was dropped
+                lonely_since = lonely_since or time.time()
+                if time.time() - lonely_since > max(max_solve_time, 1.0):
+                    raise RuntimeError("pmpc_b200.remote.solve_problems: no PMPC worker answers (%d problems left)" % len(queue))
+                print("All PMPC workers deemed dead, rescanning all PMPC workers.")
+                rescan_workers(force=True, redis_config=redis_config)
+                idle = list(WORKER_ADDRS) if redis is not None else []
+                time.sleep(0.2)
+    finally:
+        for sock in socks.values():
+            sock.close(0)
+        if bar is not None:
+            bar.close()
     return [results[i] for i in range(len(problems))]
 
 
 # -- worker ----------------------------------------------------------------------------------------
+_SOLVE_SIGNATURE = inspect.signature(scp_mpc.scp_solve)
+
+
 def _as_problem(args: tuple, kwargs: dict) -> Dict[str, Any]:
     """The keyword form (what ``solve_problems`` takes) of a ``solve(*args, **kwargs)`` request."""
-    bound = inspect.signature(scp_mpc.scp_solve).bind(*args, **kwargs).arguments
+    bound = _SOLVE_SIGNATURE.bind(*args, **kwargs).arguments
     extra = bound.pop("extra_kw", {})
     return dict(bound, **extra)
 
@@ -475,14 +512,14 @@ class Worker:
                     print(traceback.format_exc())
         for i, (method, args, kwargs) in decoded.items():
             replies[i] = self._run(method, args, kwargs)
+        self.requests += len(frames)  # (before the replies leave: a client may ask for server_info right after its answer)
+        self.cycles += 1
         for fr, ret in zip(frames, replies):
             try:
                 payload = pack_reply(_portable(ret))
             except Exception:
                 payload = pack_reply(traceback.format_exc())
             self.sock.send_multipart(fr[:-1] + [payload])
-        self.requests += len(frames)
-        self.cycles += 1
         return len(frames)
 
 

@@ -5,7 +5,7 @@ batched launches.  Prints one JSON line per slot count, with the in-process batc
 it.  The wire numbers are bounded by the client's and worker's Python (pickle + zstd + ZeroMQ per problem), not by
 the GPU: they say what an unchanged farm client gets, the device-resident figures are bench.py's.
 
-    python scripts/remote_farm_bench.py [K] [slots ...]
+    python scripts/remote_farm_bench.py [K] [slots ...]        (FARM_WINDOW_MS=<ms>[,<ms>...]: the worker's collecting window)
 """
 import json
 import os
@@ -64,25 +64,28 @@ def main():
     local = pmpc_b200.solve_problems(probs)
     t_local = time.time() - t
     print(json.dumps(dict(path="in-process batch", problems=K, seconds=round(t_local, 4), solves_per_s=round(K / t_local, 1))), flush=True)
+    windows = [float(w) for w in os.getenv("FARM_WINDOW_MS", "1").split(",")]
     for slots in slot_counts:
-        port = free_port_run(slots)
-        srv = remote.Server(port, None, slots=slots)
-        try:
-            assert srv.wait_ready(300.0), "worker did not come up"
-            remote.WORKER_ADDRS[:] = [("127.0.0.1", port + i) for i in range(slots)]
-            remote.solve_problems(probs[: 2 * slots], rescan=False, max_solve_time=120.0)  # warm
-            before = remote.call("server_info", "127.0.0.1", port, True)
-            t = time.time()
-            out = remote.solve_problems(probs, rescan=False, max_solve_time=120.0)
-            dt = time.time() - t
-            info = remote.call("server_info", "127.0.0.1", port, True)
-            worst = max(float(np.abs(a[1] - b[1]).max()) for a, b in zip(out, local))
-            print(json.dumps(dict(path="wire, 1 client process -> 1 GPU worker", slots=slots, problems=K, seconds=round(dt, 4),
-                                  solves_per_s=round(K / dt, 1), worker_cycles=info["cycles"] - before["cycles"],
-                                  coalesced_calls=info["coalesced_calls"] - before["coalesced_calls"],
-                                  largest_batch=info["largest_batch"], max_abs_diff_vs_in_process=worst)), flush=True)
-        finally:
-            srv.stop()
+        for window_ms in windows:
+            port = free_port_run(slots)
+            srv = remote.Server(port, None, slots=slots, batch_window=1e-3 * window_ms)
+            try:
+                assert srv.wait_ready(300.0), "worker did not come up"
+                remote.WORKER_ADDRS[:] = [("127.0.0.1", port + i) for i in range(slots)]
+                remote.solve_problems(probs[: 2 * slots], rescan=False, max_solve_time=120.0)  # warm
+                before = remote.call("server_info", "127.0.0.1", port, True)
+                t = time.time()
+                out = remote.solve_problems(probs, rescan=False, max_solve_time=120.0)
+                dt = time.time() - t
+                info = remote.call("server_info", "127.0.0.1", port, True)
+                worst = max(float(np.abs(a[1] - b[1]).max()) for a, b in zip(out, local))
+                print(json.dumps(dict(path="wire, 1 client process -> 1 GPU worker", slots=slots, window_ms=window_ms, problems=K,
+                                      seconds=round(dt, 4), solves_per_s=round(K / dt, 1),
+                                      worker_cycles=info["cycles"] - before["cycles"],
+                                      coalesced_calls=info["coalesced_calls"] - before["coalesced_calls"],
+                                      largest_batch=info["largest_batch"], max_abs_diff_vs_in_process=worst)), flush=True)
+            finally:
+                srv.stop()
 
 
 if __name__ == "__main__":
