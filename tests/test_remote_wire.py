@@ -381,6 +381,22 @@ def test_spawned_worker_on_a_box_without_a_device_fails_loudly():
         cold.stop()
 
 
+def test_worker_launcher_refuses_to_start_without_a_device():
+    """`python -m pmpc_b200.remote` (the counterpart of `python -m pmpc.remote`, remote.py:456-517) on a box without a
+    CUDA device: exits with the library's error instead of starting workers that could not serve."""
+    from pmpc_b200 import _lib
+
+    try:
+        have_gpu = _lib.device_count() > 0
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        pytest.skip("this test is about a box without a device")
+    r = subprocess.run([sys.executable, "-m", "pmpc_b200.remote", "--port", str(free_ports(1)), "--worker-num", "0"],
+                       env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, cwd="/tmp", timeout=120)
+    assert r.returncode != 0 and ("no CUDA device" in r.stderr or "PmpcError" in r.stderr), r.stderr[-2000:]
+
+
 REF_CLIENT = r"""
 import sys, json, numpy as np
 import pmpc.remote as ref                       # the UNMODIFIED reference client (PYTHONPATH = baseline/_ref)
