@@ -641,10 +641,15 @@ class Server:
             self.old_signal_handler = None
         self.process.start()
 
-    def stop(self):
+    def stop(self, timeout: float = 30.0):
+        """Ask the serving loop to leave and wait for the process; one that does not leave within ``timeout`` (stuck in
+        a solve) is killed, so that stopping never hangs the caller."""
         if self.process is not None:
             self.exit_flag.value = True
-            self.process.join()
+            self.process.join(timeout)
+            if self.process.is_alive():
+                self.process.kill()
+                self.process.join()
             self.process.close()
             self.process = self.exit_flag = self.status_flag = None
 
