@@ -206,6 +206,17 @@ def test_worker_answers_calls_errors_and_garbage():
             assert "Traceback" in remote.unpack_reply(s.recv())
             s.close(0)
         assert remote.call("echo", HOST, h.port, True, "still alive") == (("still alive",), {})
+        # remote.solve / remote.tune_scp go where their attributes point (remote.py:100-120)
+        saved = [(f, f.hostname, f.port, f.blocking) for f in (remote.solve, remote.tune_scp)]
+        try:
+            remote.solve.hostname, remote.solve.port = HOST, h.port
+            X2, U2, _ = remote.solve(p["f_fx_fu_fn"], p["Q"], p["R"], p["x0"], reg_x=p["reg_x"])
+            assert np.array_equal(X2, Xe) and np.array_equal(U2, Ue)
+            remote.tune_scp.hostname, remote.tune_scp.port, remote.tune_scp.blocking = HOST, h.port, False
+            assert "Unsupported method 'tune_scp'" in wait_all([remote.tune_scp(1, 2)])[0]
+        finally:
+            for f, a, b, c in saved:
+                f.hostname, f.port, f.blocking = a, b, c
 
 
 def test_results_leave_the_worker_without_process_local_handles():
@@ -481,20 +492,20 @@ def test_gpu_worker_serves_solves_bit_identical_to_in_process_calls(gpu, worker_
         d, p = config_c1()
         kw = dict(d)
         Q, R, x0 = kw.pop("Q"), kw.pop("R"), kw.pop("x0")
-        remote.solve.hostname, remote.solve.port = HOST, port
+        remote.solve.hostname, remote.solve.port, remote.solve.blocking = HOST, port, False  # polled: a dead worker fails the test, not hangs it
         try:
             fn = dubins.make_f_fx_fu_fn(p)
-            Xw, Uw, dw = solved(remote.solve(fn, Q, R, x0, **kw))
+            Xw, Uw, dw = solved(wait_all([remote.solve(fn, Q, R, x0, **kw)], 180.0)[0])
             Xl, Ul, dl = pmpc_b200.solve(fn, Q, R, x0, **kw)
             assert np.array_equal(Xw, Xl) and np.array_equal(Uw, Ul)
             assert [h["obj"] for h in dw["hist"]] == [h["obj"] for h in dl["hist"]]
             car = pmpc_b200.DubinsCar(p=p, eps=1e-6)
-            Xw, Uw, dw = solved(remote.solve(car, Q, R, x0, **kw))
+            Xw, Uw, dw = solved(wait_all([remote.solve(car, Q, R, x0, **kw)], 180.0)[0])
             assert "device_solver" not in dw and dw["hist"]
             Xl, Ul, dl = pmpc_b200.solve(car, Q, R, x0, **kw)
             assert np.array_equal(Xw, Xl) and np.array_equal(Uw, Ul)
         finally:
-            remote.solve.hostname, remote.solve.port = remote.DEFAULT_HOSTNAME, remote.DEFAULT_PORT
+            remote.solve.hostname, remote.solve.port, remote.solve.blocking = remote.DEFAULT_HOSTNAME, remote.DEFAULT_PORT, True
         probs = _dubins_problems(24, np.random.default_rng(5)) + [None]
         worker_addrs[:] = [(HOST, port + i) for i in range(slots)]
         out = remote.solve_problems(probs, rescan=False, max_solve_time=120.0)
@@ -508,7 +519,7 @@ def test_gpu_worker_serves_solves_bit_identical_to_in_process_calls(gpu, worker_
             assert len(dw["hist"]) == len(dl["hist"]) and abs(dw["hist"][-1]["obj"] - dl["hist"][-1]["obj"]) <= 1e-9
             exact += int(np.array_equal(Xw, Xl) and np.array_equal(Uw, Ul))
         print("wire farm: %d of %d results bit-identical to the local batch" % (exact, len(local)))
-        info = remote.call("server_info", HOST, port, True)
+        info = wait_all([remote.call("server_info", HOST, port, False)], 30.0)[0]
         assert info["requests"] >= 27 and info["pid"] != os.getpid()
         assert info["coalesced_calls"] >= 1 and info["largest_batch"] >= 2, info
     finally:
