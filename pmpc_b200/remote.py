@@ -734,10 +734,17 @@ def main(argv=None):
     for key in ("host", "port", "password"):
         if getattr(args, "redis_" + key) is not None:
             redis_config[key] = getattr(args, "redis_" + key)
-    for i in range(args.worker_num):
-        start_server(args.port + i * args.slots, verbose=args.verbose, redis_config=redis_config, device=i % n_gpu,
-                     slots=args.slots, batch_window=1e-3 * args.batch_window_ms)
+    # Ctrl-C and `kill` both end in the orderly shutdown below, also when the launcher was started with SIGINT ignored
+    # (a background job of a non-interactive shell)
+    def interrupt(sig, frame):
+        raise KeyboardInterrupt
+
+    signal.signal(signal.SIGINT, signal.default_int_handler)
+    signal.signal(signal.SIGTERM, interrupt)
     try:
+        for i in range(args.worker_num):
+            start_server(args.port + i * args.slots, verbose=args.verbose, redis_config=redis_config, device=i % n_gpu,
+                         slots=args.slots, batch_window=1e-3 * args.batch_window_ms)
         while True:
             for port, server in list(SERVERS.items()):
                 if not server.is_alive():
@@ -751,9 +758,12 @@ def main(argv=None):
                         start_server(new_port, verbose=args.verbose, redis_config=redis_config, **options)
             time.sleep(1.0)
     except KeyboardInterrupt:
-        for port, server in SERVERS.items():
-            print("Stopping server on port %d" % port)
-            server.stop()
+        pass
+    finally:
+        signal.signal(signal.SIGINT, signal.SIG_IGN)  # a second Ctrl-C must not cut the shutdown short
+        for port in sorted(SERVERS):
+            print("Stopping server on port %d" % port, flush=True)
+            SERVERS.pop(port).stop()
 
 
 if __name__ == "__main__":

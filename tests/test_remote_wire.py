@@ -552,3 +552,47 @@ def test_repeated_batches_reuse_one_handle_without_carrying_state(gpu):
         assert np.array_equal(Xr, Xf) and np.array_equal(Ur, Uf) and len(dr["hist"]) == len(df["hist"])
     single = pmpc_b200.solve(**B[2])
     assert np.array_equal(single[0], fresh[2][0]) and np.array_equal(single[1], fresh[2][1])
+
+
+@pytest.mark.gpu
+def test_worker_launcher_serves_on_every_slot_and_stops_on_sigint(gpu, tmp_path):
+    """`python -m pmpc_b200.remote --worker-num 0 --slots 3` (remote.py:456-517 with GPUs in the place of cores): one worker
+    per visible GPU comes up warmed, owns its GPU, answers on all of its slot ports, solves, and the launcher stops its
+    workers and exits cleanly on SIGINT."""
+    import signal
+
+    import pmpc_b200
+
+    slots = 3
+    port = free_ports(slots * gpu)
+    log = tmp_path / "launcher.log"
+    out = lambda: log.read_text()[-3000:]
+    with open(log, "w") as fh:
+        proc = subprocess.Popen([sys.executable, "-m", "pmpc_b200.remote", "--port", str(port), "--worker-num", "0", "--slots",
+                                 str(slots)], env=dict(os.environ, PYTHONPATH=ROOT, PYTHONUNBUFFERED="1"), cwd="/tmp", stdout=fh,
+                                stderr=subprocess.STDOUT)
+    try:
+        info, t0 = None, time.time()
+        while info is None and time.time() - t0 < 240.0:
+            assert proc.poll() is None, "launcher exited: " + out()
+            poll = remote.call("server_info", HOST, port + slots - 1, False)
+            try:
+                info = wait_all([poll], 2.0)[0]
+            except AssertionError:
+                poll.ctx.destroy()
+        assert info is not None, "no worker answered within 240 s: " + out()
+        assert info["ports"] == [port + i for i in range(slots)] and info["device"] == "0" and info["pid"] != proc.pid
+        car = pmpc_b200.DubinsCar(p=np.array([1.0, 1.0, 0.3]))
+        args = (car, np.tile(np.eye(4), (15, 1, 1)), np.tile(1e-2 * np.eye(2), (15, 1, 1)), np.ones(4))
+        kw = dict(u_l=-np.ones((15, 2)), u_u=np.ones((15, 2)), max_it=20, res_tol=1e-6, verbose=False,
+                  solver_settings=dict(solver="osqp"))
+        Xw, Uw, _ = solved(wait_all([remote.call("solve", HOST, port + 1, False, *args, **kw)], 120.0)[0])
+        Xl, Ul, _ = pmpc_b200.solve(*args, **kw)
+        assert Xw.shape == (16, 4) and np.array_equal(Xw, Xl) and np.array_equal(Uw, Ul)
+        proc.send_signal(signal.SIGINT)
+        assert proc.wait(90) == 0, out()
+        assert "Stopping server on port %d" % port in out()
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+            proc.wait(30)
