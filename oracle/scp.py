@@ -47,9 +47,11 @@ def aff_solve(
     )
     args = (x0, f, fx, fu, X_prev, U_prev, Q, R, X_ref, U_ref)
     if lin_rows is not None:
-        assert qp == "exact"
+        assert callable(qp) or qp == "exact"
         kw["lin_rows"] = lin_rows
-    if qp == "exact":
+    if callable(qp):  # another treatment of the same sub-problem (oracle.barrier: the cone route's smoothed box rows)
+        X, U, info = qp(*args, **kw)
+    elif qp == "exact":
         X, U, info = _lqp_exact(*args, **kw)
     else:
         X, U, info = _lqp_osqp(*args, osqp_settings=osqp_settings, **kw)
