@@ -20,10 +20,10 @@
  *                       stage-interleaved order with the consensus block last instead of AMD.
  *   split / bookkeeping lqp_utils.jl:395-423; pmpc/scp_mpc.py:337-428 (loop, max_res, obj, stop rule)
  *
- * Parity status: **parity unpinned** for the convex sub-problem (the reference stores no golden outputs for
- * it and Julia/OSQP are absent from the image).  This file is pinned against the NumPy oracle (oracle/lqp.py, osqp_port.py, dubins.py, scp.py)
- * (tests/test_oracle_cpu.py), which in turn is pinned against the reference's own Dubins model and SCP loop
- * executed here (tests/golden/).
+ * Parity status: pinned through the NumPy oracle (oracle/lqp.py, osqp_port.py, dubins.py, scp.py; tests/test_oracle_cpu.py),
+ * which is pinned against the reference's own Dubins model and SCP loop executed here (tests/golden/) and against the
+ * iteration tables the reference's real solver stack printed into its notebooks (4 digits;
+ * tests/test_reference_notebook_traces.py).  No full-precision output of the reference's solver exists.
  *
  * Layouts are NumPy C-order as `pmpc.solve` sees them: vectors (M,N,d), matrices (M,N,rows,cols).
  */

@@ -80,19 +80,6 @@ def test_exact_oracle_reproduces_the_reference_table_of_gpu_solver_notebook():
     assert np.abs(U).max() <= 1.0 + 1e-9 and np.isclose(np.abs(U).max(), 1.0)  # the box is active in this problem
 
 
-def test_osqp_restatement_reproduces_the_reference_table_of_gpu_solver_notebook():
-    """The same table through the OTHER oracle solver, the reference's OSQP route restated at OSQP's default settings
-    (`oracle/osqp_port.py`; eps_abs = eps_rel = 1e-3): it follows the table as closely as that tolerance allows — obj
-    within 2e-3, resid within 7 % over the first 12 rows — which is also how far the reference's own `solver="osqp"` runs
-    sit from its cone-solver runs."""
-    fn = dubins.make_f_fx_fu_fn(np.array([1.0, 1.0, 0.3]), eps=1e-3)
-    d = base()
-    X, U, data = oscp.scp_solve(fn, d.pop("Q"), d.pop("R"), d.pop("x0"), **d, **dict(GPU_SOLVER, max_it=12), qp="osqp")
-    obj, resid = hist(data)
-    ref_obj, ref_resid = table("gpu_solver_cpu_check")
-    assert rel(obj, ref_obj[:12]).max() <= 2e-3 and rel(resid, ref_resid[:12]).max() <= 7e-2
-
-
 def test_barrier_oracle_reproduces_the_reference_table_with_slew_and_smoothing():
     """tests/root_testing.ipynb cell 4: T = 1 car, slew penalty 1e2, log-barrier box (alpha = 0.1), 20 iterations down to
     resid 1.022e-05 — every printed obj and resid at print precision."""
