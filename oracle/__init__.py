@@ -11,11 +11,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``pmpc_b200`` never does (it fails loudly when the CUDA library is missing).
 
 Parity status: **pinned on the reference's own printed output** — the reference's tests hold no golden vectors and
-neither Julia nor OSQP / ECOS exist in the build image, but three notebooks of the reference repository
+neither Julia nor OSQP / ECOS exist in the build image, but notebooks of the reference repository
 keep the iteration tables its real solver stack (PMPC.jl behind ``pmpc.solve``) printed for fully specified,
 deterministic problems; ``tests/test_reference_notebook_traces.py`` reproduces them row by row (``obj``, ``resid`` at the 4
 printed digits): a hard-box single-particle run with ``oracle.lqp`` inside ``oracle.scp`` (and with the CUDA path), a
-single-particle run with a slew penalty and a 20-particle consensus run through ``oracle.barrier`` (those runs smoothed
+single-particle run with a slew penalty, one with zero control cost and a 20-particle consensus run through
+``oracle.barrier`` (those runs smoothed
 the box rows with the cone route's log barrier; same matrices, different treatment of the box rows).  The pin is as
 sharp as the printed digits: 5e-4 relative, no full-precision vector of the reference's solver exists anywhere.
 Beside it:

@@ -23,6 +23,10 @@ SOURCES = dict(
                          "solve(**problem) of cell 3 with p = problem['P'] = ones(N), i.e. v_scale = w_scale = T = 1 (car of cell 2, eps 1e-6): N 20, "
                          "Q = I, R = 1e-2 I, x0 = 1, |u| <= 1, reg_x = reg_u = 1, slew_rate 1e2, max_it 20, res_tol 1e-12, "
                          "solver_settings = dict(smooth_alpha=1e-1, solver='ecos')"),
+    demo_cost_cpu=("tests/demo_cost_jax.ipynb", 3,
+                   "first table of the cell = solve_cpu (pmpc.solve) on cells 1-2: tests/dubins_car.py model (eps 1e-6, p = (1, 1, 0.3)), "
+                   "N 30, Q = I, R = 0, x0 = 1, X_ref = 0.4, warm start 0, |u| <= 1, default reg_x 1 / reg_u 1e-2, max_it 100, "
+                   "solver_settings = dict(smooth_cstr='logbarrier', smooth_alpha=1e3)"),
     root_testing_consensus=("tests/root_testing.ipynb", 11,
                             "solve(**problem) of cell 10: M = 20 particles, P_i = linspace(0.7, 1, M) of shape (M, N, 1) so that p[..., 1] and "
                             "p[..., 2] clamp to p[..., 0] (JAX indexing): v_scale = w_scale = T = P_i; Nc 5, slew_rate 1e2, reg_x = reg_u = 1, "
@@ -37,6 +41,8 @@ def table(path, cell):
     for line in text.splitlines():
         if re.match(r"\| \d{4} \|", line):
             cols = [c.strip() for c in line.strip("|").split("|")]
+            if int(cols[0]) != len(rows) + 1:  # a second table in the same cell (another solver): not ours
+                break
             rows.append(dict(it=int(cols[0]), obj=float(cols[2]), resid=float(cols[3]), reg_x=float(cols[4]), reg_u=float(cols[5])))
     return rows
 

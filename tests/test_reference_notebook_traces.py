@@ -9,8 +9,9 @@ its exact minimiser and the SCP bookkeeping to agree with the reference, iterati
 
 * `examples/gpu_solver.ipynb` cell 18 (one particle, hard control box): 50 rows.  The hard-box sub-problem is the one
   the CUDA path solves: the exact CPU oracle AND `pmpc_b200.solve` on the GPU are compared with the table.
-* `tests/root_testing.ipynb` cell 4 (one particle, slew penalty 1e2, `smooth_alpha = 1e-1`) and cell 11 (M = 20 particles,
-  consensus over the first 5 controls, slew penalty, `smooth_alpha = 1`): those runs smoothed the box rows with the cone
+* `tests/root_testing.ipynb` cell 4 (one particle, slew penalty 1e2, `smooth_alpha = 1e-1`), cell 11 (M = 20 particles,
+  consensus over the first 5 controls, slew penalty, `smooth_alpha = 1`) and `tests/demo_cost_jax.ipynb` cell 3 (N = 30,
+  R = 0, X_ref = 0.4, `smooth_alpha = 1e3`): those runs smoothed the box rows with the cone
   route's log barrier, so they are compared with `oracle.barrier`, the barrier variant on top of the SAME matrices
   `oracle.lqp.build_lqp` assembles for the QP — they pin everything but the treatment of the box rows.
 
@@ -99,6 +100,24 @@ def test_barrier_oracle_reproduces_the_reference_table_with_slew_and_smoothing()
         _, _, other = oscp.scp_solve(fn, d.pop("Q"), d.pop("R"), d.pop("x0"), **d, **dict(dict(reg_x=1.0, reg_u=1.0, slew_rate=1e2,
                                      max_it=1, res_tol=1e-12), **change), qp=qp)
         assert rel(other["hist"][0]["obj"], ref_obj[0]) > 0.1
+
+
+def test_barrier_oracle_follows_the_reference_table_with_zero_control_cost():
+    """tests/demo_cost_jax.ipynb cell 3 (its `solve_cpu` table): N = 30, R = 0 (the proximal weight reg_u = 1e-2 is the
+    only curvature in the controls), X_ref = 0.4, default weights, barrier alpha = 1e3.  A looser pin, by the reference's
+    own doing: it linearises with autograd through the eps = 1e-6 formula at U_prev = 0, where that formula loses ~6
+    digits, and iterations 2-3 inherit the noise.  Same 26 iterations; obj at print precision from the 4th
+    row on (the converged cost 0.6955 included) and within 3 % before; resid within 5 % on every row."""
+    ref_obj, ref_resid = table("demo_cost_cpu")
+    fn = dubins.make_f_fx_fu_fn(np.array([1.0, 1.0, 0.3]), eps=1e-6)
+    Z = lambda d: np.zeros((30, d))
+    X, U, data = oscp.scp_solve(fn, np.tile(np.eye(n), (30, 1, 1)), np.zeros((30, m, m)), np.ones(n), 0.4 * np.ones((30, n)), Z(m), Z(n),
+                                Z(m), u_l=-np.ones((30, m)), u_u=np.ones((30, m)), max_it=100,
+                                qp=lambda *a, **k: barrier.barrier_lqp_solve(*a, smooth_alpha=1e3, **k))
+    obj, resid = hist(data)
+    assert len(obj) == len(ref_obj) == 26
+    assert rel(obj[3:], ref_obj[3:]).max() <= 3e-4 and rel(obj[:3], ref_obj[:3]).max() <= 3e-2
+    assert rel(resid, ref_resid).max() <= 5e-2
 
 
 def test_barrier_oracle_reproduces_the_reference_consensus_table():
