@@ -564,11 +564,12 @@ def test_worker_launcher_serves_on_every_slot_and_stops_on_sigint(gpu, tmp_path)
     import pmpc_b200
 
     slots = 3
-    port = free_ports(slots * gpu)
+    workers = "0" if gpu == 1 else "2"  # 0 = one per visible GPU; on a multi-GPU box two workers are enough for the test
+    port = free_ports(slots * min(gpu, 2))
     log = tmp_path / "launcher.log"
     out = lambda: log.read_text()[-3000:]
     with open(log, "w") as fh:
-        proc = subprocess.Popen([sys.executable, "-m", "pmpc_b200.remote", "--port", str(port), "--worker-num", "0", "--slots",
+        proc = subprocess.Popen([sys.executable, "-m", "pmpc_b200.remote", "--port", str(port), "--worker-num", workers, "--slots",
                                  str(slots)], env=dict(os.environ, PYTHONPATH=ROOT, PYTHONUNBUFFERED="1"), cwd="/tmp", stdout=fh,
                                 stderr=subprocess.STDOUT)
     try:
