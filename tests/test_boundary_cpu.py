@@ -381,3 +381,69 @@ def test_extra_cstrs_tuples_are_mapped_to_stage_rows_or_refused_by_name():
     G3[0, ucol(0, 0)] = 1.0  # a row on the shared control of a multi-particle problem
     with pytest.raises(NotImplementedError, match="shared"):
         from_extra_cstrs([(1, [], 0, G3, np.zeros((1, 0)), np.ones(1), np.zeros(nz), np.zeros(0))], M, N, n, m, Nc)
+
+
+def test_batched_result_records_follow_the_reference_format(monkeypatch):
+    """batch.solve_same_shape (host logic, a stand-in for the device handle): one (X, U, data) per problem with X including x0,
+    `data["hist"]` one dict per SCP iteration of THAT problem with the reference's keys (scp_mpc.py:409-417), per-problem
+    device counters, (None, None, None) for a problem the device reports as failed, and the single-particle shapes."""
+    from pmpc_b200 import batch
+
+    its = np.array([3, 5, 2])
+    seen = {}
+
+    class Handle:
+        def __init__(self, M, N, n, m, Nc, B=1, device=-1):
+            self.B, self.M, self.N, self.n, self.m, self.Nc = B, M, N, n, m, Nc
+
+        def set_settings(self, **kw):
+            seen["settings"] = kw
+
+        def set_problem(self, x0, Q, R, *rest):
+            seen["x0"], seen["Q"] = np.array(x0), np.array(Q)
+
+        def set_warm_start(self, Xp, Up):
+            seen["warm"] = (Xp, Up)
+
+        def set_ltv(self, A, B, c):
+            seen["ltv"] = (A.shape, B.shape, c)
+
+        def scp_solve(self, max_it, res_tol):
+            seen["stop"] = (max_it, res_tol)
+
+        def solution(self):
+            X = np.arange(self.B * self.M * self.N * self.n, dtype=float).reshape(self.B, self.M, self.N, self.n)
+            return X, -np.ones((self.B, self.M, self.N, self.m))
+
+        def info(self):
+            return dict(status=np.array([0, 0, 1]), scp_iters=its, factorizations=np.array([7, 8, 9]))
+
+        def hist(self, k):
+            assert k == 5
+            t = np.arange(5)[:, None] + 10.0 * np.arange(3)[None, :]
+            return dict(obj=t, resid=-t, admm_iters=(2 * t).astype(np.int64), kkt=t)
+
+    monkeypatch.setattr(batch, "DeviceSolver", Handle)
+    N, n, m = 4, 3, 2
+    for M in (None, 2):
+        lead = () if M is None else (M,)
+        probs = [dict(f_fx_fu_fn=pmpc_b200.LTI(np.eye(n), np.ones((n, m))), Q=np.tile(np.eye(n), lead + (N, 1, 1)),
+                      R=np.tile(np.eye(m), lead + (N, 1, 1)), x0=np.full(lead + (n,), 100.0 + b), reg_x=2.0, reg_u=0.5, max_it=9,
+                      res_tol=1e-3, solver_settings=dict(Nc=1, solver="osqp")) for b in range(3)]
+        out, ds = batch.solve_same_shape(probs)
+        assert isinstance(ds, Handle) and ds.B == 3 and seen["stop"] == (9, 1e-3) and seen["warm"] == (None, None)
+        assert out[2] == (None, None, None)
+        for b in range(2):
+            X, U, data = out[b]
+            assert X.shape == lead + (N + 1, n) and U.shape == lead + (N, m)
+            assert np.all(X[..., 0, :] == 100.0 + b) and np.all(U == -1.0)
+            full = np.arange(3 * (M or 1) * N * n, dtype=float).reshape(3, M or 1, N, n)[b]
+            assert np.array_equal(X[..., 1:, :], full if M else full[0])
+            assert [h["it"] for h in data["hist"]] == list(range(1, its[b] + 1))
+            assert [h["obj"] for h in data["hist"]] == [i + 10.0 * b for i in range(its[b])]
+            assert [h["resid"] for h in data["hist"]] == [-(i + 10.0 * b) for i in range(its[b])]
+            assert all(set(h) == {"it", "elaps", "obj", "resid", "reg_x", "reg_u"} and (h["reg_x"], h["reg_u"]) == (2.0, 0.5)
+                       for h in data["hist"])
+            assert [s["admm_iters"] for s in data["solver_data"]] == [int(2 * (i + 10 * b)) for i in range(its[b])]
+            assert len(data["t_aff_solve"]) == its[b] and data["device"] == dict(status=0, scp_iters=int(its[b]), factorizations=7 + b)
+            assert all(type(h["obj"]) is float and type(h["it"]) is int for h in data["hist"])
